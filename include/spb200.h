@@ -1,0 +1,197 @@
+/*
+ * spb200.h -- C ABI of libspb200.so: the B200-native (sm_100a) batched log-likelihood hot path of
+ * rodluger/starry_process, for ydeg = 15 (N = 256 spherical-harmonic coefficients), fp64.
+ *
+ * This is the drop-in boundary.  Every entry point replaces one (or a fused group) of the
+ * reference's Theano ops / Python glue on the lnlike path; the reference interface each one
+ * replaces is cited as file:line under starry_process/.  INTEGRATION.md shows the ctypes binding.
+ *
+ * Conventions
+ *   - all pointers are DEVICE pointers unless the name ends in _host; all arrays are C-contiguous
+ *     row-major float64 (as the reference enforces, ops/include/theano_helpers.h:55-63);
+ *   - the caller owns all memory (outputs and workspaces); workspace sizes come from the
+ *     *_workspace_bytes functions;
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*; NULL = default
+ *     stream), re-entrant across streams/devices, and performs no host synchronisation;
+ *   - return value: 0 on success, non-zero on a usage / CUDA error (message: spb_last_error());
+ *   - per-batch-element numerical failures (non positive-definite K, normalised process outside
+ *     its validity range) never fail the call: they set info[b] != 0 and lnlike[b] = -inf, the
+ *     batched analogue of the reference's NaN -> -inf convention (math.py:82-91, sp.py:1178-1188);
+ *   - Ylm index n = l^2 + l + m; angles in radians at this level (the Python surface takes degrees).
+ */
+#ifndef SPB200_H
+#define SPB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SPB_YDEG 15
+#define SPB_N 256      /* (ydeg+1)^2,                         ops/include/constants.h:27 */
+#define SPB_NWIG 5456  /* packed Wigner matrix size,          ops/include/constants.h:33-34 */
+#define SPB_NEIG 31    /* 2*ydeg+1, rank of the Wigner integrals, integrals.py:112-114 */
+
+typedef struct spb_context spb_context;
+
+/* info[] bits */
+#define SPB_INFO_NOT_PD 1       /* Cholesky met a non-positive pivot (math.py:82-91) */
+#define SPB_INFO_Z_RANGE 2      /* normalised process: z > normalization_zmax (sp.py:1178-1183) */
+#define SPB_INFO_BOUNDS 4       /* hyperparameter outside CheckBoundsOp range (ops/exceptions.py:30-48) */
+#define SPB_INFO_EIG_NOCONV 8   /* latitude eigen-solve did not converge (eigh.py:12-16 -> NaN) */
+
+const char *spb_last_error(void);
+int spb_version(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Context: holds the hyperparameter-independent constant tables in device memory.
+ *
+ * `tables_host` is a packed host blob produced by starry_process_b200/_tables.py (the host-side
+ * mirror of the reference's graph-build-time NumPy precomputations: size.py:10-43 Spot operator,
+ * wigner.py:295-372 polynomial Wigner tensors, longitude.py:9-49 + integrals.py:116-124 longitude
+ * tensors, flux.py:107-179 inclination-marginalisation integrals).  Layout: spb_tables.h.
+ * ------------------------------------------------------------------------------------------- */
+int spb_create(int device, const double *tables_host, size_t tables_count, spb_context **out);
+void spb_destroy(spb_context *ctx);
+int spb_device(const spb_context *ctx);
+
+/* ---------------------------------------------------------------------------------------------
+ * (a1) gauss2beta -- latitude.py:14-77.  mu, sigma in DEGREES (as the reference takes them).
+ * ------------------------------------------------------------------------------------------- */
+int spb_gauss2beta(spb_context *ctx, int B, const double *mu_deg, const double *sigma_deg,
+                   double *a, double *b, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * (a2-a9) Ylm moment integrals: size -> latitude -> longitude -> contrast.
+ * Replaces SizeIntegral/LatitudeIntegral/LongitudeIntegral/ContrastIntegral
+ * (size.py:93-115, latitude.py:171-212 + ops/latitude/latitude.cc:19-81 + ops/include/latitude.h:22-173
+ *  + special.h:173-232, integrals.py:116-151, math.py:121-139 + ops/eigh/eigh.py:11-20,
+ *  longitude.py:9-49, contrast.py:9-33).
+ *   r_deg, a, b, c, n : (B) hyperparameters (r in degrees; a, b the Beta shape parameters)
+ *   mean_ylm          : (B, 256)       out
+ *   cov_ylm           : (B, 256, 256)  out
+ *   info              : (B)            out (bit mask above)
+ * ------------------------------------------------------------------------------------------- */
+size_t spb_ylm_moments_workspace_bytes(const spb_context *ctx, int B);
+int spb_ylm_moments(spb_context *ctx, int B, const double *r_deg, const double *a, const double *b,
+                    const double *c, const double *n, double *mean_ylm, double *cov_ylm,
+                    int32_t *info, void *workspace, size_t workspace_bytes, void *stream);
+
+/* Cholesky factor of cov_ylm and prior draws -- sp.py:265-271, 489-509.
+ *   L_ylm : (B,256,256) out, lower triangle (upper zeroed);  unit_normals: (B, nsamples, 256)
+ *   y     : (B, nsamples, 256) out = mean + L u                                              */
+int spb_cho_cov_ylm(spb_context *ctx, int B, const double *cov_ylm, double *L_ylm, int32_t *info,
+                    void *stream);
+int spb_sample_ylm(spb_context *ctx, int B, int nsamples, const double *mean_ylm,
+                   const double *L_ylm, const double *unit_normals, double *y, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * (a13) flux operator rTA1 / rTA1L(u) -- ops/flux/rTA1.cc:7-30, rTA1L.cc:22-60,
+ * ops/include/flux.h:302-309, 501-523.  u: (nu, 2) quadratic limb darkening; out: (nu, 256).
+ * ------------------------------------------------------------------------------------------- */
+int spb_flux_operator(spb_context *ctx, int nu, const double *u, double *rTA1, void *stream);
+
+/* (a10) real Wigner x-rotation matrices, packed -- ops/wigner/Rx.cc:10-49, wigner.h:37-284.
+ *   theta: (nang) radians; Rx: (nang, 5456)                                                   */
+int spb_Rx(spb_context *ctx, int nang, const double *theta, double *Rx, void *stream);
+
+/* (a11) tensordotRz -- ops/wigner/tensordotRz.cc:10-56, wigner.h:290-339.
+ *   M: (K,256), theta: (K) -> f: (K,256)                                                      */
+int spb_tensordotRz(spb_context *ctx, int K, const double *M, const double *theta, double *f,
+                    void *stream);
+
+/* (a12) design matrix A(t; i, p, u) -- flux.py:88-105, 278-281, 345-350.
+ *   t: (nt); inc_rad: (I); period: (I) or NULL (=> 1.0); rTA1: (I,256) or (1,256) broadcast
+ *   (rTA1_stride = 256 or 0);  A: (I, nt, 256)                                                */
+int spb_design_matrix(spb_context *ctx, int I, int nt, const double *t, const double *inc_rad,
+                      const double *period, const double *rTA1, int rTA1_stride, double *A,
+                      void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * (a14-a18) flux-space GP mean and covariance.
+ *
+ * Marginalised over inclination -- flux.py:55-62, 181-231, 256-276, 295-333 and
+ * ops/wigner/special_tensordotRz.cc:10-65 (wigner.h:410-459):
+ *   mean_ylm (B,256), cov_ylm (B,256,256), rTA1 (256) [shared], t (nt), period p, covpts
+ *   -> gp_mean (B) (the scalar flux mean), kernel coefficient table coef (B, 4, covpts+1),
+ *      var (B) (the nt == 1 variance).  The dense (nt,nt) covariance is then either materialised
+ *      by spb_kernel_matrix or generated on the fly inside spb_lnlike_marginal.
+ *
+ * Conditional on inclination -- flux.py:335-343:
+ *   K[b] = A cov_ylm[b] A^T, gp_mean[b] = (A mean_ylm[b])[0];  A: (nt,256) shared by the batch.
+ * ------------------------------------------------------------------------------------------- */
+size_t spb_flux_marginal_workspace_bytes(const spb_context *ctx, int B);
+int spb_flux_marginal(spb_context *ctx, int B, const double *mean_ylm, const double *cov_ylm,
+                      const double *rTA1, int covpts, double *gp_mean, double *var, double *coef,
+                      void *workspace, size_t workspace_bytes, void *stream);
+
+size_t spb_flux_conditional_workspace_bytes(const spb_context *ctx, int B, int nt);
+int spb_flux_conditional(spb_context *ctx, int B, int nt, const double *A, const double *mean_ylm,
+                         const double *cov_ylm, double *gp_mean, double *K, int ldk,
+                         void *workspace, size_t workspace_bytes, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * (a17, a19, a21) assemble the GP covariance that is factorised:
+ *   marginal:  K_ij = cubic(|theta_i - theta_j|) from coef            (flux.py:256-276)
+ *   normalised (normalized != 0): K <- (alpha/mu^2) K + z((alpha+beta) p p^T - alpha q q^T),
+ *              mu = 1 + gp_mean, z = mean(K)/mu^2                      (sp.py:705-727, norm.py:26-44)
+ *   K += data_cov (scalar | per-point vector | full matrix) + baseline_var (scalar | matrix)
+ *                                                                      (sp.py:1135-1151)
+ * data_kind / base_kind: 0 = scalar (pointer to 1 or B values, stride given), 1 = (nt) vector,
+ * 2 = (nt,nt) matrix; strides are in elements between batch entries (0 = shared).
+ *   z_out: (B) the normalisation series parameter (0 when not normalised).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  int normalized;            /* sp.py:699-701 */
+  int normalization_order;   /* defaults.py:19 (20) */
+  double normalization_zmax; /* defaults.py:20 (0.023) */
+  int data_kind;
+  const double *data_cov;
+  long long data_stride;
+  int base_kind;
+  const double *baseline_var;
+  long long base_stride;
+} spb_noise_model;
+
+size_t spb_assemble_workspace_bytes(const spb_context *ctx, int B, int nt);
+int spb_assemble_marginal(spb_context *ctx, int B, int nt, const double *t, double period, int covpts,
+                          const double *coef, const double *var, const double *gp_mean,
+                          const spb_noise_model *noise, double *K, int ldk, double *z_out,
+                          int32_t *info, void *workspace, size_t workspace_bytes, void *stream);
+int spb_assemble_conditional(spb_context *ctx, int B, int nt, const double *gp_mean,
+                             const spb_noise_model *noise, double *K, int ldk, double *z_out,
+                             int32_t *info, void *workspace, size_t workspace_bytes, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * (a20, a21) batched Cholesky + triangular solve + log-determinant -> log-likelihood.
+ * Replaces cho_factor / cho_solve (math.py:75-100 -> LAPACK dpotrf/dtrtrs) and the lnlike
+ * reduction of sp.py:1154-1188.
+ *   K      : (B, nt, ldk) in: symmetric (lower triangle read); out: L in the lower triangle
+ *   resid  : (B, M, ldr)  in: residual light curves r = flux - mean, one per ROW;
+ *                         out: y = L^{-1} r   (resid_stride elements between batch entries)
+ *   lnlike : (B) out = -1/2 sum y^2 - M sum log L_ii - 1/2 nt M log(2 pi); -inf when info[b] != 0
+ *   quad   : (B, M) out or NULL: per-light-curve r^T K^{-1} r;  logdet: (B) or NULL: sum log L_ii
+ * ldk and ldr must be even and the base pointers 16-byte aligned.
+ * ------------------------------------------------------------------------------------------- */
+int spb_cholesky_lnlike(spb_context *ctx, int B, int nt, double *K, int ldk, long long K_stride,
+                        int M, double *resid, int ldr, long long resid_stride, double *lnlike,
+                        double *quad, double *logdet, int32_t *info, void *stream);
+
+/* Forward solve y = L^{-1} r for many right-hand sides against ONE factor, the RHS rows split
+ * across the whole GPU (config "1 factorisation + 1024 RHS").  quad: (M) out.               */
+int spb_cholesky_solve_rows(spb_context *ctx, int nt, const double *L, int ldk, int M, double *resid,
+                            int ldr, double *quad, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Measurement helpers (not part of the reference interface): FP64 tensor-pipe (DMMA) peak
+ * micro-benchmark used as the roofline denominator; returns achieved TFLOP/s via *tflops_host.
+ * ------------------------------------------------------------------------------------------- */
+int spb_dmma_peak(spb_context *ctx, int iters, double *tflops_host, double *ms_host);
+int spb_launch_count(const spb_context *ctx, long long *count_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPB200_H */

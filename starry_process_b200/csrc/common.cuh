@@ -1,0 +1,77 @@
+// Shared device/host helpers for libspb200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+#include "../../include/spb200.h"
+
+#define SPB_LMAX 15
+#define SPB_NSM_DEFAULT 148
+
+struct spb_context {
+  int device;
+  int num_sms;
+  double *d_tables;       // device copy of the packed constant blob
+  size_t tables_count;
+  long long launches;     // number of kernels launched through this context
+  // offsets (in doubles) into d_tables, see spb_tables.h
+  const double *tab(size_t off) const { return d_tables + off; }
+};
+
+void spb_set_error(const std::string &msg);
+
+#define SPB_CHECK_CUDA(expr)                                                          \
+  do {                                                                                \
+    cudaError_t _e = (expr);                                                          \
+    if (_e != cudaSuccess) {                                                          \
+      spb_set_error(std::string(#expr) + ": " + cudaGetErrorString(_e));              \
+      return 1;                                                                       \
+    }                                                                                 \
+  } while (0)
+
+#define SPB_REQUIRE(cond, msg)                                                        \
+  do {                                                                                \
+    if (!(cond)) {                                                                    \
+      spb_set_error(std::string("spb200: ") + msg);                                   \
+      return 2;                                                                       \
+    }                                                                                 \
+  } while (0)
+
+#define SPB_LAUNCH_CHECK(ctx)                                                         \
+  do {                                                                                \
+    (ctx)->launches += 1;                                                             \
+    cudaError_t _e = cudaGetLastError();                                              \
+    if (_e != cudaSuccess) {                                                          \
+      spb_set_error(std::string("kernel launch: ") + cudaGetErrorString(_e));         \
+      return 1;                                                                       \
+    }                                                                                 \
+  } while (0)
+
+// ---- FP64 tensor-core MMA (DMMA): D(8x8) += A(8x4, row) * B(4x8, col) ------------------------
+// fragment layout (PTX ISA, mma.m8n8k4 .f64): g = lane>>2, tg = lane&3
+//   a = A[g][tg]      b = B[tg][g]      d0,d1 = D[g][2*tg + {0,1}]
+__device__ __forceinline__ void dmma_m8n8k4(double &d0, double &d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(d0), "+d"(d1)
+               : "d"(a), "d"(b));
+}
+
+// ---- cp.async (LDGSTS) 16-byte copy with zero-fill when src_bytes == 0 ------------------------
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc, int src_bytes) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gsrc),
+               "r"(src_bytes));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}

@@ -1,0 +1,603 @@
+// Batched dense Cholesky + forward solve + log-determinant -> log-likelihood, FP64 tensor cores.
+//
+// Replaces, for a batch of B independent GP covariances, the reference's
+//   cho_factor  -> scipy.linalg.cholesky  (LAPACK dpotrf)        math.py:75-94
+//   cho_solve   -> 2 x solve_triangular   (LAPACK dtrtrs)        math.py:20-38, 97-100
+//   lnlike = -1/2 r^T K^-1 r - M sum(log diag L) - 1/2 K M log 2pi   sp.py:1154-1188
+//
+// Design (B200-first, not a LAPACK transliteration)
+//   * one CTA (256 threads, 8 warps) owns one matrix at a time; grid = min(B, 2 x #SM) persistent
+//     CTAs, 2 CTAs resident per SM so one CTA's latency-bound diagonal-block work overlaps the
+//     other's tensor-pipe work;
+//   * LEFT-looking blocked factorisation, panel width NB = 64: every block column is read once
+//     as the C operand and the already-factored part of L is streamed as A/B operands, so HBM/L2
+//     traffic is ~n^3/(6 NB) reads + one write of L (a right-looking update would re-write the
+//     trailing matrix once per panel);
+//   * the panel update  P = K[:, j] - L[:, :j] L[j, :j]^T  runs on mma.sync.m8n8k4.f64 (DMMA) from
+//     a cp.async double-buffered shared-memory pipeline; each warp owns 16 full rows x 64 columns
+//     of the panel in registers;
+//   * the triangular solve  X = P L_jj^-T  is done IN REGISTERS on the tensor pipe as an 8x8-blocked
+//     forward substitution (accumulator fragments are re-shaped into A fragments with warp
+//     shuffles), so the panel never round-trips through shared memory;
+//   * the residual light curves r are appended as extra ROWS of the matrix ("augmented" Cholesky):
+//     the same panel loop then produces y = L^-1 r, so lnlike needs no back substitution:
+//         r^T K^-1 r = |y|^2;
+//   * only the 64x64 diagonal block is factorised with scalar FP64 (shared memory, one barrier per
+//     column, column scaling deferred).
+//
+// Algorithmic flops per matrix: nt^3/3 (factor) + nt^2 M (forward solve); see DESIGN.md.
+#include "common.cuh"
+
+namespace {
+
+constexpr int NB = 64;         // panel width
+constexpr int TM = 128;        // rows per tile (8 warps x 16 rows)
+constexpr int KC = 16;         // k-chunk per pipeline stage
+constexpr int KS = KC + 4;     // smem row stride (doubles): 20 -> conflict-free 8x4 fragment loads
+constexpr int LS = NB + 4;     // smem stride of the diagonal block: 68
+constexpr int DS = 12;         // smem stride of the 8x8 diagonal-inverse blocks
+constexpr int STAGES = 2;
+constexpr int NTHREADS = 256;
+
+enum { KIND_NONE = 0, KIND_DIAG = 1, KIND_PAD = 2, KIND_BELOW = 3, KIND_RHS = 4 };
+enum { MODE_FACTOR = 1, MODE_SOLVE = 0 };
+
+struct PotrfParams {
+  double *K;
+  int n, ld;
+  long long strideK;
+  double *R;
+  int M, ldr;
+  long long strideR;
+  double *lnlike, *quad, *logdet;
+  int32_t *info;
+  int B;
+  int mode;
+  int rows_per_cta;  // MODE_SOLVE: RHS rows per work item
+};
+
+struct RowMap {
+  double *Kb, *Rb;
+  int n, M, ld, ldr, c0, nbelow, mode, rb, nrhs;
+  __device__ __forceinline__ double *row(int v, int &kind) const {
+    if (mode == MODE_FACTOR) {
+      if (v < NB) {
+        int r = c0 + v;
+        if (r < n) {
+          kind = KIND_DIAG;
+          return Kb + (size_t)r * ld;
+        }
+        kind = KIND_PAD;
+        return nullptr;
+      }
+      int w = v - NB;
+      if (w < nbelow) {
+        kind = KIND_BELOW;
+        return Kb + (size_t)(c0 + NB + w) * ld;
+      }
+      w -= nbelow;
+      if (w < M) {
+        kind = KIND_RHS;
+        return Rb + (size_t)w * ldr;
+      }
+      kind = KIND_NONE;
+      return nullptr;
+    }
+    if (v < nrhs) {
+      kind = KIND_RHS;
+      return Rb + (size_t)(rb + v) * ldr;
+    }
+    kind = KIND_NONE;
+    return nullptr;
+  }
+};
+
+struct Smem {
+  double As[STAGES][TM][KS];
+  double Bs[STAGES][NB][KS];
+  double Ld[NB][LS];   // diagonal block L_jj (lower), valid after potf2
+  double Dv[NB][DS];   // 8 inverses of the 8x8 diagonal blocks of L_jj: Dv[8*nb + r][c]
+  double red[NTHREADS / 32];
+  int bad;
+};
+
+// ------------------------------------------------------------------------------------------
+// acc(16 rows x 64 cols per warp) = sum_k A[v0 + rows][k] * L[c0 + cols][k],  k in [0, c0)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void gemm_tile(Smem &sm, const RowMap &rm, int v0, int c0,
+                                          double (&acc)[2][8][2]) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, tg = lane & 3;
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
+  const int nchunks = c0 / KC;
+  if (nchunks == 0) return;
+
+  // this thread's cp.async assignments: A: 4 x 16B, B: 2 x 16B per chunk
+  const int seg = tid & 7;
+  const double *arow[4];
+  int abytes[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int kind;
+    double *p = rm.row(v0 + (tid >> 3) + 32 * i, kind);
+    arow[i] = p ? p : rm.Kb;
+    abytes[i] = p ? 16 : 0;
+  }
+  const double *brow[2];
+  int bbytes[2];
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    int r = c0 + (tid >> 3) + 32 * i;
+    brow[i] = (r < rm.n) ? rm.Kb + (size_t)r * rm.ld : rm.Kb;
+    bbytes[i] = (r < rm.n) ? 16 : 0;
+  }
+  auto load_chunk = [&](int ch, int st) {
+    const int k0 = ch * KC + seg * 2;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      cp_async16(&sm.As[st][(tid >> 3) + 32 * i][seg * 2], arow[i] + k0, abytes[i]);
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+      cp_async16(&sm.Bs[st][(tid >> 3) + 32 * i][seg * 2], brow[i] + k0, bbytes[i]);
+    cp_async_commit();
+  };
+
+  load_chunk(0, 0);
+  for (int ch = 0; ch < nchunks; ++ch) {
+    const int st = ch & 1;
+    cp_async_wait<0>();
+    __syncthreads();  // chunk ch landed for everyone; everyone finished reading stage st^1
+    if (ch + 1 < nchunks) load_chunk(ch + 1, st ^ 1);
+#pragma unroll
+    for (int kk = 0; kk < KC / 4; ++kk) {
+      double a[2], b[8];
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) a[mt] = sm.As[st][warp * 16 + mt * 8 + g][kk * 4 + tg];
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) b[nt] = sm.Bs[st][nt * 8 + g][kk * 4 + tg];
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) dmma_m8n8k4(acc[mt][nt][0], acc[mt][nt][1], a[mt], b[nt]);
+    }
+  }
+  __syncthreads();  // all reads of the stage buffers done before the next tile refills them
+}
+
+// P = Kval - acc for the two rows this thread owns in m-tile mt; returns through acc.
+__device__ __forceinline__ void load_subtract(const RowMap &rm, int v, int c0, int g_unused,
+                                              int tg, double (&accrow)[8][2]) {
+  int kind;
+  double *p = rm.row(v, kind);
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int col = nt * 8 + 2 * tg + e;
+      const int gc = c0 + col;
+      double kv = 0.0;
+      if (kind == KIND_PAD) {
+        kv = (col == v) ? 1.0 : 0.0;
+      } else if (kind != KIND_NONE) {
+        if (gc < rm.n) {
+          // the strictly upper part of the diagonal block is never used; skip the load
+          if (!(kind == KIND_DIAG && col > v)) kv = p[gc];
+        }
+      }
+      accrow[nt][e] = kv - accrow[nt][e];
+    }
+  }
+}
+
+// Accumulator fragment (8x8, C layout) -> A fragment of its k-block q (columns 4q..4q+3).
+__device__ __forceinline__ double c_to_a(double d0, double d1, int q, int lane) {
+  const int tg = lane & 3;
+  const int src = (lane & ~3) | (2 * q + (tg >> 1));
+  const double v0 = __shfl_sync(0xffffffffu, d0, src);
+  const double v1 = __shfl_sync(0xffffffffu, d1, src);
+  return (tg & 1) ? v1 : v0;
+}
+
+// In-register TRSM on the tensor pipe: X = P L_jj^-T for one 8-row m-tile (acc rows), 8x8-blocked
+// forward substitution.  On exit accrow holds X.
+__device__ __forceinline__ void trsm_mtile(const Smem &sm, double (&accrow)[8][2], int lane) {
+  const int g = lane >> 2, tg = lane & 3;
+  double nx[16];  // -X as A fragments, k-block kb = columns 4kb..4kb+3
+#pragma unroll
+  for (int nb = 0; nb < 8; ++nb) {
+    double s0 = accrow[nb][0], s1 = accrow[nb][1];
+#pragma unroll
+    for (int kb = 0; kb < 2 * nb; ++kb) {
+      const double b = sm.Ld[nb * 8 + g][kb * 4 + tg];
+      dmma_m8n8k4(s0, s1, nx[kb], b);
+    }
+    // X_nb = S * Dinv_nb^T
+    const double a0 = c_to_a(s0, s1, 0, lane);
+    const double a1 = c_to_a(s0, s1, 1, lane);
+    double x0 = 0.0, x1 = 0.0;
+    dmma_m8n8k4(x0, x1, a0, sm.Dv[nb * 8 + g][tg]);
+    dmma_m8n8k4(x0, x1, a1, sm.Dv[nb * 8 + g][4 + tg]);
+    accrow[nb][0] = x0;
+    accrow[nb][1] = x1;
+    nx[2 * nb] = -c_to_a(x0, x1, 0, lane);
+    nx[2 * nb + 1] = -c_to_a(x0, x1, 1, lane);
+  }
+}
+
+// Store X rows (below-diagonal rows of L, or y rows of the RHS) and accumulate |y|^2.
+// Called by all 32 lanes of a warp (the shuffles are unconditional).
+__device__ __forceinline__ void store_rows(const RowMap &rm, int v, int c0, int tg,
+                                           const double (&accrow)[8][2], double &quad_part,
+                                           double *quad_out) {
+  int kind;
+  double *p = rm.row(v, kind);
+  const bool live = (kind == KIND_BELOW || kind == KIND_RHS);
+  double q = 0.0;
+  if (live) {
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int gc = c0 + nt * 8 + 2 * tg + e;
+        if (gc < rm.n) {
+          p[gc] = accrow[nt][e];
+          q += accrow[nt][e] * accrow[nt][e];
+        }
+      }
+    }
+  }
+  if (kind != KIND_RHS) q = 0.0;
+  quad_part += q;
+  if (quad_out) {  // uniform across the grid
+    // the 4 lanes of a quad share the row: reduce before the atomic
+    q += __shfl_xor_sync(0xffffffffu, q, 1);
+    q += __shfl_xor_sync(0xffffffffu, q, 2);
+    if (kind == KIND_RHS && tg == 0) {
+      const int m = (rm.mode == MODE_FACTOR) ? (v - NB - rm.nbelow) : (rm.rb + v);
+      atomicAdd(quad_out + m, q);
+    }
+  }
+}
+
+// 64x64 Cholesky of sm.Ld (lower triangle), scalar FP64, one barrier per column; column scaling is
+// deferred to a final pass.  Also produces the 8 inverses of the 8x8 diagonal blocks (sm.Dv) and
+// returns this thread's share of sum(log L_ii) over the valid columns.
+__device__ __forceinline__ double potf2_block(Smem &sm, int nvalid) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int c = 0; c < NB - 1; ++c) {
+    __syncthreads();
+    const double d = sm.Ld[c][c];
+    const double invd = 1.0 / d;
+    // rows c+1+warp, +8, ...; lanes run along columns j in (c, i]
+    for (int i = c + 1 + warp; i < NB; i += 8) {
+      const double lic = sm.Ld[i][c] * invd;
+      for (int j = c + 1 + lane; j <= i; j += 32) sm.Ld[i][j] -= lic * sm.Ld[j][c];
+    }
+  }
+  __syncthreads();
+  // pivots
+  double logpart = 0.0;
+  double dj = 1.0;
+  if (tid < NB) {
+    dj = sm.Ld[tid][tid];
+    if (!(dj > 0.0)) {  // also catches NaN
+      sm.bad = 1;
+      dj = 1.0;
+    }
+    if (tid < nvalid) logpart = 0.5 * log(dj);
+  }
+  __syncthreads();
+  // scale columns: L[i][j] = v[i][j] / sqrt(d_j); zero the strict upper triangle
+  for (int idx = tid; idx < NB * NB; idx += NTHREADS) {
+    const int i = idx >> 6, j = idx & 63;
+    double v = 0.0;
+    if (j <= i) {
+      double djj = sm.Ld[j][j];
+      if (!(djj > 0.0)) djj = 1.0;
+      v = (i == j) ? sqrt(djj) : sm.Ld[i][j] / sqrt(djj);
+    }
+    if (j != i) {
+      // diagonal entries are read by other threads in this pass: write them afterwards
+      if (j < i) sm.Ld[i][j] = v;
+      else sm.Ld[i][j] = 0.0;
+    }
+  }
+  __syncthreads();
+  if (tid < NB) {
+    double djj = sm.Ld[tid][tid];
+    if (!(djj > 0.0)) djj = 1.0;
+    sm.Ld[tid][tid] = sqrt(djj);
+  }
+  __syncthreads();
+  // inverses of the eight 8x8 diagonal blocks: warp w, lane c < 8 -> column c of block w
+  if (lane < 8) {
+    const int o = warp * 8;
+    double x[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      double s = (i == lane) ? 1.0 : 0.0;
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        if (k < i && k >= lane) s -= sm.Ld[o + i][o + k] * x[k];
+      x[i] = (i >= lane) ? s / sm.Ld[o + i][o + i] : 0.0;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) sm.Dv[o + i][lane] = x[i];
+  }
+  __syncthreads();
+  return logpart;
+}
+
+// Inverses of the 8x8 diagonal blocks only (MODE_SOLVE: L_jj comes from global memory).
+__device__ __forceinline__ void diag_inverses(Smem &sm) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (lane < 8) {
+    const int o = warp * 8;
+    double x[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      double s = (i == lane) ? 1.0 : 0.0;
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        if (k < i && k >= lane) s -= sm.Ld[o + i][o + k] * x[k];
+      x[i] = (i >= lane) ? s / sm.Ld[o + i][o + i] : 0.0;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) sm.Dv[o + i][lane] = x[i];
+  }
+  (void)tid;
+  __syncthreads();
+}
+
+__device__ __forceinline__ double block_sum(Smem &sm, double v) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) sm.red[warp] = v;
+  __syncthreads();
+  double t = 0.0;
+#pragma unroll
+  for (int w = 0; w < NTHREADS / 32; ++w) t += sm.red[w];
+  __syncthreads();
+  return t;
+}
+
+__global__ void __launch_bounds__(NTHREADS, 2) potrf_lnlike_kernel(PotrfParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, tg = lane & 3;
+
+  int nitems;
+  if (p.mode == MODE_FACTOR) nitems = p.B;
+  else nitems = (p.M + p.rows_per_cta - 1) / p.rows_per_cta;
+
+  for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+    RowMap rm;
+    rm.n = p.n;
+    rm.ld = p.ld;
+    rm.ldr = p.ldr;
+    rm.mode = p.mode;
+    double *quad_out;
+    if (p.mode == MODE_FACTOR) {
+      rm.Kb = p.K + (size_t)item * p.strideK;
+      rm.Rb = p.R ? p.R + (size_t)item * p.strideR : nullptr;
+      rm.M = p.R ? p.M : 0;
+      rm.rb = 0;
+      rm.nrhs = rm.M;
+      quad_out = p.quad ? p.quad + (size_t)item * p.M : nullptr;
+    } else {
+      rm.Kb = p.K;
+      rm.Rb = p.R;
+      rm.M = p.M;
+      rm.rb = item * p.rows_per_cta;
+      rm.nrhs = min(p.rows_per_cta, p.M - rm.rb);
+      quad_out = p.quad;
+    }
+    if (tid == 0) sm.bad = 0;
+    if (quad_out) {
+      if (p.mode == MODE_FACTOR) {
+        for (int m = tid; m < rm.M; m += NTHREADS) quad_out[m] = 0.0;
+      } else {
+        for (int m = tid; m < rm.nrhs; m += NTHREADS) quad_out[rm.rb + m] = 0.0;
+      }
+    }
+    __syncthreads();
+
+    double logdet_part = 0.0, quad_part = 0.0;
+    double acc[2][8][2];
+
+    for (int c0 = 0; c0 < p.n; c0 += NB) {
+      rm.c0 = c0;
+      rm.nbelow = max(0, p.n - c0 - NB);
+      const int nvirt = (p.mode == MODE_FACTOR) ? NB + rm.nbelow + rm.M : rm.nrhs;
+      if (p.mode == MODE_SOLVE) {
+        // fetch L_jj (identity-padded) and invert its 8x8 diagonal blocks
+        for (int idx = tid; idx < NB * NB; idx += NTHREADS) {
+          const int i = idx >> 6, j = idx & 63;
+          double v = 0.0;
+          if (j <= i) {
+            if (c0 + i < p.n) v = rm.Kb[(size_t)(c0 + i) * p.ld + c0 + j];
+            else v = (i == j) ? 1.0 : 0.0;
+          }
+          sm.Ld[i][j] = v;
+        }
+        __syncthreads();
+        diag_inverses(sm);
+      }
+      for (int v0 = 0; v0 < nvirt; v0 += TM) {
+        // MODE_FACTOR, first tile: rows 0..63 are the diagonal block (warps 0-3), rows 64..127 the
+        // first rows below it (warps 4-7)
+        const bool diag_tile = (p.mode == MODE_FACTOR) && (v0 == 0);
+        gemm_tile(sm, rm, v0, c0, acc);
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+          load_subtract(rm, v0 + warp * 16 + mt * 8 + g, c0, g, tg, acc[mt]);
+        if (diag_tile) {
+          if (warp < 4) {
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) {
+              const int lr = warp * 16 + mt * 8 + g;
+#pragma unroll
+              for (int nt = 0; nt < 8; ++nt) {
+                sm.Ld[lr][nt * 8 + 2 * tg] = acc[mt][nt][0];
+                sm.Ld[lr][nt * 8 + 2 * tg + 1] = acc[mt][nt][1];
+              }
+            }
+          }
+          logdet_part += potf2_block(sm, min(NB, p.n - c0));
+          // write L_jj back (lower triangle, valid rows/cols only)
+          for (int idx = tid; idx < NB * NB; idx += NTHREADS) {
+            const int i = idx >> 6, j = idx & 63;
+            if (j <= i && c0 + i < p.n) rm.Kb[(size_t)(c0 + i) * p.ld + c0 + j] = sm.Ld[i][j];
+          }
+        }
+        if (!(diag_tile && warp < 4)) {
+#pragma unroll
+          for (int mt = 0; mt < 2; ++mt) {
+            trsm_mtile(sm, acc[mt], lane);
+            store_rows(rm, v0 + warp * 16 + mt * 8 + g, c0, tg, acc[mt], quad_part, quad_out);
+          }
+        }
+      }
+      __syncthreads();  // Ld/Dv are rewritten by the next panel; global writes of this panel done
+      __threadfence_block();
+    }
+
+    // ---- reductions -> lnlike
+    const double quad = block_sum(sm, quad_part);
+    const double logdet = block_sum(sm, logdet_part);
+    if (p.mode == MODE_FACTOR && tid == 0) {
+      const bool bad = sm.bad != 0;
+      double ll = -0.5 * quad - (double)rm.M * logdet -
+                  0.5 * (double)p.n * (double)rm.M * 1.8378770664093453;  // log(2 pi)
+      if (bad || ll != ll) ll = -INFINITY;
+      if (p.lnlike) p.lnlike[item] = ll;
+      if (p.logdet) p.logdet[item] = bad ? NAN : logdet;
+      if (p.info) p.info[item] = (p.info[item] & ~SPB_INFO_NOT_PD) | (bad ? SPB_INFO_NOT_PD : 0);
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// DMMA peak micro-benchmark: 8 warps x 16 independent accumulator tiles, operands in registers.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256, 2) dmma_peak_kernel(int iters, double *sink) {
+  double acc[16][2];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) acc[i][0] = acc[i][1] = 0.0;
+  double a = 1.0 + threadIdx.x * 1e-9, b = 1.0 - threadIdx.x * 1e-9;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) dmma_m8n8k4(acc[i][0], acc[i][1], a, b);
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) s += acc[i][0] + acc[i][1];
+  if (s == 123.456) sink[0] = s;
+}
+
+}  // namespace
+
+static int potrf_launch(spb_context *ctx, PotrfParams &p, void *stream) {
+  SPB_REQUIRE(p.n > 0 && p.B > 0, "cholesky: empty problem");
+  SPB_REQUIRE(p.ld >= p.n && (p.ld % 2) == 0, "cholesky: ldk must be even and >= nt");
+  SPB_REQUIRE(((uintptr_t)p.K % 16) == 0 && (p.strideK % 2) == 0,
+              "cholesky: K must be 16-byte aligned with an even batch stride");
+  if (p.R) {
+    SPB_REQUIRE(p.ldr >= p.n && (p.ldr % 2) == 0, "cholesky: ldr must be even and >= nt");
+    SPB_REQUIRE(((uintptr_t)p.R % 16) == 0 && (p.strideR % 2) == 0,
+                "cholesky: resid must be 16-byte aligned with an even batch stride");
+  }
+  SPB_CHECK_CUDA(cudaSetDevice(ctx->device));
+  const size_t smem = sizeof(Smem);
+  static bool attr_set[64] = {false};
+  if (!attr_set[ctx->device & 63]) {
+    SPB_CHECK_CUDA(cudaFuncSetAttribute(potrf_lnlike_kernel,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set[ctx->device & 63] = true;
+  }
+  int nitems = (p.mode == MODE_FACTOR) ? p.B : (p.M + p.rows_per_cta - 1) / p.rows_per_cta;
+  int grid = nitems < 2 * ctx->num_sms ? nitems : 2 * ctx->num_sms;
+  potrf_lnlike_kernel<<<grid, NTHREADS, smem, (cudaStream_t)stream>>>(p);
+  SPB_LAUNCH_CHECK(ctx);
+  return 0;
+}
+
+extern "C" int spb_cholesky_lnlike(spb_context *ctx, int B, int nt, double *K, int ldk,
+                                   long long K_stride, int M, double *resid, int ldr,
+                                   long long resid_stride, double *lnlike, double *quad,
+                                   double *logdet, int32_t *info, void *stream) {
+  SPB_REQUIRE(ctx != nullptr, "null context");
+  PotrfParams p;
+  p.K = K;
+  p.n = nt;
+  p.ld = ldk;
+  p.strideK = K_stride;
+  p.R = (M > 0) ? resid : nullptr;
+  p.M = M;
+  p.ldr = ldr;
+  p.strideR = resid_stride;
+  p.lnlike = lnlike;
+  p.quad = quad;
+  p.logdet = logdet;
+  p.info = info;
+  p.B = B;
+  p.mode = MODE_FACTOR;
+  p.rows_per_cta = 0;
+  return potrf_launch(ctx, p, stream);
+}
+
+extern "C" int spb_cholesky_solve_rows(spb_context *ctx, int nt, const double *L, int ldk, int M,
+                                       double *resid, int ldr, double *quad, void *stream) {
+  SPB_REQUIRE(ctx != nullptr, "null context");
+  SPB_REQUIRE(M > 0 && resid != nullptr, "solve_rows: no right-hand sides");
+  PotrfParams p;
+  p.K = const_cast<double *>(L);
+  p.n = nt;
+  p.ld = ldk;
+  p.strideK = 0;
+  p.R = resid;
+  p.M = M;
+  p.ldr = ldr;
+  p.strideR = 0;
+  p.lnlike = nullptr;
+  p.quad = quad;
+  p.logdet = nullptr;
+  p.info = nullptr;
+  p.B = 1;
+  p.mode = MODE_SOLVE;
+  // spread the RHS rows over the whole GPU in multiples of 16 rows (one warp's share)
+  // one full 128-row tile per work item (a tile costs the same DMMA time however many of its
+  // rows are live, so smaller items would only replicate the streaming of L)
+  p.rows_per_cta = TM;
+  return potrf_launch(ctx, p, stream);
+}
+
+extern "C" int spb_dmma_peak(spb_context *ctx, int iters, double *tflops_host, double *ms_host) {
+  SPB_REQUIRE(ctx != nullptr, "null context");
+  SPB_CHECK_CUDA(cudaSetDevice(ctx->device));
+  double *sink = nullptr;
+  SPB_CHECK_CUDA(cudaMalloc(&sink, 8));
+  cudaEvent_t e0, e1;
+  SPB_CHECK_CUDA(cudaEventCreate(&e0));
+  SPB_CHECK_CUDA(cudaEventCreate(&e1));
+  const int grid = 2 * ctx->num_sms;
+  dmma_peak_kernel<<<grid, 256>>>(iters / 10 + 1, sink);  // warm-up
+  SPB_CHECK_CUDA(cudaEventRecord(e0));
+  dmma_peak_kernel<<<grid, 256>>>(iters, sink);
+  SPB_CHECK_CUDA(cudaEventRecord(e1));
+  SPB_CHECK_CUDA(cudaEventSynchronize(e1));
+  ctx->launches += 2;
+  float ms = 0.f;
+  SPB_CHECK_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+  const double flops = (double)grid * 8.0 * 16.0 * (double)iters * 512.0;
+  if (tflops_host) *tflops_host = flops / (ms * 1e-3) / 1e12;
+  if (ms_host) *ms_host = ms;
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(sink);
+  return 0;
+}
