@@ -105,9 +105,10 @@ int spb_tensordotRz(spb_context *ctx, int K, const double *M, const double *thet
 /* (a12) design matrix A(t; i, p, u) -- flux.py:88-105, 278-281, 345-350.
  *   t: (nt); inc_rad: (I); period: (I) or NULL (=> 1.0); rTA1: (I,256) or (1,256) broadcast
  *   (rTA1_stride = 256 or 0);  A: (I, nt, 256)                                                */
+size_t spb_design_matrix_workspace_bytes(const spb_context *ctx, int I, int nt);
 int spb_design_matrix(spb_context *ctx, int I, int nt, const double *t, const double *inc_rad,
                       const double *period, const double *rTA1, int rTA1_stride, double *A,
-                      void *stream);
+                      void *workspace, size_t workspace_bytes, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
  * (a14-a18) flux-space GP mean and covariance.
@@ -120,7 +121,8 @@ int spb_design_matrix(spb_context *ctx, int I, int nt, const double *t, const do
  *      by spb_kernel_matrix or generated on the fly inside spb_lnlike_marginal.
  *
  * Conditional on inclination -- flux.py:335-343:
- *   K[b] = A cov_ylm[b] A^T, gp_mean[b] = (A mean_ylm[b])[0];  A: (nt,256) shared by the batch.
+ *   K[b] = A cov_ylm[b] A^T, gp_mean[b] = (A mean_ylm[b])[0];  A: (nt,256) shared by the batch
+ *   (A_stride = 0) or one design matrix per element (A_stride = nt*256, e.g. one inclination each).
  * ------------------------------------------------------------------------------------------- */
 size_t spb_flux_marginal_workspace_bytes(const spb_context *ctx, int B);
 int spb_flux_marginal(spb_context *ctx, int B, const double *mean_ylm, const double *cov_ylm,
@@ -128,9 +130,9 @@ int spb_flux_marginal(spb_context *ctx, int B, const double *mean_ylm, const dou
                       void *workspace, size_t workspace_bytes, void *stream);
 
 size_t spb_flux_conditional_workspace_bytes(const spb_context *ctx, int B, int nt);
-int spb_flux_conditional(spb_context *ctx, int B, int nt, const double *A, const double *mean_ylm,
-                         const double *cov_ylm, double *gp_mean, double *K, int ldk,
-                         void *workspace, size_t workspace_bytes, void *stream);
+int spb_flux_conditional(spb_context *ctx, int B, int nt, const double *A, long long A_stride,
+                         const double *mean_ylm, const double *cov_ylm, double *gp_mean, double *K,
+                         int ldk, void *workspace, size_t workspace_bytes, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
  * (a17, a19, a21) assemble the GP covariance that is factorised:

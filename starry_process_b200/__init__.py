@@ -1,0 +1,11 @@
+"""starry_process_b200 -- B200-native (sm_100a) batched log-likelihood path of starry_process.
+
+Public surface mirrors the reference for this path: ``StarryProcess``, ``gauss2beta``,
+``beta2gauss``.  Importing the package does not touch the GPU; constructing a ``StarryProcess``
+loads ``libspb200.so`` (build it with ``python -m starry_process_b200.build``) and fails loudly if it
+or a CUDA device is missing.
+"""
+from .sp import StarryProcess, beta2gauss, defaults, gauss2beta, get_context  # noqa: F401
+from .distributed import gather_lnlike, shard_range  # noqa: F401
+
+__version__ = "0.1.0"

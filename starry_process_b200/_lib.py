@@ -39,11 +39,12 @@ PROTOTYPES = {
     "spb_flux_operator": (_I, [_P, _I, _P, _P, _P]),
     "spb_Rx": (_I, [_P, _I, _P, _P, _P]),
     "spb_tensordotRz": (_I, [_P, _I, _P, _P, _P, _P]),
-    "spb_design_matrix": (_I, [_P, _I, _I, _P, _P, _P, _P, _I, _P, _P]),
+    "spb_design_matrix_workspace_bytes": (_SZ, [_P, _I, _I]),
+    "spb_design_matrix": (_I, [_P, _I, _I, _P, _P, _P, _P, _I, _P, _P, _SZ, _P]),
     "spb_flux_marginal_workspace_bytes": (_SZ, [_P, _I]),
     "spb_flux_marginal": (_I, [_P, _I, _P, _P, _P, _I, _P, _P, _P, _P, _SZ, _P]),
     "spb_flux_conditional_workspace_bytes": (_SZ, [_P, _I, _I]),
-    "spb_flux_conditional": (_I, [_P, _I, _I, _P, _P, _P, _P, _P, _I, _P, _SZ, _P]),
+    "spb_flux_conditional": (_I, [_P, _I, _I, _P, _LL, _P, _P, _P, _P, _I, _P, _SZ, _P]),
     "spb_assemble_workspace_bytes": (_SZ, [_P, _I, _I]),
     "spb_assemble_marginal": (_I, [_P, _I, _I, _P, _D, _I, _P, _P, _P, _c.POINTER(NoiseModel),
                                    _P, _I, _P, _P, _P, _SZ, _P]),

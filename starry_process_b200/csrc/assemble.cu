@@ -1,0 +1,257 @@
+// Assembly of the GP covariance that is factorised by the Cholesky kernel.
+//
+//   marginal kernel interpolation    flux.py:256-276  (cubic in the phase lag on the covpts grid)
+//   normalisation series             sp.py:705-727, ops/norm/norm.py:26-44
+//   data covariance + baseline       sp.py:1135-1151
+//
+// The dense (nt x nt) matrix is written exactly ONCE: for the normalised process the row sums that
+// the series needs are obtained by re-evaluating the (cheap) interpolant in a compute-only pass
+// instead of writing K, reading it back and rewriting it.
+#include "common.cuh"
+
+namespace {
+
+struct AsmParams {
+  int B, nt, ldk, covpts;
+  const double *t;
+  double period;
+  const double *coef;     // (B,4,covpts+1)   marginal only
+  const double *var;      // (B)
+  const double *gp_mean;  // (B)
+  spb_noise_model nm;
+  double *K;              // (B,nt,ldk)
+  double *rowq;           // (B,nt)  workspace: row sums, then q_i
+  double *scal;           // (B,4)   workspace: s1, s2, s3
+  double *z_out;
+  int32_t *info;
+  int marginal;
+};
+
+__device__ __forceinline__ double interp_cov(const double *cf, int nc, double dx, double thi,
+                                             double thj) {
+  // flux.py:262-271
+  const double x = fabs(thi - thj);
+  const int ind = (int)floor(x / dx);
+  const double xp1 = -dx + (ind + 1) * dx;
+  const double x0 = (x - xp1) / dx;
+  return cf[ind] + cf[nc + ind] * x0 + cf[2 * nc + ind] * (x0 * x0) + cf[3 * nc + ind] * (x0 * x0 * x0);
+}
+
+// theta_i = 2 pi mod(t_i / p, 1)  (flux.py:261)
+__device__ __forceinline__ double phase_of(double t, double period) {
+  const double x = t / period;
+  return 2.0 * 3.14159265358979323846 * (x - floor(x));
+}
+
+// ---- pass A (normalised only): row sums of the raw covariance -------------------------------
+__global__ void __launch_bounds__(256) rowsum_kernel(AsmParams p) {
+  extern __shared__ double sh[];  // coef (4*nc) | theta (nt)
+  const int b = blockIdx.y;
+  const int nc = p.covpts + 1;
+  double *cf = sh, *th = sh + 4 * nc;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (p.marginal) {
+    for (int k = tid; k < 4 * nc; k += 256) cf[k] = p.coef[(size_t)b * 4 * nc + k];
+    for (int k = tid; k < p.nt; k += 256) th[k] = phase_of(p.t[k], p.period);
+  }
+  __syncthreads();
+  const double dx = 2.0 * 3.14159265358979323846 / p.covpts;
+  for (int i = blockIdx.x * 8 + warp; i < p.nt; i += gridDim.x * 8) {
+    double s = 0.0;
+    if (p.marginal) {
+      if (p.nt == 1) {
+        s = (lane == 0) ? p.var[b] : 0.0;
+      } else {
+        const double thi = th[i];
+        for (int j = lane; j < p.nt; j += 32) s += interp_cov(cf, nc, dx, thi, th[j]);
+      }
+    } else {
+      const double *row = p.K + ((size_t)b * p.nt + i) * p.ldk;
+      for (int j = lane; j < p.nt; j += 32) s += row[j];
+    }
+    s = warp_sum(s);
+    if (lane == 0) p.rowq[(size_t)b * p.nt + i] = s;
+  }
+}
+
+// ---- pass S: per-sample scalars of the normalisation series ---------------------------------
+__global__ void __launch_bounds__(256) norm_scalars_kernel(AsmParams p) {
+  __shared__ double red[8];
+  __shared__ double mshare;
+  const int b = blockIdx.x, tid = threadIdx.x;
+  double s = 0.0;
+  for (int i = tid; i < p.nt; i += 256) s += p.rowq[(size_t)b * p.nt + i];
+  s = warp_sum(s);
+  if ((tid & 31) == 0) red[tid >> 5] = s;
+  __syncthreads();
+  if (tid == 0) {
+    double tot = 0.0;
+    for (int k = 0; k < 8; ++k) tot += red[k];
+    const double K = (double)p.nt;
+    const double m = tot / (K * K);             // tt.mean(Sig)
+    const double mu = 1.0 + p.gp_mean[b];       // sp.py:700-701
+    const double z = m / (mu * mu);
+    double fac = 1.0, alpha = 0.0, beta = 0.0;  // norm.py:26-44
+    for (int n = 0; n <= p.nm.normalization_order; ++n) {
+      alpha += fac;
+      beta += 2 * n * fac;
+      fac *= z * (2 * n + 3);
+    }
+    p.scal[4 * b + 0] = alpha / (mu * mu);
+    p.scal[4 * b + 1] = z * (alpha + beta);
+    p.scal[4 * b + 2] = z * alpha;
+    p.scal[4 * b + 3] = m;
+    if (p.z_out) p.z_out[b] = z;
+    if (p.info && (z > p.nm.normalization_zmax)) atomicOr(&p.info[b], SPB_INFO_Z_RANGE);
+    mshare = m;
+  }
+  __syncthreads();
+  const double km = (double)p.nt * mshare;
+  for (int i = tid; i < p.nt; i += 256) p.rowq[(size_t)b * p.nt + i] /= km;  // q = Sig 1 / (K m)
+}
+
+__device__ __forceinline__ double noise_term(const spb_noise_model &nm, int b, int i, int j, int nt) {
+  double v = 0.0;
+  if (nm.data_cov) {
+    if (nm.data_kind == 0) {
+      if (i == j) v += nm.data_cov[(size_t)b * nm.data_stride];
+    } else if (nm.data_kind == 1) {
+      if (i == j) v += nm.data_cov[(size_t)b * nm.data_stride + i];
+    } else {
+      v += nm.data_cov[(size_t)b * nm.data_stride + (size_t)i * nt + j];
+    }
+  }
+  if (nm.baseline_var) {
+    if (nm.base_kind == 0) v += nm.baseline_var[(size_t)b * nm.base_stride];
+    else v += nm.baseline_var[(size_t)b * nm.base_stride + (size_t)i * nt + j];
+  }
+  return v;
+}
+
+// ---- pass W: write K (marginal) or update it in place (conditional) ---------------------------
+__global__ void __launch_bounds__(256) write_kernel(AsmParams p) {
+  extern __shared__ double sh[];
+  const int b = blockIdx.y;
+  const int nc = p.covpts + 1;
+  double *cf = sh, *th = sh + (p.marginal ? 4 * nc : 0), *q = th + (p.marginal ? p.nt : 0);
+  const int tid = threadIdx.x;
+  if (p.marginal) {
+    for (int k = tid; k < 4 * nc; k += 256) cf[k] = p.coef[(size_t)b * 4 * nc + k];
+    for (int k = tid; k < p.nt; k += 256) th[k] = phase_of(p.t[k], p.period);
+  }
+  double s1 = 1.0, s2 = 0.0, s3 = 0.0;
+  if (p.nm.normalized) {
+    for (int k = tid; k < p.nt; k += 256) q[k] = p.rowq[(size_t)b * p.nt + k];
+    s1 = p.scal[4 * b + 0];
+    s2 = p.scal[4 * b + 1];
+    s3 = p.scal[4 * b + 2];
+  }
+  __syncthreads();
+  const double dx = 2.0 * 3.14159265358979323846 / p.covpts;
+  // each CTA owns a band of rows; threads run along columns (coalesced 8-byte stores)
+  for (int i = blockIdx.x; i < p.nt; i += gridDim.x) {
+    double *row = p.K + ((size_t)b * p.nt + i) * p.ldk;
+    const double thi = p.marginal ? th[i] : 0.0;
+    const double qi = p.nm.normalized ? q[i] : 0.0;
+    for (int j = tid; j < p.nt; j += 256) {
+      double v;
+      if (p.marginal) v = (p.nt == 1) ? p.var[b] : interp_cov(cf, nc, dx, thi, th[j]);
+      else v = row[j];
+      if (p.nm.normalized) {
+        const double qj = q[j];
+        v = s1 * v + (s2 * ((1.0 - qi) * (1.0 - qj)) - s3 * (qi * qj));  // sp.py:721-726
+      }
+      v += noise_term(p.nm, b, i, j, p.nt);
+      row[j] = v;
+    }
+  }
+}
+
+int run_assemble(spb_context *ctx, AsmParams &p, void *workspace, size_t workspace_bytes,
+                 cudaStream_t stream) {
+  SPB_REQUIRE(p.B > 0 && p.nt > 0 && p.ldk >= p.nt, "assemble: bad arguments");
+  SPB_REQUIRE(p.B <= 65535, "assemble: batch too large for one launch");
+  const size_t need = ((size_t)p.B * p.nt + (size_t)p.B * 4) * sizeof(double);
+  SPB_REQUIRE(workspace != nullptr && workspace_bytes >= need, "assemble: workspace too small");
+  SPB_CHECK_CUDA(cudaSetDevice(ctx->device));
+  p.rowq = reinterpret_cast<double *>(workspace);
+  p.scal = p.rowq + (size_t)p.B * p.nt;
+  const int nc = p.covpts + 1;
+  const size_t smA = (p.marginal ? (4 * nc + p.nt) : 0) * sizeof(double);
+  const size_t smW = smA + (p.nm.normalized ? p.nt : 0) * sizeof(double);
+  SPB_REQUIRE(smW <= 200 * 1024, "assemble: nt too large for the shared-memory staging");
+  static bool attr = false;
+  if (!attr) {
+    SPB_CHECK_CUDA(cudaFuncSetAttribute(rowsum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        200 * 1024));
+    SPB_CHECK_CUDA(cudaFuncSetAttribute(write_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        200 * 1024));
+    attr = true;
+  }
+  if (p.nm.normalized) {
+    dim3 gridA(min((p.nt + 7) / 8, 16), p.B);
+    rowsum_kernel<<<gridA, 256, smA, stream>>>(p);
+    SPB_LAUNCH_CHECK(ctx);
+    norm_scalars_kernel<<<p.B, 256, 0, stream>>>(p);
+    SPB_LAUNCH_CHECK(ctx);
+  } else if (p.z_out) {
+    SPB_CHECK_CUDA(cudaMemsetAsync(p.z_out, 0, (size_t)p.B * sizeof(double), stream));
+  }
+  dim3 gridW(min(p.nt, 32), p.B);
+  write_kernel<<<gridW, 256, smW, stream>>>(p);
+  SPB_LAUNCH_CHECK(ctx);
+  return 0;
+}
+
+}  // namespace
+
+extern "C" size_t spb_assemble_workspace_bytes(const spb_context *ctx, int B, int nt) {
+  (void)ctx;
+  return ((size_t)B * nt + (size_t)B * 4) * sizeof(double) + 256;
+}
+
+extern "C" int spb_assemble_marginal(spb_context *ctx, int B, int nt, const double *t, double period,
+                                     int covpts, const double *coef, const double *var,
+                                     const double *gp_mean, const spb_noise_model *noise, double *K,
+                                     int ldk, double *z_out, int32_t *info, void *workspace,
+                                     size_t workspace_bytes, void *stream) {
+  SPB_REQUIRE(ctx != nullptr && noise != nullptr && t != nullptr && coef != nullptr,
+              "assemble_marginal: null argument");
+  SPB_REQUIRE(period > 0.0, "assemble_marginal: period must be positive");
+  AsmParams p = {};
+  p.B = B;
+  p.nt = nt;
+  p.ldk = ldk;
+  p.covpts = covpts;
+  p.t = t;
+  p.period = period;
+  p.coef = coef;
+  p.var = var;
+  p.gp_mean = gp_mean;
+  p.nm = *noise;
+  p.K = K;
+  p.z_out = z_out;
+  p.info = info;
+  p.marginal = 1;
+  return run_assemble(ctx, p, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+extern "C" int spb_assemble_conditional(spb_context *ctx, int B, int nt, const double *gp_mean,
+                                        const spb_noise_model *noise, double *K, int ldk,
+                                        double *z_out, int32_t *info, void *workspace,
+                                        size_t workspace_bytes, void *stream) {
+  SPB_REQUIRE(ctx != nullptr && noise != nullptr, "assemble_conditional: null argument");
+  AsmParams p = {};
+  p.B = B;
+  p.nt = nt;
+  p.ldk = ldk;
+  p.covpts = 1;
+  p.period = 1.0;
+  p.gp_mean = gp_mean;
+  p.nm = *noise;
+  p.K = K;
+  p.z_out = z_out;
+  p.info = info;
+  p.marginal = 0;
+  return run_assemble(ctx, p, workspace, workspace_bytes, (cudaStream_t)stream);
+}

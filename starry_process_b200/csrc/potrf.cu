@@ -472,10 +472,12 @@ __global__ void __launch_bounds__(NTHREADS, 2) potrf_lnlike_kernel(PotrfParams p
       const bool bad = sm.bad != 0;
       double ll = -0.5 * quad - (double)rm.M * logdet -
                   0.5 * (double)p.n * (double)rm.M * 1.8378770664093453;  // log(2 pi)
-      if (bad || ll != ll) ll = -INFINITY;
+      // flags raised by earlier stages (bounds, normalisation range) also map to -inf
+      const int prev = p.info ? (p.info[item] & ~SPB_INFO_NOT_PD) : 0;
+      if (bad || (prev & (SPB_INFO_Z_RANGE | SPB_INFO_BOUNDS)) || ll != ll) ll = -INFINITY;
       if (p.lnlike) p.lnlike[item] = ll;
       if (p.logdet) p.logdet[item] = bad ? NAN : logdet;
-      if (p.info) p.info[item] = (p.info[item] & ~SPB_INFO_NOT_PD) | (bad ? SPB_INFO_NOT_PD : 0);
+      if (p.info) p.info[item] = prev | (bad ? SPB_INFO_NOT_PD : 0);
     }
     __syncthreads();
   }

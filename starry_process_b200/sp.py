@@ -1,0 +1,536 @@
+"""
+``StarryProcess`` -- B200-native drop-in for the batched likelihood path of
+``starry_process.StarryProcess`` (reference: starry_process/sp.py:38-284, 420-441, 489-509,
+643-727, 1052-1188).
+
+Same constructor keywords, property names and method signatures as the reference for the hot
+path; inputs/outputs are ``torch.float64`` CUDA tensors and evaluation is eager.  Extension: any of
+``r, mu, sigma, a, b, c, n`` may be a ``(B,)`` tensor (one hyperparameter sample per element), and
+``i`` may be ``(B,)`` in the conditional branch; outputs then carry a leading batch axis and
+``log_likelihood`` returns ``(B,)``.  All numerics run in ``libspb200.so`` (hand-written sm_100a CUDA
+behind ``include/spb200.h``) -- there is no CPU or PyTorch fallback: without the library (or without
+a CUDA device) construction raises.
+
+Out of scope in this drop-in (callers, listed under "next"): the uniform
+spot-size prior (``dr``), time-variable surfaces (``tau``), ``predict``/conditional sampling,
+pixel-space moments and visualisation.  They raise ``NotImplementedError``.
+"""
+import ctypes
+import math
+
+import numpy as np
+import torch
+
+from . import _lib, _tables
+
+__all__ = ["StarryProcess", "gauss2beta", "beta2gauss", "defaults"]
+
+# starry_process/defaults.py:4-35
+defaults = dict(
+    ydeg=15, udeg=2, r=20.0, dr=None, a=0.40, b=0.27, c=0.1, n=10.0, p=1.0, i=60.0,
+    u=[0.0, 0.0], tau=None, normalized=True, normalization_order=20, normalization_zmax=0.023,
+    marginalize_over_inclination=True, baseline_mean=0.0, baseline_var=0.0, covpts=300,
+    log_alpha_max=10, log_beta_max=10, abmin=1e-12, sigma_max=45.0, epsy=1e-12, epsy15=1e-9,
+)
+
+_CTX = {}
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+class _Context(object):
+    """One libspb200 context (constant tables resident in HBM) per CUDA device."""
+
+    def __init__(self, device):
+        if not torch.cuda.is_available():
+            raise RuntimeError("starry_process_b200 needs a CUDA device (sm_100a); no CPU fallback")
+        self.lib = _lib.load()
+        self.device = torch.device("cuda", device)
+        blob, _ = _tables.build_tables()
+        h = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            torch.cuda.current_stream().synchronize()
+            _lib.check(self.lib.spb_create(device, blob.ctypes.data_as(ctypes.c_void_p), blob.size,
+                                           ctypes.byref(h)))
+        self.handle = h
+
+    def launches(self):
+        n = ctypes.c_longlong()
+        _lib.check(self.lib.spb_launch_count(self.handle, ctypes.byref(n)))
+        return n.value
+
+
+def get_context(device=None):
+    if device is None:
+        device = torch.cuda.current_device() if torch.cuda.is_available() else 0
+    if isinstance(device, torch.device):
+        device = device.index if device.index is not None else torch.cuda.current_device()
+    if device not in _CTX:
+        _CTX[device] = _Context(int(device))
+    return _CTX[device]
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _is_batched(x):
+    return (isinstance(x, torch.Tensor) and x.ndim > 0) or (isinstance(x, np.ndarray) and x.ndim > 0) \
+        or isinstance(x, (list, tuple))
+
+
+def gauss2beta(mu, sigma, log_alpha_max=10, log_beta_max=10):
+    """latitude.py:14-77 (host utility; accepts floats, arrays or tensors, angles in degrees)."""
+    tens = isinstance(mu, torch.Tensor) or isinstance(sigma, torch.Tensor)
+    m = torch.as_tensor(mu, dtype=torch.float64) * math.pi / 180
+    v = (torch.as_tensor(sigma, dtype=torch.float64) * math.pi / 180) ** 2
+    c1, c2, c3 = torch.cos(m), torch.cos(2 * m), torch.cos(3 * m)
+    term = 1.0 / (16 * v * torch.cos(0.5 * m) ** 4)
+    alpha = (2 + 4 * v + (3 + 8 * v) * c1 + 2 * c2 + c3) * term
+    beta = (c1 + 2 * v * (3 + c2) - c3) * term
+    a = torch.log(alpha) / log_alpha_max
+    b = torch.clamp((torch.log(beta) - math.log(0.5)) / (log_beta_max - math.log(0.5)), min=0.0)
+    if tens:
+        return a, b
+    if a.ndim == 0:
+        return float(a), float(b)
+    return a.numpy(), b.numpy()
+
+
+def beta2gauss(a, b, log_alpha_max=10, log_beta_max=10):
+    """latitude.py:80-168 (host utility)."""
+    tens = isinstance(a, torch.Tensor) or isinstance(b, torch.Tensor)
+    a_ = torch.as_tensor(a, dtype=torch.float64)
+    b_ = torch.as_tensor(b, dtype=torch.float64)
+    alpha = torch.exp(a_ * log_alpha_max)
+    beta = torch.exp(math.log(0.5) + b_ * (log_beta_max - math.log(0.5)))
+    term = 4 * alpha ** 2 - 8 * alpha - 6 * beta + 4 * alpha * beta + beta ** 2 + 5
+    mu = 2 * torch.atan(torch.sqrt(2 * alpha + beta - 2 - torch.sqrt(term)))
+    term = 1 - alpha + beta + (beta - 1) * torch.cos(mu) + (alpha - 1) / torch.cos(mu) ** 2
+    sigma = torch.sin(mu) / torch.sqrt(term)
+    invalid = (alpha <= 1) | (beta <= 0.5)
+    nan = torch.full_like(mu, float("nan"))
+    mu = torch.where(invalid, nan, mu) * 180 / math.pi
+    sigma = torch.where(invalid, nan, sigma) * 180 / math.pi
+    if tens:
+        return mu, sigma
+    if mu.ndim == 0:
+        return float(mu), float(sigma)
+    return mu.numpy(), sigma.numpy()
+
+
+def _check_bounds(name, x, lower=-np.inf, upper=np.inf, tol=1e-6):
+    """ops/exceptions.py:30-48 for host-resident values."""
+    xv = np.atleast_1d(np.asarray(x, dtype=np.float64))
+    low = xv < lower - tol
+    high = xv > upper + tol
+    if low.any():
+        raise ValueError("%s out of bounds: %f %s %f" % (name, xv[low][0], "<=", lower))
+    if high.any():
+        raise ValueError("%s out of bounds: %f %s %f" % (name, xv[high][0], ">=", upper))
+
+
+class StarryProcess(object):
+    def __init__(self, r=defaults["r"], dr=defaults["dr"], c=defaults["c"], n=defaults["n"],
+                 tau=defaults["tau"], temporal_kernel=None,
+                 marginalize_over_inclination=defaults["marginalize_over_inclination"],
+                 normalized=defaults["normalized"], covpts=defaults["covpts"], device=None,
+                 **kwargs):
+        # sp.py:204-222
+        mu = kwargs.pop("mu", None)
+        sigma = kwargs.pop("sigma", None)
+        if mu is None and sigma is None:
+            a = kwargs.pop("a", defaults["a"])
+            b = kwargs.pop("b", defaults["b"])
+        elif (kwargs.get("a", None) is None and kwargs.get("b", None) is None) and (
+                mu is not None and sigma is not None):
+            a = b = None
+        else:
+            raise ValueError("Must provide either `a` and `b` *or* `mu` and `sigma`.")
+        if dr is not None:
+            raise NotImplementedError("uniform spot-size prior (dr) is outside the lnlike hot path")
+        if tau is not None:
+            raise NotImplementedError("time-variable surfaces (tau) are outside the lnlike hot path")
+        self._ydeg = int(kwargs.pop("ydeg", defaults["ydeg"]))
+        self._udeg = int(kwargs.pop("udeg", defaults["udeg"]))
+        if self._ydeg != 15:
+            raise NotImplementedError("libspb200 is specialised for ydeg = 15 (constants.h:14-34 bakes "
+                                      "the degree in at compile time in the reference as well)")
+        if self._udeg not in (0, 2):
+            raise NotImplementedError("udeg must be 0 or 2")
+        for key, val in (("epsy", 1e-12), ("epsy15", 1e-9), ("abmin", 1e-12), ("log_alpha_max", 10),
+                         ("log_beta_max", 10)):
+            if kwargs.pop(key, val) != val:
+                raise NotImplementedError("non-default `%s` is not supported" % key)
+        self._normN = int(kwargs.pop("normalization_order", defaults["normalization_order"]))
+        self._normzmax = float(kwargs.pop("normalization_zmax", defaults["normalization_zmax"]))
+        self._max_chunk_bytes = int(kwargs.pop("max_chunk_bytes", 24 << 30))
+        kwargs.pop("seed", None)
+        self._nylm = (self._ydeg + 1) ** 2
+        self._covpts = int(covpts)
+        self._normalized = bool(normalized)
+        self._marginalize_over_inclination = bool(marginalize_over_inclination)
+
+        self._ctx = get_context(device)
+        self.device = self._ctx.device
+        self._lib = self._ctx.lib
+
+        params = dict(r=r, c=c, n=n)
+        if a is None:
+            params.update(mu=mu, sigma=sigma)
+        else:
+            params.update(a=a, b=b)
+        self._batched = any(_is_batched(v) for v in params.values())
+        # host-side bounds checks, as the reference raises (device-resident tensors are flagged
+        # per element through info[] instead of forcing a device->host sync)
+        hostvals = {k: v for k, v in params.items()
+                    if not (isinstance(v, torch.Tensor) and v.is_cuda)}
+        if "r" in hostvals:
+            _check_bounds("r", np.asarray(hostvals["r"], dtype=np.float64) * np.pi / 180, 0,
+                          0.5 * np.pi)
+        if "a" in hostvals:
+            _check_bounds("a", hostvals["a"], 0, 1)
+        if "b" in hostvals:
+            _check_bounds("b", hostvals["b"], 0, 1)
+        if "n" in hostvals:
+            _check_bounds("n", hostvals["n"], 0, np.inf)
+        tens = {k: torch.as_tensor(v, dtype=torch.float64).to(self.device).reshape(-1)
+                for k, v in params.items()}
+        B = max(t.numel() for t in tens.values())
+        for k, t in tens.items():
+            if t.numel() not in (1, B):
+                raise ValueError("hyperparameter `%s` has %d elements, expected 1 or %d" %
+                                 (k, t.numel(), B))
+            tens[k] = t.expand(B).contiguous()
+        self._B = B
+        self._r, self._c, self._n = tens["r"], tens["c"], tens["n"]
+        if a is None:
+            self._a = torch.empty(B, dtype=torch.float64, device=self.device)
+            self._b = torch.empty(B, dtype=torch.float64, device=self.device)
+            with torch.cuda.device(self.device):
+                _lib.check(self._lib.spb_gauss2beta(self._ctx.handle, B, _ptr(tens["mu"]),
+                                                    _ptr(tens["sigma"]), _ptr(self._a),
+                                                    _ptr(self._b), _stream()))
+            if "mu" in hostvals:
+                ah, bh = gauss2beta(torch.as_tensor(hostvals["mu"], dtype=torch.float64),
+                                    torch.as_tensor(hostvals["sigma"], dtype=torch.float64))
+                _check_bounds("a", ah.numpy(), 0, 1)
+                _check_bounds("b", bh.numpy(), 0, 1)
+        else:
+            self._a, self._b = tens["a"], tens["b"]
+        self._mean_ylm = None
+        self._cov_ylm = None
+        self._cho_cov_ylm = None
+        self._info = torch.zeros(B, dtype=torch.int32, device=self.device)
+        self._z = None
+        self._rTA1_cache = {}
+
+    # ------------------------------------------------------------------ hyperparameters
+    @property
+    def a(self):
+        return self._out(self._a)
+
+    @property
+    def b(self):
+        return self._out(self._b)
+
+    @property
+    def batch_size(self):
+        return self._B
+
+    @property
+    def info(self):
+        """Per-element status bits (include/spb200.h: SPB_INFO_*)."""
+        return self._info
+
+    def _out(self, t):
+        return t if self._batched else t[0]
+
+    # ------------------------------------------------------------------ Ylm moments
+    def _compute_moments(self):
+        if self._mean_ylm is not None:
+            return
+        B = self._B
+        with torch.cuda.device(self.device):
+            mean = torch.empty(B, 256, dtype=torch.float64, device=self.device)
+            cov = torch.empty(B, 256, 256, dtype=torch.float64, device=self.device)
+            nbytes = self._lib.spb_ylm_moments_workspace_bytes(self._ctx.handle, B)
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+            _lib.check(self._lib.spb_ylm_moments(
+                self._ctx.handle, B, _ptr(self._r), _ptr(self._a), _ptr(self._b), _ptr(self._c),
+                _ptr(self._n), _ptr(mean), _ptr(cov), _ptr(self._info), _ptr(ws), nbytes, _stream()))
+            del ws
+        self._mean_ylm, self._cov_ylm = mean, cov
+
+    @property
+    def mean_ylm(self):
+        """sp.py:420-426."""
+        self._compute_moments()
+        return self._out(self._mean_ylm)
+
+    @property
+    def cov_ylm(self):
+        """sp.py:428-434."""
+        self._compute_moments()
+        return self._out(self._cov_ylm)
+
+    @property
+    def cho_cov_ylm(self):
+        """sp.py:436-441 (lower Cholesky factor of ``cov_ylm``)."""
+        self._compute_moments()
+        if self._cho_cov_ylm is None:
+            with torch.cuda.device(self.device):
+                L = torch.empty_like(self._cov_ylm)
+                info = torch.zeros(self._B, dtype=torch.int32, device=self.device)
+                _lib.check(self._lib.spb_cho_cov_ylm(self._ctx.handle, self._B, _ptr(self._cov_ylm),
+                                                     _ptr(L), _ptr(info), _stream()))
+                bad = (info & 1) != 0
+                L = torch.where(bad[:, None, None], torch.full_like(L, float("nan")), L)
+            self._cho_cov_ylm = L
+        return self._out(self._cho_cov_ylm)
+
+    def sample_ylm(self, t=None, nsamples=1, u=None, generator=None):
+        """sp.py:489-509 (``t`` must be None: static surfaces).  ``u`` optionally supplies the
+        standard-normal draws, shape ``(nylm, nsamples)`` as in the reference's
+        ``random_normal(self.random, (nylm, nsamples))`` or ``(B, nylm, nsamples)``."""
+        if t is not None:
+            raise NotImplementedError("time-variable sampling (tau) is outside the lnlike hot path")
+        L = self.cho_cov_ylm
+        L = L if self._batched else L[None]
+        B = self._B
+        with torch.cuda.device(self.device):
+            if u is None:
+                un = torch.randn(B, nsamples, 256, dtype=torch.float64, device=self.device,
+                                 generator=generator)
+            else:
+                un = torch.as_tensor(u, dtype=torch.float64).to(self.device)
+                nsamples = un.shape[-1]
+                if un.ndim == 2:
+                    un = un[None].expand(B, 256, nsamples)
+                un = un.transpose(1, 2).contiguous()
+            y = torch.empty(B, nsamples, 256, dtype=torch.float64, device=self.device)
+            _lib.check(self._lib.spb_sample_ylm(self._ctx.handle, B, nsamples, _ptr(self._mean_ylm),
+                                                _ptr(L.contiguous()), _ptr(un), _ptr(y), _stream()))
+        return self._out(y)
+
+    # ------------------------------------------------------------------ flux operator / design
+    def _u(self, u):
+        u = torch.as_tensor(defaults["u"] if u is None else u, dtype=torch.float64).reshape(-1)
+        if self._udeg == 0:
+            return torch.zeros(2, dtype=torch.float64, device=self.device)
+        if u.numel() < self._udeg:
+            raise ValueError("Vector `u` has the wrong size. Expected %d, got %d." %
+                             (self._udeg, u.numel()))
+        return u[: self._udeg].to(self.device).contiguous()
+
+    def _rTA1(self, u):
+        ud = self._u(u)
+        out = torch.empty(256, dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.spb_flux_operator(self._ctx.handle, 1, _ptr(ud), _ptr(out),
+                                                   _stream()))
+        return out
+
+    def _t(self, t):
+        return torch.as_tensor(t, dtype=torch.float64).to(self.device).reshape(-1).contiguous()
+
+    def _inc(self, i):
+        if not (isinstance(i, torch.Tensor) and i.is_cuda):
+            _check_bounds("i", np.asarray(i, dtype=np.float64) * np.pi / 180, 0, 0.5 * np.pi)
+        it = torch.as_tensor(i, dtype=torch.float64).to(self.device).reshape(-1) * (math.pi / 180)
+        return it.contiguous()
+
+    def design_matrix(self, t, i=defaults["i"], p=defaults["p"], u=None):
+        """flux.py:345-350: ``A (nt, 256)``, or ``(I, nt, 256)`` for a vector of inclinations."""
+        t = self._t(t)
+        inc = self._inc(i)
+        _check_bounds("p", p, 0, np.inf)
+        I, nt = inc.numel(), t.numel()
+        rta1 = self._rTA1(u)
+        with torch.cuda.device(self.device):
+            per = torch.full((I,), float(p), dtype=torch.float64, device=self.device)
+            A = torch.empty(I, nt, 256, dtype=torch.float64, device=self.device)
+            nbytes = self._lib.spb_design_matrix_workspace_bytes(self._ctx.handle, I, nt)
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+            _lib.check(self._lib.spb_design_matrix(self._ctx.handle, I, nt, _ptr(t), _ptr(inc),
+                                                   _ptr(per), _ptr(rta1), 0, _ptr(A), _ptr(ws),
+                                                   nbytes, _stream()))
+        return A if _is_batched(i) else A[0]
+
+    # ------------------------------------------------------------------ flux mean / covariance
+    def _noise_model(self, nt, data_cov, baseline_var, keep):
+        nm = _lib.NoiseModel()
+        nm.normalized = 1 if self._normalized else 0
+        nm.normalization_order = self._normN
+        nm.normalization_zmax = self._normzmax
+        nm.data_cov = None
+        nm.baseline_var = None
+        nm.data_stride = 0
+        nm.base_stride = 0
+        if data_cov is not None:
+            d = torch.as_tensor(data_cov, dtype=torch.float64).to(self.device).contiguous()
+            if d.ndim == 0:
+                nm.data_kind, d = 0, d.reshape(1)
+            elif d.ndim == 1:
+                if d.numel() != nt:
+                    raise ValueError("data_cov vector has the wrong length")
+                nm.data_kind = 1
+            else:
+                if tuple(d.shape) != (nt, nt):
+                    raise ValueError("data_cov matrix has the wrong shape")
+                nm.data_kind = 2
+            keep.append(d)
+            nm.data_cov = d.data_ptr()
+        if baseline_var is not None:
+            bv = torch.as_tensor(baseline_var, dtype=torch.float64).to(self.device).contiguous()
+            if bv.ndim == 0:
+                nm.base_kind, bv = 0, bv.reshape(1)
+            else:
+                if tuple(bv.shape) != (nt, nt):
+                    raise ValueError("baseline_var must be a scalar or an (nt, nt) matrix")
+                nm.base_kind = 2
+            keep.append(bv)
+            nm.baseline_var = bv.data_ptr()
+        return nm
+
+    def _flux_cov_chunk(self, b0, b1, t, inc, p, rta1, marg, data_cov, baseline_var, ldk):
+        """GP mean (scalar per element) and the (noise-augmented) covariance for elements b0:b1.
+        Returns (gp_mean, K, z)."""
+        lib, h = self._lib, self._ctx.handle
+        Bc, nt = b1 - b0, t.numel()
+        dev = self.device
+        keep = []
+        nm = self._noise_model(nt, data_cov, baseline_var, keep)
+        mean_ylm = self._mean_ylm[b0:b1]
+        cov_ylm = self._cov_ylm[b0:b1]
+        info = self._info[b0:b1]
+        gp_mean = torch.empty(Bc, dtype=torch.float64, device=dev)
+        K = torch.empty(Bc, nt, ldk, dtype=torch.float64, device=dev)
+        z = torch.zeros(Bc, dtype=torch.float64, device=dev)
+        nb_as = lib.spb_assemble_workspace_bytes(h, Bc, nt)
+        ws_as = torch.empty(nb_as, dtype=torch.uint8, device=dev)
+        if marg:
+            nc = self._covpts + 1
+            var = torch.empty(Bc, dtype=torch.float64, device=dev)
+            coef = torch.empty(Bc, 4, nc, dtype=torch.float64, device=dev)
+            nb = lib.spb_flux_marginal_workspace_bytes(h, Bc)
+            ws = torch.empty(nb, dtype=torch.uint8, device=dev)
+            _lib.check(lib.spb_flux_marginal(h, Bc, _ptr(mean_ylm), _ptr(cov_ylm), _ptr(rta1),
+                                             self._covpts, _ptr(gp_mean), _ptr(var), _ptr(coef),
+                                             _ptr(ws), nb, _stream()))
+            _lib.check(lib.spb_assemble_marginal(h, Bc, nt, _ptr(t), float(p), self._covpts,
+                                                 _ptr(coef), _ptr(var), _ptr(gp_mean),
+                                                 ctypes.byref(nm), _ptr(K), ldk, _ptr(z), _ptr(info),
+                                                 _ptr(ws_as), nb_as, _stream()))
+        else:
+            inc_c = inc if inc.numel() == 1 else inc[b0:b1].contiguous()
+            Ic = inc_c.numel()
+            per = torch.full((Ic,), float(p), dtype=torch.float64, device=dev)
+            A = torch.empty(Ic, nt, 256, dtype=torch.float64, device=dev)
+            nbd = lib.spb_design_matrix_workspace_bytes(h, Ic, nt)
+            wsd = torch.empty(nbd, dtype=torch.uint8, device=dev)
+            _lib.check(lib.spb_design_matrix(h, Ic, nt, _ptr(t), _ptr(inc_c), _ptr(per), _ptr(rta1),
+                                             0, _ptr(A), _ptr(wsd), nbd, _stream()))
+            nb = lib.spb_flux_conditional_workspace_bytes(h, Bc, nt)
+            ws = torch.empty(nb, dtype=torch.uint8, device=dev)
+            _lib.check(lib.spb_flux_conditional(h, Bc, nt, _ptr(A), 0 if Ic == 1 else nt * 256,
+                                                _ptr(mean_ylm), _ptr(cov_ylm), _ptr(gp_mean),
+                                                _ptr(K), ldk, _ptr(ws), nb, _stream()))
+            _lib.check(lib.spb_assemble_conditional(h, Bc, nt, _ptr(gp_mean), ctypes.byref(nm),
+                                                    _ptr(K), ldk, _ptr(z), _ptr(info), _ptr(ws_as),
+                                                    nb_as, _stream()))
+        return gp_mean, K, z
+
+    def _chunks(self, nt, ldk):
+        per = nt * ldk * 8 + 4 * 256 * 256 * 8
+        step = max(1, min(self._B, self._max_chunk_bytes // per))
+        return [(b0, min(self._B, b0 + step)) for b0 in range(0, self._B, step)]
+
+    def _prep(self, t, i, p, u, marginalize_over_inclination):
+        marg = self._marginalize_over_inclination if marginalize_over_inclination is None \
+            else bool(marginalize_over_inclination)
+        self._compute_moments()
+        t = self._t(t)
+        inc = self._inc(i)
+        if inc.numel() not in (1, self._B):
+            raise ValueError("`i` must be a scalar or have one entry per batch element")
+        _check_bounds("p", p, 0, np.inf)
+        rta1 = self._rTA1(u)
+        return marg, t, inc, rta1
+
+    def mean(self, t, i=defaults["i"], p=defaults["p"], u=None, marginalize_over_inclination=None):
+        """sp.py:643-672."""
+        marg, t, inc, rta1 = self._prep(t, i, p, u, marginalize_over_inclination)
+        nt = t.numel()
+        if self._normalized:
+            out = torch.zeros(self._B, nt, dtype=torch.float64, device=self.device)
+            return self._out(out)
+        with torch.cuda.device(self.device):
+            gm = []
+            for b0, b1 in self._chunks(nt, nt + (nt & 1)):
+                g, _, _ = self._flux_cov_chunk(b0, b1, t, inc, p, rta1, marg, None, None,
+                                               nt + (nt & 1))
+                gm.append(g)
+            g = torch.cat(gm)
+        return self._out(g[:, None].expand(self._B, nt).contiguous())
+
+    def cov(self, t, i=defaults["i"], p=defaults["p"], u=None, marginalize_over_inclination=None):
+        """sp.py:674-703: the (normalised, if requested) GP flux covariance, ``(nt, nt)`` or
+        ``(B, nt, nt)``."""
+        marg, t, inc, rta1 = self._prep(t, i, p, u, marginalize_over_inclination)
+        nt = t.numel()
+        ldk = nt + (nt & 1)
+        outs, zs = [], []
+        with torch.cuda.device(self.device):
+            for b0, b1 in self._chunks(nt, ldk):
+                _, K, z = self._flux_cov_chunk(b0, b1, t, inc, p, rta1, marg, None, None, ldk)
+                outs.append(K[:, :, :nt])
+                zs.append(z)
+        self._z = torch.cat(zs)
+        K = torch.cat(outs) if len(outs) > 1 else outs[0]
+        return self._out(K)
+
+    # ------------------------------------------------------------------ log likelihood
+    def log_likelihood(self, t, flux, data_cov, i=defaults["i"], p=defaults["p"], u=None,
+                       baseline_mean=defaults["baseline_mean"],
+                       baseline_var=defaults["baseline_var"], marginalize_over_inclination=None):
+        """sp.py:1052-1188.  ``flux`` is ``(nt,)`` or ``(M, nt)`` (M light curves sharing period,
+        limb darkening, inclination and noise, scored jointly); returns a scalar, or ``(B,)`` for a
+        batch of hyperparameter samples."""
+        marg, t, inc, rta1 = self._prep(t, i, p, u, marginalize_over_inclination)
+        nt = t.numel()
+        ldk = nt + (nt & 1)
+        dev = self.device
+        f = torch.as_tensor(flux, dtype=torch.float64).to(dev)
+        if f.ndim == 1:
+            f = f[None]
+        if f.shape[1] != nt:
+            raise ValueError("flux must have shape (nt,) or (M, nt)")
+        M = f.shape[0]
+        bm = torch.as_tensor(baseline_mean, dtype=torch.float64).to(dev)
+        bvar = None
+        if isinstance(baseline_var, (torch.Tensor, np.ndarray)) or baseline_var != 0.0:
+            bvar = baseline_var
+        lnlike = torch.empty(self._B, dtype=torch.float64, device=dev)
+        zs = []
+        lib, h = self._lib, self._ctx.handle
+        with torch.cuda.device(dev):
+            for b0, b1 in self._chunks(nt, ldk):
+                Bc = b1 - b0
+                gp_mean, K, z = self._flux_cov_chunk(b0, b1, t, inc, p, rta1, marg, data_cov, bvar,
+                                                     ldk)
+                zs.append(z)
+                # r = flux - (gp_mean + baseline_mean)  (sp.py:1157-1161); normalised: mean == 0
+                resid = torch.zeros(Bc, M, ldk, dtype=torch.float64, device=dev)
+                if self._normalized:
+                    resid[:, :, :nt] = (f - bm)[None]
+                else:
+                    resid[:, :, :nt] = f[None] - (gp_mean[:, None, None] + bm)
+                _lib.check(lib.spb_cholesky_lnlike(
+                    h, Bc, nt, _ptr(K), ldk, nt * ldk, M, _ptr(resid), ldk, M * ldk,
+                    _ptr(lnlike[b0:b1]), None, None, _ptr(self._info[b0:b1]), _stream()))
+                del K, resid
+        self._z = torch.cat(zs)
+        return self._out(lnlike)
