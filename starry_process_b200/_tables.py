@@ -42,7 +42,7 @@ LAYOUT = [
     ("LON_T", NEIG * NWIG),
     ("FLUX_WNP", NWIG),
     ("FLUX_W", N * N),
-    ("FLUX_OMEGA", 16 * N * N),
+    ("FLUX_OMEGA", 31 * N * N),
     ("RX90", NWIG),
     ("GL_X", 32),
     ("GL_W", 32),
@@ -427,10 +427,17 @@ def build_tables(use_pinned_longitude=True):
     put("RX90", rx90)
     Rx = _blockdiag(rx90).astype(np.longdouble)
     WR = Wnp.astype(np.longdouble) @ Rx.T
-    Om = np.zeros((16, N, N))
+    #   b_m = sum_{i in group m} sgn(m_i) sum_j W_ij Ez_{i jbar}   (the sine lane of wigner.h:440-458;
+    #       zero for an exactly symmetric Ez, but the reference carries its rounding-level value)
+    bar = l_of * l_of + l_of - m_of
+    WRb = Wnp[:, bar].astype(np.longdouble) @ Rx.T
+    Om = np.zeros((31, N, N))
     for mm in range(16):
         sel = np.abs(m_of) == mm
         Om[mm] = (Rx[:, sel] @ WR[sel, :]).astype(np.float64)
+        if mm > 0:
+            sg = np.sign(m_of[sel]).astype(np.longdouble)
+            Om[15 + mm] = ((Rx[:, sel] * sg[None, :]) @ WRb[sel, :]).astype(np.float64)
     put("FLUX_OMEGA", Om)
 
     # ---- Gauss-Legendre rule on [0, 1] (32 nodes: exact to degree 63)

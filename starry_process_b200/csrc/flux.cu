@@ -10,9 +10,9 @@
 // and then evaluates, for each of the 304 grid lags, two (256 x 256) contractions.  Because the
 // z-rotation only multiplies row i by cos/sin(m_i theta), the lag dependence collapses to
 //      f(theta_k) = sum_m a_m cos(m theta_k),   a_m = sum_{i: |m_i| = m} sum_j W_ij Ez_ij
-// (the sine lane vanishes identically for a stationary kernel; in the reference it is ~1e-10 of
-// a_0 in rounding noise).  With Ez = Rx^T (Sigma + mu mu^T) Rx the Sigma part of a_m is a fixed
-// quadratic form <Omega_m(u), Sigma>; the 16 forms are pre-folded on the host (tables) and
+// plus the sine lane b_m sin(m theta_k), which vanishes for an exactly symmetric Ez but is carried
+// at its rounding-level value (~1e-9 of a_0) so that the kernel equals the reference's.  With Ez = Rx^T (Sigma + mu mu^T) Rx the Sigma part of a_m is a fixed
+// quadratic form <Omega_m(u), Sigma>; the 16 + 15 forms are pre-folded on the host (tables) and
 // evaluated for the whole batch as ONE tensor-core GEMM (B x 65536) . (65536 x 16) that streams
 // each cov_ylm exactly once from HBM; the rank-one mu mu^T part is evaluated directly from
 // ez = mu . Rx(pi/2).
@@ -66,7 +66,7 @@ struct MargParams {
   const double *rTA1;      // (256)
   const double *tab;
   double *gp_mean;         // (B)
-  double *amu;             // (B,16)
+  double *amu;             // (B,32): a_0..a_15, b_1..b_15 (mu mu^T part)
 };
 
 __global__ void __launch_bounds__(256) marginal_mu_kernel(MargParams p) {
@@ -113,6 +113,7 @@ __global__ void __launch_bounds__(256) marginal_mu_kernel(MargParams p) {
   }
   __syncthreads();
   ez[n] = zez[n] * arow[n];  // A_i (ez is no longer needed)
+  mu[n] = zez[l * l + l - m];  // zez at the (l, -m) partner (mu is no longer needed)
   __syncthreads();
   if (n < 16) {
     // a_m (mu part) = sum over rows with |m_i| = m, fixed order => deterministic
@@ -121,7 +122,25 @@ __global__ void __launch_bounds__(256) marginal_mu_kernel(MargParams p) {
       s += ez[ll * ll + ll + n];
       if (n > 0) s += ez[ll * ll + ll - n];
     }
-    p.amu[(size_t)b * 16 + n] = s;
+    p.amu[(size_t)b * 32 + n] = s;
+  }
+  __syncthreads();
+  // sine lane: B_i = zez_i sum_j Wnp_ij zez_jbar
+  for (int i = warp; i < 256; i += 8) {
+    const double *wr = p.tab + SPB_TAB_FLUX_W + (size_t)i * 256;
+    double acc = 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc = fma(wr[lane + 32 * k], mu[lane + 32 * k], acc);
+    acc = warp_sum(acc);
+    if (lane == 0) arow[i] = acc;
+  }
+  __syncthreads();
+  ez[n] = zez[n] * arow[n];
+  __syncthreads();
+  if (n >= 1 && n < 16) {
+    double s = 0.0;
+    for (int ll = n; ll <= SPB_LMAX; ++ll) s += ez[ll * ll + ll + n] - ez[ll * ll + ll - n];
+    p.amu[(size_t)b * 32 + 15 + n] = s;
   }
   (void)red;
 }
@@ -129,7 +148,7 @@ __global__ void __launch_bounds__(256) marginal_mu_kernel(MargParams p) {
 // ---- Omega_m(u)[p][q] = Omega_m[p][q] z_{l_p} z_{l_q} ---------------------------------------
 __global__ void omega_scale_kernel(const double *tab, const double *rTA1, double *out) {
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (size_t)16 * 65536) return;
+  if (idx >= (size_t)31 * 65536) return;
   const int pq = (int)(idx & 65535);
   const int pr = pq >> 8, q = pq & 255;
   int lp, mp, lq, mq;
@@ -149,10 +168,10 @@ struct CoefParams {
 
 __global__ void __launch_bounds__(128) marginal_coef_kernel(CoefParams p) {
   extern __shared__ double yp[];  // covpts + 4
-  __shared__ double am[16];
+  __shared__ double am[32];  // a_0..a_15, b_1..b_15
   const int b = blockIdx.x, tid = threadIdx.x;
-  if (tid < 16) {
-    double s = p.amu[(size_t)b * 16 + tid];
+  if (tid < 31) {
+    double s = p.amu[(size_t)b * 32 + tid];
     for (int k = 0; k < p.ksplit; ++k) s += p.acov_part[(size_t)k * p.strideSplit + (size_t)b * 64 + tid];
     am[tid] = s;
   }
@@ -162,13 +181,17 @@ __global__ void __launch_bounds__(128) marginal_coef_kernel(CoefParams p) {
   const double dx = 2.0 * 3.14159265358979323846 / p.covpts;
   for (int k = tid; k < npts; k += 128) {
     const double x = -dx + k * dx;  // flux.py:311-314 (numpy arange: start + k*step)
-    double c1 = cos(x), cm1 = 1.0, cm = c1;
-    double s = am[0] + am[1] * c1;
+    const double c1 = cos(x), s1 = sin(x);
+    double cm1 = 1.0, cm = c1, sm1 = 0.0, sm = s1;
+    double s = am[0] + am[1] * c1 + am[16] * s1;
     for (int mm = 2; mm < 16; ++mm) {
       const double cn = 2.0 * cm * c1 - cm1;  // wigner.h:311-316
+      const double sn = 2.0 * sm * c1 - sm1;
       cm1 = cm;
       cm = cn;
-      s += am[mm] * cn;
+      sm1 = sm;
+      sm = sn;
+      s += am[mm] * cn + am[15 + mm] * sn;
     }
     yp[k] = s - mean * mean;  // flux.py:320
   }
@@ -221,9 +244,9 @@ extern "C" int spb_flux_operator(spb_context *ctx, int nu, const double *u, doub
 
 extern "C" size_t spb_flux_marginal_workspace_bytes(const spb_context *ctx, int B) {
   (void)ctx;
-  size_t bytes = (size_t)16 * 65536 * 8;                 // Omega(u)
+  size_t bytes = (size_t)31 * 65536 * 8;                 // Omega(u)
   bytes += (size_t)MARG_KSPLIT * B * 64 * 8;             // split-K partials
-  bytes += (size_t)B * 16 * 8;                           // mu part
+  bytes += (size_t)B * 32 * 8;                           // mu part
   return bytes + 1024;
 }
 
@@ -239,7 +262,7 @@ extern "C" int spb_flux_marginal(spb_context *ctx, int B, const double *mean_ylm
   cudaStream_t stream = (cudaStream_t)stream_;
   SPB_CHECK_CUDA(cudaSetDevice(ctx->device));
   double *omega_u = reinterpret_cast<double *>(workspace);
-  double *part = omega_u + (size_t)16 * 65536;
+  double *part = omega_u + (size_t)31 * 65536;
   double *amu = part + (size_t)MARG_KSPLIT * B * 64;
 
   MargParams mp;
@@ -251,7 +274,7 @@ extern "C" int spb_flux_marginal(spb_context *ctx, int B, const double *mean_ylm
   mp.amu = amu;
   marginal_mu_kernel<<<B, 256, 0, stream>>>(mp);
   SPB_LAUNCH_CHECK(ctx);
-  omega_scale_kernel<<<(16 * 65536 + 255) / 256, 256, 0, stream>>>(ctx->d_tables, rTA1, omega_u);
+  omega_scale_kernel<<<(31 * 65536 + 255) / 256, 256, 0, stream>>>(ctx->d_tables, rTA1, omega_u);
   SPB_LAUNCH_CHECK(ctx);
 
   // acov[b][m] = sum_k cov[b][k] Omega_u[m][k], K = 65536, split-K partials
@@ -268,7 +291,7 @@ extern "C" int spb_flux_marginal(spb_context *ctx, int B, const double *mean_ylm
     d.strideC = 0;
     d.ldc = 64;
     d.M = Bc;
-    d.N = 16;
+    d.N = 31;
     d.K = 65536;
     d.batch = 1;
     d.ksplit = MARG_KSPLIT;

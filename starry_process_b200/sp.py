@@ -248,6 +248,23 @@ class StarryProcess(object):
     def _out(self, t):
         return t if self._batched else t[0]
 
+    # optional per-stage CUDA-event timing (bench.py sets ``_stage_ms`` to a dict)
+    _stage_ms = None
+
+    def _mark(self, name):
+        if self._stage_ms is None:
+            return None
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        self._stage_ms.setdefault(name, []).append((e0, e1))
+        return e1
+
+    @staticmethod
+    def _mark_end(ev):
+        if ev is not None:
+            ev.record()
+
     # ------------------------------------------------------------------ Ylm moments
     def _compute_moments(self):
         if self._mean_ylm is not None:
@@ -258,9 +275,11 @@ class StarryProcess(object):
             cov = torch.empty(B, 256, 256, dtype=torch.float64, device=self.device)
             nbytes = self._lib.spb_ylm_moments_workspace_bytes(self._ctx.handle, B)
             ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+            ev = self._mark("moments")
             _lib.check(self._lib.spb_ylm_moments(
                 self._ctx.handle, B, _ptr(self._r), _ptr(self._a), _ptr(self._b), _ptr(self._c),
                 _ptr(self._n), _ptr(mean), _ptr(cov), _ptr(self._info), _ptr(ws), nbytes, _stream()))
+            self._mark_end(ev)
             del ws
         self._mean_ylm, self._cov_ylm = mean, cov
 
@@ -417,13 +436,17 @@ class StarryProcess(object):
             coef = torch.empty(Bc, 4, nc, dtype=torch.float64, device=dev)
             nb = lib.spb_flux_marginal_workspace_bytes(h, Bc)
             ws = torch.empty(nb, dtype=torch.uint8, device=dev)
+            ev = self._mark("flux_marginal")
             _lib.check(lib.spb_flux_marginal(h, Bc, _ptr(mean_ylm), _ptr(cov_ylm), _ptr(rta1),
                                              self._covpts, _ptr(gp_mean), _ptr(var), _ptr(coef),
                                              _ptr(ws), nb, _stream()))
+            self._mark_end(ev)
+            ev = self._mark("assemble")
             _lib.check(lib.spb_assemble_marginal(h, Bc, nt, _ptr(t), float(p), self._covpts,
                                                  _ptr(coef), _ptr(var), _ptr(gp_mean),
                                                  ctypes.byref(nm), _ptr(K), ldk, _ptr(z), _ptr(info),
                                                  _ptr(ws_as), nb_as, _stream()))
+            self._mark_end(ev)
         else:
             inc_c = inc if inc.numel() == 1 else inc[b0:b1].contiguous()
             Ic = inc_c.numel()
@@ -528,9 +551,25 @@ class StarryProcess(object):
                     resid[:, :, :nt] = (f - bm)[None]
                 else:
                     resid[:, :, :nt] = f[None] - (gp_mean[:, None, None] + bm)
-                _lib.check(lib.spb_cholesky_lnlike(
-                    h, Bc, nt, _ptr(K), ldk, nt * ldk, M, _ptr(resid), ldk, M * ldk,
-                    _ptr(lnlike[b0:b1]), None, None, _ptr(self._info[b0:b1]), _stream()))
+                ev = self._mark("cholesky")
+                if Bc == 1 and M >= 64:
+                    # one factorisation + many right-hand sides (ensemble of light curves sharing
+                    # K): factor on one CTA, then spread the RHS rows over the whole GPU
+                    logdet = torch.empty(1, dtype=torch.float64, device=dev)
+                    quad = torch.empty(M, dtype=torch.float64, device=dev)
+                    _lib.check(lib.spb_cholesky_lnlike(
+                        h, 1, nt, _ptr(K), ldk, nt * ldk, 0, None, ldk, 0, None, None,
+                        _ptr(logdet), _ptr(self._info[b0:b1]), _stream()))
+                    _lib.check(lib.spb_cholesky_solve_rows(h, nt, _ptr(K), ldk, M, _ptr(resid), ldk,
+                                                           _ptr(quad), _stream()))
+                    ll = -0.5 * quad.sum() - M * logdet[0] - 0.5 * nt * M * math.log(2 * math.pi)
+                    flagged = (self._info[b0:b1] != 0) | torch.isnan(ll)
+                    lnlike[b0:b1] = torch.where(flagged, torch.full_like(ll, -float("inf")), ll)
+                else:
+                    _lib.check(lib.spb_cholesky_lnlike(
+                        h, Bc, nt, _ptr(K), ldk, nt * ldk, M, _ptr(resid), ldk, M * ldk,
+                        _ptr(lnlike[b0:b1]), None, None, _ptr(self._info[b0:b1]), _stream()))
+                self._mark_end(ev)
                 del K, resid
         self._z = torch.cat(zs)
         return self._out(lnlike)
