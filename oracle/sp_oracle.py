@@ -361,18 +361,56 @@ def wigner_poly_R(ydeg, cos_alpha=0, sin_alpha=1, cos_gamma=0, sin_gamma=-1):
 # ----------------------------------------------------------------------------------------------
 # math.py:121-139 + ops/eigh/eigh.py:11-20
 # ----------------------------------------------------------------------------------------------
+# The reference supports two eigensolver drivers (ops/eigh/eigh.py:11-26, defaults.py:24
+# `driver="numpy"`): numpy.linalg.eigh (LAPACK dsyevd) and scipy.linalg.eigh with an index subset
+# (dsyevr).  Tests flip this switch to measure how far the REFERENCE's own lnlike moves between its
+# two drivers on the same inputs -- its reproducibility floor, which bounds any third-party parity.
+EIGH_DRIVER = "numpy"
+# Probe only (reference value: 1.0): scales the `w > 1e-15` clip of math.py:134-136.  Noise-level
+# eigenvalues of the rank-deficient moment matrices sit right at that clip; whether one survives
+# depends on the LAPACK build / CPU, and each survivor moves cov_ylm by ~1e-9.
+CLIP_SCALE = 1.0
+
+
 def matrix_sqrt(Q, neig=None, mindiff=1e-15):
     N = Q.shape[0]
     neig = N if neig is None else neig
     try:
-        w, U = np.linalg.eigh(Q)
+        if EIGH_DRIVER == "scipy":
+            w, U = scipy.linalg.eigh(Q, subset_by_index=(N - neig, N - 1))
+        else:
+            w, U = np.linalg.eigh(Q)
     except np.linalg.LinAlgError:
         return np.full((N, neig), np.nan)
     w = np.ascontiguousarray(w[-neig:])
     U = np.ascontiguousarray(U[:, -neig:])
     with np.errstate(invalid="ignore"):
-        sqrtw = np.where(w > mindiff, np.sqrt(w), 0.0)
+        sqrtw = np.where(w > mindiff * CLIP_SCALE, np.sqrt(w), 0.0)
     return U @ np.diag(sqrtw)
+
+
+def reference_noise_floor(fn, ntrials=3):
+    """Relative spread of ``fn(**extra_kwargs_for_OracleProcess)`` (a scalar or array of lnlike
+    values) between the reference's two eigensolver drivers and under ``ntrials`` one-ulp
+    perturbations of the latitude moment matrix: how reproducible the REFERENCE's own number is."""
+    global EIGH_DRIVER, CLIP_SCALE
+    base = np.asarray(fn(), dtype=float)
+    dev = np.zeros_like(base)
+    old = EIGH_DRIVER
+    try:
+        EIGH_DRIVER = "scipy" if old == "numpy" else "numpy"
+        dev = np.maximum(dev, np.abs(np.asarray(fn(), dtype=float) - base))
+    finally:
+        EIGH_DRIVER = old
+    try:
+        for CLIP_SCALE in (0.25, 4.0):   # toggles modes within a factor 4 of the clip
+            dev = np.maximum(dev, np.abs(np.asarray(fn(), dtype=float) - base))
+    finally:
+        CLIP_SCALE = 1.0
+    for k in range(ntrials):
+        dev = np.maximum(dev, np.abs(np.asarray(fn(q_ulp_noise_seed=k), dtype=float) - base))
+    with np.errstate(invalid="ignore", divide="ignore"):
+        return np.where(np.isfinite(base), dev / np.abs(base), 0.0)
 
 
 def cho_factor(A):
@@ -595,7 +633,7 @@ class OracleProcess(object):
                  a=None, b=None, ydeg=15, udeg=2,
                  marginalize_over_inclination=DEFAULTS["marginalize_over_inclination"],
                  normalized=DEFAULTS["normalized"], covpts=DEFAULTS["covpts"], native="port",
-                 skip_longitude_eigh=False, **kwargs):
+                 skip_longitude_eigh=False, q_ulp_noise_seed=None, **kwargs):
         self.nat = get_native(native)
         self.ydeg = int(ydeg)
         self.udeg = int(udeg)
@@ -641,6 +679,14 @@ class OracleProcess(object):
         self.beta = np.exp(np.log(0.5) + b * (lbm - np.log(0.5)))
         R_lat = wigner_poly_R(ydeg, 0, 1, 0, -1)
         q_lat, Q_lat = self.nat.latitude(ydeg, self.udeg, self.alpha, self.beta)
+        if q_ulp_noise_seed is not None:
+            # conditioning probe (NOT part of the reference): perturb the latitude moment matrix by
+            # symmetric relative noise of one unit roundoff, the size of the error any eigensolver /
+            # BLAS / CPU micro-architecture already commits on it.  The spread of lnlike under this
+            # probe is the reference's own reproducibility floor for these hyperparameters.
+            nrng = np.random.default_rng(q_ulp_noise_seed)
+            E = nrng.standard_normal(Q_lat.shape)
+            Q_lat = Q_lat * (1.0 + 1.1e-16 * (E + E.T))
         self.q_lat, self.Q_lat = q_lat, Q_lat
         U_lat, t_lat, T_lat = wigner_integral_tensors(R_lat, q_lat, Q_lat, ydeg)
         self.U_lat = U_lat
