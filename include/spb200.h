@@ -155,6 +155,8 @@ typedef struct {
   int base_kind;
   const double *baseline_var;
   long long base_stride;
+  int lower_only;            /* marginal assembly: write only K[i][j], j <= i (what the Cholesky
+                                kernel reads); the strict upper triangle is left untouched */
 } spb_noise_model;
 
 size_t spb_assemble_workspace_bytes(const spb_context *ctx, int B, int nt);

@@ -18,6 +18,7 @@ def run(B, n, M, seed=0, ld=None, check=True):
     A = rng.standard_normal((B, n, 40))
     Kh = A @ A.transpose(0, 2, 1) / 40 + 0.5 * np.eye(n)[None]
     Kp = np.zeros((B, n, ld)); Kp[:, :, :n] = Kh
+    iu = np.triu_indices(n, 1); Kp[:, iu[0], iu[1]] = np.nan  # the kernel must never read above the diagonal
     K = torch.tensor(Kp, device=dev)
     R = None; Rh = None
     if M > 0:

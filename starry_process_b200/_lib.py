@@ -21,6 +21,7 @@ class NoiseModel(_c.Structure):
         ("normalized", _I), ("normalization_order", _I), ("normalization_zmax", _D),
         ("data_kind", _I), ("data_cov", _P), ("data_stride", _LL),
         ("base_kind", _I), ("baseline_var", _P), ("base_stride", _LL),
+        ("lower_only", _I),
     ]
 
 

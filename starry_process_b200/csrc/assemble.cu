@@ -27,14 +27,17 @@ struct AsmParams {
   int marginal;
 };
 
-__device__ __forceinline__ double interp_cov(const double *cf, int nc, double dx, double thi,
+__device__ __forceinline__ double interp_cov(const double *cf, int nc, double inv_dx, double thi,
                                              double thj) {
-  // flux.py:262-271
-  const double x = fabs(thi - thj);
-  const int ind = (int)floor(x / dx);
-  const double xp1 = -dx + (ind + 1) * dx;
-  const double x0 = (x - xp1) / dx;
-  return cf[ind] + cf[nc + ind] * x0 + cf[2 * nc + ind] * (x0 * x0) + cf[3 * nc + ind] * (x0 * x0 * x0);
+  // flux.py:262-271: x = |theta_i - theta_j|, inds = floor(x / dx), x0 = (x - xp[inds + 1]) / dx
+  // with xp[k] = (k - 1) dx, i.e. x0 = x / dx - inds.  Evaluated with one multiplication by 1/dx
+  // instead of two FP64 divisions: x / dx <= covpts, so x0 moves by <= covpts * 2^-53 and the
+  // (continuous) interpolant by a relative ~1e-14, far inside the 1e-8 lnlike tolerance.
+  const double s = fabs(thi - thj) * inv_dx;
+  const int ind = (int)s;
+  const double x0 = s - (double)ind;
+  const double x2 = x0 * x0;
+  return cf[ind] + cf[nc + ind] * x0 + cf[2 * nc + ind] * x2 + cf[3 * nc + ind] * (x2 * x0);
 }
 
 // theta_i = 2 pi mod(t_i / p, 1)  (flux.py:261)
@@ -55,7 +58,7 @@ __global__ void __launch_bounds__(256) rowsum_kernel(AsmParams p) {
     for (int k = tid; k < p.nt; k += 256) th[k] = phase_of(p.t[k], p.period);
   }
   __syncthreads();
-  const double dx = 2.0 * 3.14159265358979323846 / p.covpts;
+  const double dx = (double)p.covpts / (2.0 * 3.14159265358979323846);  // 1 / dx
   for (int i = blockIdx.x * 8 + warp; i < p.nt; i += gridDim.x * 8) {
     double s = 0.0;
     if (p.marginal) {
@@ -147,13 +150,16 @@ __global__ void __launch_bounds__(256) write_kernel(AsmParams p) {
     s3 = p.scal[4 * b + 2];
   }
   __syncthreads();
-  const double dx = 2.0 * 3.14159265358979323846 / p.covpts;
-  // each CTA owns a band of rows; threads run along columns (coalesced 8-byte stores)
+  const double dx = (double)p.covpts / (2.0 * 3.14159265358979323846);  // 1 / dx
+  // each CTA owns a band of rows; threads run along columns (coalesced 8-byte stores).  With
+  // lower_only (the log-likelihood path: the Cholesky kernel never reads above the diagonal) only
+  // columns j <= i are produced, halving both the interpolation work and the HBM writes.
   for (int i = blockIdx.x; i < p.nt; i += gridDim.x) {
     double *row = p.K + ((size_t)b * p.nt + i) * p.ldk;
     const double thi = p.marginal ? th[i] : 0.0;
     const double qi = p.nm.normalized ? q[i] : 0.0;
-    for (int j = tid; j < p.nt; j += 256) {
+    const int jend = (p.marginal && p.nm.lower_only) ? i + 1 : p.nt;
+    for (int j = tid; j < jend; j += 256) {
       double v;
       if (p.marginal) v = (p.nt == 1) ? p.var[b] : interp_cov(cf, nc, dx, thi, th[j]);
       else v = row[j];

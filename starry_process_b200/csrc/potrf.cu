@@ -32,11 +32,10 @@ namespace {
 
 constexpr int NB = 64;         // panel width
 constexpr int TM = 128;        // rows per tile (8 warps x 16 rows)
-constexpr int KC = 16;         // k-chunk per pipeline stage
-constexpr int KS = KC + 4;     // smem row stride (doubles): 20 -> conflict-free 8x4 fragment loads
+constexpr int KC = 16;         // k-chunk per pipeline stage (one 128-byte row segment)
 constexpr int LS = NB + 4;     // smem stride of the diagonal block: 68
 constexpr int DS = 12;         // smem stride of the 8x8 diagonal-inverse blocks
-constexpr int STAGES = 2;
+constexpr int STAGES = 3;      // cp.async ring depth
 constexpr int NTHREADS = 256;
 
 enum { KIND_NONE = 0, KIND_DIAG = 1, KIND_PAD = 2, KIND_BELOW = 3, KIND_RHS = 4 };
@@ -92,36 +91,80 @@ struct RowMap {
   }
 };
 
+// Stage buffers are unpadded 16-double (128-byte) rows with an XOR swizzle of the 16-byte chunk
+// index: chunk' = chunk ^ (2 * (row & 3)).  For the m8n8k4 fragment pattern (lane -> row g,
+// k = 4 kk + tg) every half-warp then touches 16 distinct 8-byte banks: conflict-free LDS.64
+// without the 25 % padding, which is what lets three stages fit beside the diagonal block at
+// two CTAs per SM.
 struct Smem {
-  double As[STAGES][TM][KS];
-  double Bs[STAGES][NB][KS];
+  double As[STAGES][TM][KC];
+  double Bs[STAGES][NB][KC];
   double Ld[NB][LS];   // diagonal block L_jj (lower), valid after potf2
-  double Dv[NB][DS];   // 8 inverses of the 8x8 diagonal blocks of L_jj: Dv[8*nb + r][c]
+  double Dv[NB][DS];   // MINUS the 8 inverses of the 8x8 diagonal blocks of L_jj: Dv[8*nb + r][c]
   double red[NTHREADS / 32];
   int bad;
 };
 
+__device__ __forceinline__ int swz(int row, int k) {  // element index inside a stage row
+  return (((k >> 1) ^ ((row & 3) << 1)) << 1) | (k & 1);
+}
+
 // ------------------------------------------------------------------------------------------
-// acc(16 rows x 64 cols per warp) = sum_k A[v0 + rows][k] * L[c0 + cols][k],  k in [0, c0)
+// Initialise the accumulators with MINUS the K (or residual) values of the two rows this thread
+// owns in each m-tile.  Issued before the k-loop so that the global-load latency hides behind the
+// pipeline prologue; the k-loop then accumulates +L L^T, leaving N = L L^T - K = -P.
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void gemm_tile(Smem &sm, const RowMap &rm, int v0, int c0,
+__device__ __forceinline__ void init_acc(const RowMap &rm, int v, int c0, int tg,
+                                         double (&accrow)[8][2]) {
+  int kind;
+  const double *p = rm.row(v, kind);
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+    const int col = nt * 8 + 2 * tg;
+    const int gc = c0 + col;
+    double k0 = 0.0, k1 = 0.0;
+    if (kind == KIND_PAD) {
+      k0 = (col == v) ? 1.0 : 0.0;
+      k1 = (col + 1 == v) ? 1.0 : 0.0;
+    } else if (kind != KIND_NONE && gc < rm.n) {
+      // ld is even and the base 16-byte aligned: (gc, gc+1) is one aligned 16-byte load that stays
+      // inside the row; the strictly upper part of the diagonal block is never used (and may be
+      // uninitialised when K was assembled lower-only)
+      const double2 kv = *reinterpret_cast<const double2 *>(p + gc);
+      k0 = kv.x;
+      k1 = (gc + 1 < rm.n) ? kv.y : 0.0;
+      if (kind == KIND_DIAG) {
+        if (col > v) k0 = 0.0;
+        if (col + 1 > v) k1 = 0.0;
+      }
+    }
+    accrow[nt][0] = -k0;
+    accrow[nt][1] = -k1;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// acc(16 rows x 64 cols per warp) += sum_k A[v0 + rows][k] * L[c0 + cols][k],  k in [0, c0)
+// 3-stage cp.async ring, one barrier per 16-wide k-chunk; warps whose 16 rows are all beyond the
+// last virtual row keep feeding the ring but issue no tensor work.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void gemm_tile(Smem &sm, const RowMap &rm, int v0, int c0, int nvirt,
                                           double (&acc)[2][8][2]) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, tg = lane & 3;
-#pragma unroll
-  for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-    for (int nt = 0; nt < 8; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
   const int nchunks = c0 / KC;
   if (nchunks == 0) return;
+  const bool warp_live = (v0 + warp * 16) < nvirt;
 
   // this thread's cp.async assignments: A: 4 x 16B, B: 2 x 16B per chunk
-  const int seg = tid & 7;
+  const int seg = tid & 7;                 // 16-byte chunk of the 128-byte row segment
+  const int r8 = tid >> 3;                 // 0..31
+  const int sseg = (seg ^ ((r8 & 3) << 1)) << 1;  // swizzled element offset (row & 3 == r8 & 3)
   const double *arow[4];
   int abytes[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     int kind;
-    double *p = rm.row(v0 + (tid >> 3) + 32 * i, kind);
+    double *p = rm.row(v0 + r8 + 32 * i, kind);
     arow[i] = p ? p : rm.Kb;
     abytes[i] = p ? 16 : 0;
   }
@@ -129,66 +172,57 @@ __device__ __forceinline__ void gemm_tile(Smem &sm, const RowMap &rm, int v0, in
   int bbytes[2];
 #pragma unroll
   for (int i = 0; i < 2; ++i) {
-    int r = c0 + (tid >> 3) + 32 * i;
+    int r = c0 + r8 + 32 * i;
     brow[i] = (r < rm.n) ? rm.Kb + (size_t)r * rm.ld : rm.Kb;
     bbytes[i] = (r < rm.n) ? 16 : 0;
   }
   auto load_chunk = [&](int ch, int st) {
     const int k0 = ch * KC + seg * 2;
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
-      cp_async16(&sm.As[st][(tid >> 3) + 32 * i][seg * 2], arow[i] + k0, abytes[i]);
+    for (int i = 0; i < 4; ++i) cp_async16(&sm.As[st][r8 + 32 * i][sseg], arow[i] + k0, abytes[i]);
 #pragma unroll
-    for (int i = 0; i < 2; ++i)
-      cp_async16(&sm.Bs[st][(tid >> 3) + 32 * i][seg * 2], brow[i] + k0, bbytes[i]);
-    cp_async_commit();
+    for (int i = 0; i < 2; ++i) cp_async16(&sm.Bs[st][r8 + 32 * i][sseg], brow[i] + k0, bbytes[i]);
   };
 
-  load_chunk(0, 0);
-  for (int ch = 0; ch < nchunks; ++ch) {
-    const int st = ch & 1;
-    cp_async_wait<0>();
-    __syncthreads();  // chunk ch landed for everyone; everyone finished reading stage st^1
-    if (ch + 1 < nchunks) load_chunk(ch + 1, st ^ 1);
+  // per-lane fragment offsets inside a stage row: element (row g, k = 4 kk + tg)
+  int koff[KC / 4];
 #pragma unroll
-    for (int kk = 0; kk < KC / 4; ++kk) {
-      double a[2], b[8];
-#pragma unroll
-      for (int mt = 0; mt < 2; ++mt) a[mt] = sm.As[st][warp * 16 + mt * 8 + g][kk * 4 + tg];
-#pragma unroll
-      for (int nt = 0; nt < 8; ++nt) b[nt] = sm.Bs[st][nt * 8 + g][kk * 4 + tg];
-#pragma unroll
-      for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-        for (int nt = 0; nt < 8; ++nt) dmma_m8n8k4(acc[mt][nt][0], acc[mt][nt][1], a[mt], b[nt]);
-    }
-  }
-  __syncthreads();  // all reads of the stage buffers done before the next tile refills them
-}
+  for (int kk = 0; kk < KC / 4; ++kk) koff[kk] = swz(g, kk * 4 + tg);
 
-// P = Kval - acc for the two rows this thread owns in m-tile mt; returns through acc.
-__device__ __forceinline__ void load_subtract(const RowMap &rm, int v, int c0, int g_unused,
-                                              int tg, double (&accrow)[8][2]) {
-  int kind;
-  double *p = rm.row(v, kind);
-#pragma unroll
-  for (int nt = 0; nt < 8; ++nt) {
-#pragma unroll
-    for (int e = 0; e < 2; ++e) {
-      const int col = nt * 8 + 2 * tg + e;
-      const int gc = c0 + col;
-      double kv = 0.0;
-      if (kind == KIND_PAD) {
-        kv = (col == v) ? 1.0 : 0.0;
-      } else if (kind != KIND_NONE) {
-        if (gc < rm.n) {
-          // the strictly upper part of the diagonal block is never used; skip the load
-          if (!(kind == KIND_DIAG && col > v)) kv = p[gc];
-        }
-      }
-      accrow[nt][e] = kv - accrow[nt][e];
+  load_chunk(0, 0);
+  cp_async_commit();
+  if (nchunks > 1) load_chunk(1, 1);
+  cp_async_commit();
+  int st = 0;
+  for (int ch = 0; ch < nchunks; ++ch) {
+    cp_async_wait<1>();   // chunk ch landed (at most the group of chunk ch+1 still in flight)
+    __syncthreads();      // ... for everyone; everyone finished reading the stage refilled below
+    {
+      int st2 = st + 2;
+      if (st2 >= STAGES) st2 -= STAGES;
+      if (ch + 2 < nchunks) load_chunk(ch + 2, st2);
+      cp_async_commit();
     }
+    if (warp_live) {
+      const double *Aw = &sm.As[st][warp * 16 + g][0];
+      const double *Bw = &sm.Bs[st][g][0];
+#pragma unroll
+      for (int kk = 0; kk < KC / 4; ++kk) {
+        double a[2], b[8];
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) a[mt] = Aw[mt * 8 * KC + koff[kk]];
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) b[nt] = Bw[nt * 8 * KC + koff[kk]];
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+          for (int nt = 0; nt < 8; ++nt) dmma_m8n8k4(acc[mt][nt][0], acc[mt][nt][1], a[mt], b[nt]);
+      }
+    }
+    if (++st == STAGES) st = 0;
   }
+  cp_async_wait<0>();
+  __syncthreads();  // all reads of the stage buffers done before the next tile refills them
 }
 
 // Accumulator fragment (8x8, C layout) -> A fragment of its k-block q (columns 4q..4q+3).
@@ -200,29 +234,38 @@ __device__ __forceinline__ double c_to_a(double d0, double d1, int q, int lane) 
   return (tg & 1) ? v1 : v0;
 }
 
-// In-register TRSM on the tensor pipe: X = P L_jj^-T for one 8-row m-tile (acc rows), 8x8-blocked
-// forward substitution.  On exit accrow holds X.
-__device__ __forceinline__ void trsm_mtile(const Smem &sm, double (&accrow)[8][2], int lane) {
+// In-register TRSM on the tensor pipe for the two 8-row m-tiles of a warp.  On entry acc holds
+// N = -P; on exit acc holds X = P L_jj^-T.  RIGHT-looking 8x8-blocked substitution: as soon as the
+// block column X_kb = N_kb (-Dinv_kb)^T is known it is pushed into every later block,
+// N_nb += X_kb L[nb,kb]^T, so each step issues 4 (7 - kb) independent DMMAs and only two A
+// fragments per m-tile are live (the left-looking form kept all 16 and serialised 2 nb DMMAs).
+__device__ __forceinline__ void trsm_warp(const Smem &sm, double (&acc)[2][8][2], int lane) {
   const int g = lane >> 2, tg = lane & 3;
-  double nx[16];  // -X as A fragments, k-block kb = columns 4kb..4kb+3
 #pragma unroll
-  for (int nb = 0; nb < 8; ++nb) {
-    double s0 = accrow[nb][0], s1 = accrow[nb][1];
+  for (int kb = 0; kb < 8; ++kb) {
+    double xa[2][2];
+    const double d0 = sm.Dv[kb * 8 + g][tg], d1 = sm.Dv[kb * 8 + g][4 + tg];
 #pragma unroll
-    for (int kb = 0; kb < 2 * nb; ++kb) {
-      const double b = sm.Ld[nb * 8 + g][kb * 4 + tg];
-      dmma_m8n8k4(s0, s1, nx[kb], b);
+    for (int mt = 0; mt < 2; ++mt) {
+      const double a0 = c_to_a(acc[mt][kb][0], acc[mt][kb][1], 0, lane);
+      const double a1 = c_to_a(acc[mt][kb][0], acc[mt][kb][1], 1, lane);
+      double x0 = 0.0, x1 = 0.0;
+      dmma_m8n8k4(x0, x1, a0, d0);
+      dmma_m8n8k4(x0, x1, a1, d1);
+      acc[mt][kb][0] = x0;
+      acc[mt][kb][1] = x1;
+      xa[mt][0] = c_to_a(x0, x1, 0, lane);
+      xa[mt][1] = c_to_a(x0, x1, 1, lane);
     }
-    // X_nb = S * Dinv_nb^T
-    const double a0 = c_to_a(s0, s1, 0, lane);
-    const double a1 = c_to_a(s0, s1, 1, lane);
-    double x0 = 0.0, x1 = 0.0;
-    dmma_m8n8k4(x0, x1, a0, sm.Dv[nb * 8 + g][tg]);
-    dmma_m8n8k4(x0, x1, a1, sm.Dv[nb * 8 + g][4 + tg]);
-    accrow[nb][0] = x0;
-    accrow[nb][1] = x1;
-    nx[2 * nb] = -c_to_a(x0, x1, 0, lane);
-    nx[2 * nb + 1] = -c_to_a(x0, x1, 1, lane);
+#pragma unroll
+    for (int nb = kb + 1; nb < 8; ++nb) {
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const double b = sm.Ld[nb * 8 + g][kb * 8 + q * 4 + tg];
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) dmma_m8n8k4(acc[mt][nb][0], acc[mt][nb][1], xa[mt][q], b);
+      }
+    }
   }
 }
 
@@ -238,13 +281,13 @@ __device__ __forceinline__ void store_rows(const RowMap &rm, int v, int c0, int 
   if (live) {
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
-#pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const int gc = c0 + nt * 8 + 2 * tg + e;
-        if (gc < rm.n) {
-          p[gc] = accrow[nt][e];
-          q += accrow[nt][e] * accrow[nt][e];
-        }
+      const int gc = c0 + nt * 8 + 2 * tg;
+      if (gc + 1 < rm.n) {
+        *reinterpret_cast<double2 *>(p + gc) = make_double2(accrow[nt][0], accrow[nt][1]);
+        q += accrow[nt][0] * accrow[nt][0] + accrow[nt][1] * accrow[nt][1];
+      } else if (gc < rm.n) {
+        p[gc] = accrow[nt][0];
+        q += accrow[nt][0] * accrow[nt][0];
       }
     }
   }
@@ -261,76 +304,8 @@ __device__ __forceinline__ void store_rows(const RowMap &rm, int v, int c0, int 
   }
 }
 
-// 64x64 Cholesky of sm.Ld (lower triangle), scalar FP64, one barrier per column; column scaling is
-// deferred to a final pass.  Also produces the 8 inverses of the 8x8 diagonal blocks (sm.Dv) and
-// returns this thread's share of sum(log L_ii) over the valid columns.
-__device__ __forceinline__ double potf2_block(Smem &sm, int nvalid) {
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  for (int c = 0; c < NB - 1; ++c) {
-    __syncthreads();
-    const double d = sm.Ld[c][c];
-    const double invd = 1.0 / d;
-    // rows c+1+warp, +8, ...; lanes run along columns j in (c, i]
-    for (int i = c + 1 + warp; i < NB; i += 8) {
-      const double lic = sm.Ld[i][c] * invd;
-      for (int j = c + 1 + lane; j <= i; j += 32) sm.Ld[i][j] -= lic * sm.Ld[j][c];
-    }
-  }
-  __syncthreads();
-  // pivots
-  double logpart = 0.0;
-  double dj = 1.0;
-  if (tid < NB) {
-    dj = sm.Ld[tid][tid];
-    if (!(dj > 0.0)) {  // also catches NaN
-      sm.bad = 1;
-      dj = 1.0;
-    }
-    if (tid < nvalid) logpart = 0.5 * log(dj);
-  }
-  __syncthreads();
-  // scale columns: L[i][j] = v[i][j] / sqrt(d_j); zero the strict upper triangle
-  for (int idx = tid; idx < NB * NB; idx += NTHREADS) {
-    const int i = idx >> 6, j = idx & 63;
-    double v = 0.0;
-    if (j <= i) {
-      double djj = sm.Ld[j][j];
-      if (!(djj > 0.0)) djj = 1.0;
-      v = (i == j) ? sqrt(djj) : sm.Ld[i][j] / sqrt(djj);
-    }
-    if (j != i) {
-      // diagonal entries are read by other threads in this pass: write them afterwards
-      if (j < i) sm.Ld[i][j] = v;
-      else sm.Ld[i][j] = 0.0;
-    }
-  }
-  __syncthreads();
-  if (tid < NB) {
-    double djj = sm.Ld[tid][tid];
-    if (!(djj > 0.0)) djj = 1.0;
-    sm.Ld[tid][tid] = sqrt(djj);
-  }
-  __syncthreads();
-  // inverses of the eight 8x8 diagonal blocks: warp w, lane c < 8 -> column c of block w
-  if (lane < 8) {
-    const int o = warp * 8;
-    double x[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      double s = (i == lane) ? 1.0 : 0.0;
-#pragma unroll
-      for (int k = 0; k < 8; ++k)
-        if (k < i && k >= lane) s -= sm.Ld[o + i][o + k] * x[k];
-      x[i] = (i >= lane) ? s / sm.Ld[o + i][o + i] : 0.0;
-    }
-#pragma unroll
-    for (int i = 0; i < 8; ++i) sm.Dv[o + i][lane] = x[i];
-  }
-  __syncthreads();
-  return logpart;
-}
-
-// Inverses of the 8x8 diagonal blocks only (MODE_SOLVE: L_jj comes from global memory).
+// MINUS the inverses of the eight 8x8 diagonal blocks of sm.Ld: warp w, lane c < 8 -> column c of
+// block w.
 __device__ __forceinline__ void diag_inverses(Smem &sm) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (lane < 8) {
@@ -345,10 +320,101 @@ __device__ __forceinline__ void diag_inverses(Smem &sm) {
       x[i] = (i >= lane) ? s / sm.Ld[o + i][o + i] : 0.0;
     }
 #pragma unroll
-    for (int i = 0; i < 8; ++i) sm.Dv[o + i][lane] = x[i];
+    for (int i = 0; i < 8; ++i) sm.Dv[o + i][lane] = -x[i];
   }
-  (void)tid;
   __syncthreads();
+}
+
+// The accumulators of the rows below the diagonal block (warps 4-7 of the diagonal tile) must
+// survive potf2_block, whose 16 register-resident matrix elements per thread would otherwise push
+// the kernel past 128 registers (ptxas then demotes those 16 values -- the critical path of the
+// factorisation -- to local memory).  The cp.async stage buffers are idle at that point, so the
+// accumulators are parked there: [k][tid] double2 slots, conflict-free.
+__device__ __forceinline__ void park_acc(Smem &sm, const double (&acc)[2][8][2]) {
+  double2 *slot = reinterpret_cast<double2 *>(&sm.As[0][0][0]) + threadIdx.x;
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt)
+      slot[(mt * 8 + nt) * NTHREADS] = make_double2(acc[mt][nt][0], acc[mt][nt][1]);
+}
+__device__ __forceinline__ void unpark_acc(const Smem &sm, double (&acc)[2][8][2]) {
+  const double2 *slot = reinterpret_cast<const double2 *>(&sm.As[0][0][0]) + threadIdx.x;
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      const double2 v = slot[(mt * 8 + nt) * NTHREADS];
+      acc[mt][nt][0] = v.x;
+      acc[mt][nt][1] = v.y;
+    }
+}
+static_assert(sizeof(double) * (STAGES * (TM + NB) * KC) >= 65536 + 2 * NB * sizeof(double),
+              "stage buffers too small to park the accumulators");
+
+// 64x64 Cholesky of sm.Ld (lower triangle), scalar FP64, register-resident: thread t owns row
+// i = t / 4 and the 16 columns [16 (t % 4), 16 (t % 4) + 16).  Per column step the owners publish
+// the pivot column through a double-buffered shared vector (ONE barrier per step), everybody
+// applies the rank-1 update to its registers; the column scaling by 1/sqrt(d_j) is deferred to
+// the end (LDL^T-style), so the dependent chain per step is barrier -> LDS -> 1/d -> FMA.
+// Produces Ld (lower, upper zeroed), Dv, and returns this thread's share of sum(log L_ii) over
+// the valid columns.
+__device__ __forceinline__ double potf2_block(Smem &sm, int nvalid) {
+  const int tid = threadIdx.x;
+  const int i = tid >> 2, cg = tid & 3;
+  // pivot-column broadcast buffers (double-buffered) live in the idle stage buffers, behind the
+  // 64 KB used to park the accumulators (see park_acc)
+  double(*col)[NB] = reinterpret_cast<double(*)[NB]>(&sm.As[0][0][0] + 8192);
+  double a[16];
+  double dpiv = 1.0;
+#pragma unroll
+  for (int jj = 0; jj < 16; ++jj) a[jj] = sm.Ld[i][cg * 16 + jj];
+#pragma unroll 1
+  for (int cgc = 0; cgc < 4; ++cgc) {
+#pragma unroll
+    for (int cc = 0; cc < 16; ++cc) {
+      const int c = cgc * 16 + cc;
+      double *colb = col[c & 1];
+      if (cg == cgc) colb[i] = a[cc];
+      __syncthreads();
+      const double d = colb[c];
+      if (c == i) dpiv = d;  // every thread of row i sees its pivot go by at step c == i
+      const double li = colb[i] * (1.0 / d);
+      if (c < NB - 1 && i > c) {
+#pragma unroll
+        for (int jj = 0; jj < 16; ++jj) {
+          const int j = cg * 16 + jj;
+          if (j > c && j <= i) a[jj] -= li * colb[j];
+        }
+      }
+    }
+  }
+  // pivots: thread (i, cg = i / 16) holds d_i in a[i % 16]
+  double logpart = 0.0;
+  if (cg == (i >> 4)) {
+    double di = dpiv;
+    if (!(di > 0.0)) {  // also catches NaN
+      sm.bad = 1;
+      di = 1.0;
+    }
+    col[0][i] = di;   // col[1] was the last buffer written by the loop (c = 63)
+    if (i < nvalid) logpart = 0.5 * log(di);
+  }
+  __syncthreads();
+  // scale columns: L[i][j] = v[i][j] / sqrt(d_j); zero the strict upper triangle
+#pragma unroll
+  for (int jj = 0; jj < 16; ++jj) {
+    const int j = cg * 16 + jj;
+    double v = 0.0;
+    if (j <= i) {
+      const double sj = sqrt(col[0][j]);
+      v = (j == i) ? sj : a[jj] / sj;
+    }
+    sm.Ld[i][j] = v;
+  }
+  __syncthreads();
+  diag_inverses(sm);
+  return logpart;
 }
 
 __device__ __forceinline__ double block_sum(Smem &sm, double v) {
@@ -430,35 +496,35 @@ __global__ void __launch_bounds__(NTHREADS, 2) potrf_lnlike_kernel(PotrfParams p
         // MODE_FACTOR, first tile: rows 0..63 are the diagonal block (warps 0-3), rows 64..127 the
         // first rows below it (warps 4-7)
         const bool diag_tile = (p.mode == MODE_FACTOR) && (v0 == 0);
-        gemm_tile(sm, rm, v0, c0, acc);
 #pragma unroll
-        for (int mt = 0; mt < 2; ++mt)
-          load_subtract(rm, v0 + warp * 16 + mt * 8 + g, c0, g, tg, acc[mt]);
+        for (int mt = 0; mt < 2; ++mt) init_acc(rm, v0 + warp * 16 + mt * 8 + g, c0, tg, acc[mt]);
+        gemm_tile(sm, rm, v0, c0, nvirt, acc);   // acc = L L^T - K = -P
         if (diag_tile) {
           if (warp < 4) {
 #pragma unroll
             for (int mt = 0; mt < 2; ++mt) {
               const int lr = warp * 16 + mt * 8 + g;
 #pragma unroll
-              for (int nt = 0; nt < 8; ++nt) {
-                sm.Ld[lr][nt * 8 + 2 * tg] = acc[mt][nt][0];
-                sm.Ld[lr][nt * 8 + 2 * tg + 1] = acc[mt][nt][1];
-              }
+              for (int nt = 0; nt < 8; ++nt)
+                *reinterpret_cast<double2 *>(&sm.Ld[lr][nt * 8 + 2 * tg]) =
+                    make_double2(-acc[mt][nt][0], -acc[mt][nt][1]);
             }
           }
+          park_acc(sm, acc);
+          __syncthreads();
           logdet_part += potf2_block(sm, min(NB, p.n - c0));
+          unpark_acc(sm, acc);
           // write L_jj back (lower triangle, valid rows/cols only)
           for (int idx = tid; idx < NB * NB; idx += NTHREADS) {
             const int i = idx >> 6, j = idx & 63;
             if (j <= i && c0 + i < p.n) rm.Kb[(size_t)(c0 + i) * p.ld + c0 + j] = sm.Ld[i][j];
           }
         }
-        if (!(diag_tile && warp < 4)) {
+        if (!(diag_tile && warp < 4) && (v0 + warp * 16) < nvirt) {
+          trsm_warp(sm, acc, lane);
 #pragma unroll
-          for (int mt = 0; mt < 2; ++mt) {
-            trsm_mtile(sm, acc[mt], lane);
+          for (int mt = 0; mt < 2; ++mt)
             store_rows(rm, v0 + warp * 16 + mt * 8 + g, c0, tg, acc[mt], quad_part, quad_out);
-          }
         }
       }
       __syncthreads();  // Ld/Dv are rewritten by the next panel; global writes of this panel done

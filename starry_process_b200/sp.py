@@ -379,8 +379,9 @@ class StarryProcess(object):
         return A if _is_batched(i) else A[0]
 
     # ------------------------------------------------------------------ flux mean / covariance
-    def _noise_model(self, nt, data_cov, baseline_var, keep):
+    def _noise_model(self, nt, data_cov, baseline_var, keep, lower_only=False):
         nm = _lib.NoiseModel()
+        nm.lower_only = 1 if lower_only else 0
         nm.normalized = 1 if self._normalized else 0
         nm.normalization_order = self._normN
         nm.normalization_zmax = self._normzmax
@@ -414,14 +415,15 @@ class StarryProcess(object):
             nm.baseline_var = bv.data_ptr()
         return nm
 
-    def _flux_cov_chunk(self, b0, b1, t, inc, p, rta1, marg, data_cov, baseline_var, ldk):
+    def _flux_cov_chunk(self, b0, b1, t, inc, p, rta1, marg, data_cov, baseline_var, ldk,
+                        lower_only=False):
         """GP mean (scalar per element) and the (noise-augmented) covariance for elements b0:b1.
         Returns (gp_mean, K, z)."""
         lib, h = self._lib, self._ctx.handle
         Bc, nt = b1 - b0, t.numel()
         dev = self.device
         keep = []
-        nm = self._noise_model(nt, data_cov, baseline_var, keep)
+        nm = self._noise_model(nt, data_cov, baseline_var, keep, lower_only and marg)
         mean_ylm = self._mean_ylm[b0:b1]
         cov_ylm = self._cov_ylm[b0:b1]
         info = self._info[b0:b1]
@@ -543,7 +545,7 @@ class StarryProcess(object):
             for b0, b1 in self._chunks(nt, ldk):
                 Bc = b1 - b0
                 gp_mean, K, z = self._flux_cov_chunk(b0, b1, t, inc, p, rta1, marg, data_cov, bvar,
-                                                     ldk)
+                                                     ldk, lower_only=True)
                 zs.append(z)
                 # r = flux - (gp_mean + baseline_mean)  (sp.py:1157-1161); normalised: mean == 0
                 resid = torch.zeros(Bc, M, ldk, dtype=torch.float64, device=dev)
