@@ -320,16 +320,32 @@ def run_b200(args):
     # ---- CPU baseline: bounded sample of the same workload on the host cores
     cb_value, cb_kind, cb_out = cpu_evals(hp, t, flux, args.cpu_evals, args.workload, fens)
     parity = None
+    parity_golden = None
     if args.workload == "sweep":
-        llh = ll.cpu().numpy()[: args.cpu_evals]
+        llall = ll.cpu().numpy()
+        llh = llall[: args.cpu_evals]
         ref = np.array(cb_out)
         fin = np.isfinite(ref)
         parity = float(np.max(np.abs(llh[fin] - ref[fin]) / np.abs(ref[fin]))) if fin.any() else None
+        # the same first samples evaluated by the UNMODIFIED reference in the build container
+        # (tests/golden/bench_sweep_seed1234.npz, oracle/gen_golden_bench.py).  This is the parity
+        # figure: the live oracle on this host is only reproducible to ~1e-6 across CPUs
+        # (DESIGN.md "numerical fragility"), the fixture is what every golden file was made with.
+        gpath = os.path.join(ROOT, "tests", "golden", "bench_sweep_seed1234.npz")
+        if os.path.exists(gpath) and B >= 64:
+            gref = np.load(gpath)["lnlike_m1_n1"]
+            gfin = np.isfinite(gref)
+            same_inf = bool(np.array_equal(np.isneginf(gref), np.isneginf(llall[:64])))
+            parity_golden = {
+                "max_rel": float(np.max(np.abs(llall[:64][gfin] - gref[gfin]) / np.abs(gref[gfin]))),
+                "n": 64, "neg_inf_pattern_equal": same_inf, "tolerance": 1e-8}
     cpu_baseline = {
         "value": cb_value, "unit": "evals/s", "cores": os.cpu_count(), "kind": cb_kind,
         "sample": "%d evaluations of the same workload, oracle on the host (LAPACK multithreaded)"
                   % (args.cpu_evals if args.workload == "sweep" else 1024),
         "max_rel_lnlike_diff_vs_gpu_on_sample": parity,
+        "note": "live oracle on THIS host; the reference algorithm moves by up to ~3e-6 between "
+                "CPUs (LAPACK kernel selection), see parity_vs_reference_golden for the pinned check",
     }
     line = {
         "metric": METRIC, "value": value, "unit": "evals/s", "n_gpus": world, "steps": args.steps,
@@ -343,6 +359,7 @@ def run_b200(args):
                 "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps},
         "gpu_launches": int(launches),
         "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
+        "parity_vs_reference_golden": parity_golden,
     }
     print(json.dumps(line))
     if world > 1:

@@ -44,6 +44,7 @@ LAYOUT = [
     ("FLUX_W", N * N),
     ("FLUX_OMEGA", 31 * N * N),
     ("RX90", NWIG),
+    ("RX90_NZ", 1372),
     ("GL_X", 32),
     ("GL_W", 32),
     ("LAMBDA", N),
@@ -286,6 +287,25 @@ def rx_numeric(theta, ydeg=YDEG):
     return np.concatenate([x.reshape(-1) for x in R])
 
 
+def rx90_nonzeros(rx90):
+    """Structural non-zeros of the packed Rx(pi/2): a rotation by pi/2 about x commutes with the
+    reflections x -> -x and (y, z) -> (z, -y) ..., so each (2l+1)^2 block is a 4-way permuted block
+    diagonal and only 1372 of the 5456 entries are non-zero (the rest are <= 6e-16, against
+    >= 6e-5 for the true entries).  Returned in the order the unrolled design-matrix kernel
+    consumes them (csrc/gen_design.py): degree l, output column m, then source row m'.
+    Returns (values, [(l, mp_index, m_index), ...])."""
+    vals, idx = [], []
+    for l in range(YDEG + 1):
+        w = 2 * l + 1
+        blk = rx90[nwig(l - 1):nwig(l)].reshape(w, w)
+        for j in range(w):
+            for mp in range(w):
+                if abs(blk[mp, j]) > 1e-12:
+                    vals.append(blk[mp, j])
+                    idx.append((l, mp, j))
+    return np.array(vals), idx
+
+
 def _blockdiag(packed):
     M = np.zeros((N, N))
     for l in range(YDEG + 1):
@@ -425,6 +445,7 @@ def build_tables(use_pinned_longitude=True):
     #       = <Omega_m, Sigma> + (mu-part),  Omega_m[p, q] = sum_{i in group m} Rx[p, i] (Wnp Rx^T)[i, q]
     rx90 = rx_numeric(0.5 * np.pi)
     put("RX90", rx90)
+    put("RX90_NZ", rx90_nonzeros(rx90)[0])
     Rx = _blockdiag(rx90).astype(np.longdouble)
     WR = Wnp.astype(np.longdouble) @ Rx.T
     #   b_m = sum_{i in group m} sgn(m_i) sum_j W_ij Ez_{i jbar}   (the sine lane of wigner.h:440-458;

@@ -2,6 +2,9 @@
 #include <mutex>
 
 #include "common.cuh"
+#include "spb_tables.h"
+
+int spb_wigner_init(spb_context *ctx);  // wigner.cu: constant-bank copy of the Rx(pi/2) non-zeros
 
 static thread_local std::string g_last_error;
 
@@ -31,6 +34,10 @@ extern "C" int spb_create(int device, const double *tables_host, size_t tables_c
     SPB_CHECK_CUDA(cudaMalloc(&ctx->d_tables, tables_count * sizeof(double)));
     SPB_CHECK_CUDA(cudaMemcpy(ctx->d_tables, tables_host, tables_count * sizeof(double),
                               cudaMemcpyHostToDevice));
+    if (tables_count == SPB_TAB_TOTAL) {
+      int st = spb_wigner_init(ctx);
+      if (st) return st;
+    }
   }
   *out = ctx;
   return 0;

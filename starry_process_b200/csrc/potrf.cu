@@ -100,7 +100,7 @@ struct Smem {
   double As[STAGES][TM][KC];
   double Bs[STAGES][NB][KC];
   double Ld[NB][LS];   // diagonal block L_jj (lower), valid after potf2
-  double Dv[NB][DS];   // MINUS the 8 inverses of the 8x8 diagonal blocks of L_jj: Dv[8*nb + r][c]
+  double Dv[NB][DS];   // the 8 inverses of the 8x8 diagonal blocks of L_jj: Dv[8*nb + r][c]
   double red[NTHREADS / 32];
   int bad;
 };
@@ -109,15 +109,34 @@ __device__ __forceinline__ int swz(int row, int k) {  // element index inside a 
   return (((k >> 1) ^ ((row & 3) << 1)) << 1) | (k & 1);
 }
 
+__device__ __forceinline__ double negate(double x) {  // sign flip on the integer pipe
+  return __hiloint2double(__double2hiint(x) ^ (int)0x80000000, __double2loint(x));
+}
+
 // ------------------------------------------------------------------------------------------
-// Initialise the accumulators with MINUS the K (or residual) values of the two rows this thread
-// owns in each m-tile.  Issued before the k-loop so that the global-load latency hides behind the
-// pipeline prologue; the k-loop then accumulates +L L^T, leaving N = L L^T - K = -P.
+// Initialise the accumulators with the K (or residual) values of the two rows this thread owns in
+// each m-tile; the k-loop then accumulates (-L) L^T, leaving the Schur complement
+// P = K - L L^T.  `full` (block-uniform: the whole 64-column panel lies inside the matrix, so no
+// padding rows/columns exist) selects the fast path: plain 16-byte loads straight into the
+// accumulator registers with NO dependent instruction, so that their HBM latency overlaps the
+// cp.async prologue of the k-loop instead of stalling the warp before it starts.  Rows past the
+// last virtual row load a dummy row (never stored); the strictly upper part of the diagonal block
+// may be uninitialised memory (lower-only assembly) and is never consumed.
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void init_acc(const RowMap &rm, int v, int c0, int tg,
+__device__ __forceinline__ void init_acc(const RowMap &rm, int v, int c0, int tg, bool full,
                                          double (&accrow)[8][2]) {
   int kind;
   const double *p = rm.row(v, kind);
+  if (full) {
+    if (p == nullptr) p = rm.Kb;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      const double2 kv = *reinterpret_cast<const double2 *>(p + c0 + nt * 8 + 2 * tg);
+      accrow[nt][0] = kv.x;
+      accrow[nt][1] = kv.y;
+    }
+    return;
+  }
 #pragma unroll
   for (int nt = 0; nt < 8; ++nt) {
     const int col = nt * 8 + 2 * tg;
@@ -128,8 +147,7 @@ __device__ __forceinline__ void init_acc(const RowMap &rm, int v, int c0, int tg
       k1 = (col + 1 == v) ? 1.0 : 0.0;
     } else if (kind != KIND_NONE && gc < rm.n) {
       // ld is even and the base 16-byte aligned: (gc, gc+1) is one aligned 16-byte load that stays
-      // inside the row; the strictly upper part of the diagonal block is never used (and may be
-      // uninitialised when K was assembled lower-only)
+      // inside the row
       const double2 kv = *reinterpret_cast<const double2 *>(p + gc);
       k0 = kv.x;
       k1 = (gc + 1 < rm.n) ? kv.y : 0.0;
@@ -138,13 +156,13 @@ __device__ __forceinline__ void init_acc(const RowMap &rm, int v, int c0, int tg
         if (col + 1 > v) k1 = 0.0;
       }
     }
-    accrow[nt][0] = -k0;
-    accrow[nt][1] = -k1;
+    accrow[nt][0] = k0;
+    accrow[nt][1] = k1;
   }
 }
 
 // ------------------------------------------------------------------------------------------
-// acc(16 rows x 64 cols per warp) += sum_k A[v0 + rows][k] * L[c0 + cols][k],  k in [0, c0)
+// acc(16 rows x 64 cols per warp) -= sum_k A[v0 + rows][k] * L[c0 + cols][k],  k in [0, c0)
 // 3-stage cp.async ring, one barrier per 16-wide k-chunk; warps whose 16 rows are all beyond the
 // last virtual row keep feeding the ring but issue no tensor work.
 // ------------------------------------------------------------------------------------------
@@ -210,7 +228,7 @@ __device__ __forceinline__ void gemm_tile(Smem &sm, const RowMap &rm, int v0, in
       for (int kk = 0; kk < KC / 4; ++kk) {
         double a[2], b[8];
 #pragma unroll
-        for (int mt = 0; mt < 2; ++mt) a[mt] = Aw[mt * 8 * KC + koff[kk]];
+        for (int mt = 0; mt < 2; ++mt) a[mt] = negate(Aw[mt * 8 * KC + koff[kk]]);
 #pragma unroll
         for (int nt = 0; nt < 8; ++nt) b[nt] = Bw[nt * 8 * KC + koff[kk]];
 #pragma unroll
@@ -235,9 +253,9 @@ __device__ __forceinline__ double c_to_a(double d0, double d1, int q, int lane) 
 }
 
 // In-register TRSM on the tensor pipe for the two 8-row m-tiles of a warp.  On entry acc holds
-// N = -P; on exit acc holds X = P L_jj^-T.  RIGHT-looking 8x8-blocked substitution: as soon as the
-// block column X_kb = N_kb (-Dinv_kb)^T is known it is pushed into every later block,
-// N_nb += X_kb L[nb,kb]^T, so each step issues 4 (7 - kb) independent DMMAs and only two A
+// P; on exit acc holds X = P L_jj^-T.  RIGHT-looking 8x8-blocked substitution: as soon as the
+// block column X_kb = P_kb Dinv_kb^T is known it is pushed into every later block,
+// P_nb -= X_kb L[nb,kb]^T, so each step issues 4 (7 - kb) independent DMMAs and only two A
 // fragments per m-tile are live (the left-looking form kept all 16 and serialised 2 nb DMMAs).
 __device__ __forceinline__ void trsm_warp(const Smem &sm, double (&acc)[2][8][2], int lane) {
   const int g = lane >> 2, tg = lane & 3;
@@ -254,8 +272,8 @@ __device__ __forceinline__ void trsm_warp(const Smem &sm, double (&acc)[2][8][2]
       dmma_m8n8k4(x0, x1, a1, d1);
       acc[mt][kb][0] = x0;
       acc[mt][kb][1] = x1;
-      xa[mt][0] = c_to_a(x0, x1, 0, lane);
-      xa[mt][1] = c_to_a(x0, x1, 1, lane);
+      xa[mt][0] = negate(c_to_a(x0, x1, 0, lane));
+      xa[mt][1] = negate(c_to_a(x0, x1, 1, lane));
     }
 #pragma unroll
     for (int nb = kb + 1; nb < 8; ++nb) {
@@ -304,7 +322,7 @@ __device__ __forceinline__ void store_rows(const RowMap &rm, int v, int c0, int 
   }
 }
 
-// MINUS the inverses of the eight 8x8 diagonal blocks of sm.Ld: warp w, lane c < 8 -> column c of
+// The inverses of the eight 8x8 diagonal blocks of sm.Ld: warp w, lane c < 8 -> column c of
 // block w.
 __device__ __forceinline__ void diag_inverses(Smem &sm) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -320,7 +338,7 @@ __device__ __forceinline__ void diag_inverses(Smem &sm) {
       x[i] = (i >= lane) ? s / sm.Ld[o + i][o + i] : 0.0;
     }
 #pragma unroll
-    for (int i = 0; i < 8; ++i) sm.Dv[o + i][lane] = -x[i];
+    for (int i = 0; i < 8; ++i) sm.Dv[o + i][lane] = x[i];
   }
   __syncthreads();
 }
@@ -478,6 +496,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) potrf_lnlike_kernel(PotrfParams p
       rm.c0 = c0;
       rm.nbelow = max(0, p.n - c0 - NB);
       const int nvirt = (p.mode == MODE_FACTOR) ? NB + rm.nbelow + rm.M : rm.nrhs;
+      const bool full_panel = (c0 + NB <= p.n);
       if (p.mode == MODE_SOLVE) {
         // fetch L_jj (identity-padded) and invert its 8x8 diagonal blocks
         for (int idx = tid; idx < NB * NB; idx += NTHREADS) {
@@ -497,8 +516,9 @@ __global__ void __launch_bounds__(NTHREADS, 2) potrf_lnlike_kernel(PotrfParams p
         // first rows below it (warps 4-7)
         const bool diag_tile = (p.mode == MODE_FACTOR) && (v0 == 0);
 #pragma unroll
-        for (int mt = 0; mt < 2; ++mt) init_acc(rm, v0 + warp * 16 + mt * 8 + g, c0, tg, acc[mt]);
-        gemm_tile(sm, rm, v0, c0, nvirt, acc);   // acc = L L^T - K = -P
+        for (int mt = 0; mt < 2; ++mt)
+          init_acc(rm, v0 + warp * 16 + mt * 8 + g, c0, tg, full_panel, acc[mt]);
+        gemm_tile(sm, rm, v0, c0, nvirt, acc);   // acc = K - L L^T = P
         if (diag_tile) {
           if (warp < 4) {
 #pragma unroll
@@ -507,7 +527,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) potrf_lnlike_kernel(PotrfParams p
 #pragma unroll
               for (int nt = 0; nt < 8; ++nt)
                 *reinterpret_cast<double2 *>(&sm.Ld[lr][nt * 8 + 2 * tg]) =
-                    make_double2(-acc[mt][nt][0], -acc[mt][nt][1]);
+                    make_double2(acc[mt][nt][0], acc[mt][nt][1]);
             }
           }
           park_acc(sm, acc);

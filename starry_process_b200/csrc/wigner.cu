@@ -11,6 +11,8 @@
 // multiply/add sequence as the reference's `g++ -O2` build, but PARALLEL over the (m', m) entries
 // of each degree (the reference walks them serially): one CTA per angle, the complex matrices
 // D[l] for all l kept in shared memory (43.6 KB).
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "spb_tables.h"
 
@@ -194,80 +196,107 @@ __global__ void __launch_bounds__(256) tensordotRz_kernel(int K, const double *M
 }
 
 // ------------------------------------------------------------------------------------------
-// Design matrix.  grid = (row tiles of 32 timestamps, inclinations)
-//   v        = rTA1 . Rx(-i)                      (hoisted: identical for every timestamp)
-//   f[t]     = v . Rz(theta_t),  theta_t = 2 pi mod(t/p, 1)
-//   A[t, :]  = f[t] . Rx(pi/2)                    (block diagonal, 5456 MAC per row)
-// thread n owns output column n for the 32 rows of the tile; rows are written as full 2 KB lines.
+// Design matrix  A(t; i, p, u) = rTA1 . Rx(-i) . Rz(theta_t) . Rx(pi/2)      flux.py:88-105
+//
+//   design_v_kernel   v = rTA1 . Rx(-i) once per inclination (identical for every timestamp:
+//                     hoisted out of the reference's tile(rTA1, (nt, 1)) product), stored as the
+//                     pairs (v[n], +-v[mirror(n)]) that the z-rotation consumes
+//   design_rows_kernel  one THREAD per timestamp.  cos/sin(m theta) by the reference's Chebyshev
+//                     recurrences in registers; the row is produced degree by degree by the
+//                     fully unrolled body of design_gen.inc, which visits only the 1372
+//                     structurally non-zero entries of Rx(pi/2) (of 5456) and fetches their values
+//                     as warp-uniform 16-byte shared-memory broadcasts; four finished columns leave
+//                     with one 32-byte store (STG.256: a full DRAM sector per lane, no
+//                     shared-memory transposition).  2048 B written + 8 B read per row: the kernel
+//                     is bound by HBM writes (DESIGN.md "design matrix").
 // ------------------------------------------------------------------------------------------
-constexpr int DM_ROWS = 32;
+constexpr int DM_THREADS = 128;
+constexpr int RX90_NZ = (int)SPB_TAB_RX90_NZ_COUNT;  // 1372
 
 struct DesignParams {
   int I, nt;
-  const double *t, *inc, *period, *rTA1;
-  int rTA1_stride;
-  const double *RxInc;  // (I, 5456)  Rx(-inc)
-  const double *Rx90;   // (5456)
+  const double *t, *period;
+  const double *VV;     // (I, 256, 2)
+  const double *RxNZ;   // (1372) non-zeros of Rx(pi/2), consumption order
   double *A;
 };
 
-__global__ void __launch_bounds__(256) design_kernel(DesignParams p) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  double *Rsh = reinterpret_cast<double *>(smem_raw);  // 5456
-  double *v = Rsh + SPB_NWIG;                          // 256
-  double *fsh = v + 256;                               // DM_ROWS x 256
-  double *csn = fsh + DM_ROWS * 256;                   // DM_ROWS x 32 (cos | sin)
-  const int n = threadIdx.x;
-  const int ii = blockIdx.y;
-  const int t0 = blockIdx.x * DM_ROWS;
+__global__ void __launch_bounds__(256) design_v_kernel(int I, const double *rTA1, int rTA1_stride,
+                                                       const double *RxInc, double *VV) {
+  __shared__ double v[256];
+  const int n = threadIdx.x, ii = blockIdx.x;
+  if (ii >= I) return;
   const int l = (int)floor(sqrt((double)n) + 1e-9);
   const int j = n - l * l, m = j - l, w = 2 * l + 1;
-
-  for (int idx = n; idx < SPB_NWIG; idx += 256) Rsh[idx] = p.Rx90[idx];
   // v[(l, m)] = sum_m' rTA1[(l, m')] Rx(-i)_l[m'][m]   (flux.py:95-96, 74-86)
-  {
-    const double *rt = p.rTA1 + (size_t)ii * p.rTA1_stride + l * l;
-    const double *rx = p.RxInc + (size_t)ii * SPB_NWIG + nwig(l - 1);
-    double acc = 0.0;
-    for (int mp = 0; mp < w; ++mp) acc += rt[mp] * rx[mp * w + j];
-    v[n] = acc;
-  }
-  if (n < DM_ROWS) {
-    const int t = t0 + n;
-    if (t < p.nt) {
-      const double per = p.period ? p.period[ii] : 1.0;
-      const double x = p.t[t] / per;
-      const double theta = 2.0 * 3.14159265358979323846 * (x - floor(x));  // tt.mod(t/p, 1)
-      cheb_cs(theta, csn + n * 32, csn + n * 32 + 16);
+  const double *rt = rTA1 + (size_t)ii * rTA1_stride + l * l;
+  const double *rx = RxInc + (size_t)ii * SPB_NWIG + nwig(l - 1);
+  double acc = 0.0;
+  for (int mp = 0; mp < w; ++mp) acc += rt[mp] * rx[mp * w + j];
+  v[n] = acc;
+  __syncthreads();
+  // f[l^2 + j] = v[l^2 + j] cos(m theta) + v[l^2 + 2l - j] sin(m theta), sin(-|m| theta) folded
+  // into the sign of the partner (wigner.h:319-337)
+  const double vb = v[l * l + 2 * l - j];
+  double2 *out = reinterpret_cast<double2 *>(VV) + (size_t)ii * 256 + n;
+  *out = make_double2(acc, m < 0 ? -vb : vb);
+}
+
+// The 1372 coefficients either come from the constant bank (c_rx90nz: they become direct c[][]
+// operands of the DFMAs, no load instructions at all) or from shared memory (warp-uniform
+// 16-byte broadcasts); the variants are otherwise identical.  DESIGN.md records the measured choice.
+__constant__ double2 c_rx90nz[RX90_NZ / 2];
+
+template <bool CONST_COEF, int MINB>
+__global__ void __launch_bounds__(DM_THREADS, MINB) design_rows_kernel(DesignParams p) {
+  __shared__ double2 Rs2[CONST_COEF ? 1 : RX90_NZ / 2];
+  __shared__ double2 Vs2[256];
+  const int tid = threadIdx.x, ii = blockIdx.y;
+  if (!CONST_COEF)
+    for (int k = tid; k < RX90_NZ / 2; k += DM_THREADS)
+      Rs2[k] = reinterpret_cast<const double2 *>(p.RxNZ)[k];
+  for (int k = tid; k < 256; k += DM_THREADS)
+    Vs2[k] = reinterpret_cast<const double2 *>(p.VV)[(size_t)ii * 256 + k];
+  __syncthreads();
+  const double per = p.period ? p.period[ii] : 1.0;
+  const int ntiles = (p.nt + DM_THREADS - 1) / DM_THREADS;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int t = tile * DM_THREADS + tid;
+    if (t >= p.nt) continue;
+    const double x = p.t[t] / per;
+    const double theta = 2.0 * 3.14159265358979323846 * (x - floor(x));  // tt.mod(t/p, 1)
+    double cs[16], sn[16];
+    cs[0] = 1.0;
+    sn[0] = 0.0;
+    cs[1] = cos(theta);
+    sn[1] = sin(theta);
+#pragma unroll
+    for (int k = 2; k <= SPB_LMAX; ++k) {  // wigner.h:311-316
+      cs[k] = 2.0 * cs[k - 1] * cs[1] - cs[k - 2];
+      sn[k] = 2.0 * sn[k - 1] * cs[1] - sn[k - 2];
+    }
+    double *Arow = p.A + ((size_t)ii * p.nt + t) * 256;
+    double o0, o1, o2, o3;
+    if (CONST_COEF) {
+#define RS2(q) c_rx90nz[q]
+#include "design_gen.inc"
+#undef RS2
+    } else {
+#define RS2(q) Rs2[q]
+#include "design_gen.inc"
+#undef RS2
     }
   }
-  __syncthreads();
-  const int nrows = min(DM_ROWS, p.nt - t0);
-  const double vn = v[n], vb = v[l * l + 2 * l - j];
-  const int am = m < 0 ? -m : m;
-  for (int r = 0; r < nrows; ++r) {
-    const double cm = csn[r * 32 + am];
-    const double sm = (m < 0) ? -csn[r * 32 + 16 + am] : csn[r * 32 + 16 + am];
-    fsh[r * 256 + n] = vn * cm + vb * sm;  // wigner.h:331-337
-  }
-  __syncthreads();
-  double acc[DM_ROWS];
-#pragma unroll
-  for (int r = 0; r < DM_ROWS; ++r) acc[r] = 0.0;
-  const double *rx = Rsh + nwig(l - 1) + j;
-  const double *fl = fsh + l * l;
-  for (int mp = 0; mp < w; ++mp) {
-    const double rv = rx[mp * w];
-#pragma unroll
-    for (int r = 0; r < DM_ROWS; ++r) acc[r] = fma(fl[r * 256 + mp], rv, acc[r]);
-  }
-  double *Ab = p.A + ((size_t)ii * p.nt + t0) * 256 + n;
-#pragma unroll
-  for (int r = 0; r < DM_ROWS; ++r)
-    if (r < nrows) Ab[(size_t)r * 256] = acc[r];
 }
 
 }  // namespace
+
+// called by spb_create once the table blob is resident: fills the constant-bank copy
+int spb_wigner_init(spb_context *ctx) {
+  SPB_CHECK_CUDA(cudaMemcpyToSymbol(c_rx90nz, ctx->d_tables + SPB_TAB_RX90_NZ,
+                                    RX90_NZ * sizeof(double), 0, cudaMemcpyDeviceToDevice));
+  return 0;
+}
 
 extern "C" int spb_Rx(spb_context *ctx, int nang, const double *theta, double *Rx, void *stream) {
   SPB_REQUIRE(ctx != nullptr && nang > 0, "Rx: bad arguments");
@@ -289,7 +318,7 @@ extern "C" int spb_tensordotRz(spb_context *ctx, int K, const double *M, const d
 extern "C" size_t spb_design_matrix_workspace_bytes(const spb_context *ctx, int I, int nt) {
   (void)ctx;
   (void)nt;
-  return (size_t)I * SPB_NWIG * sizeof(double);
+  return (size_t)I * (SPB_NWIG + 512) * sizeof(double);
 }
 
 extern "C" int spb_design_matrix(spb_context *ctx, int I, int nt, const double *t,
@@ -298,34 +327,46 @@ extern "C" int spb_design_matrix(spb_context *ctx, int I, int nt, const double *
                                  size_t workspace_bytes, void *stream_) {
   SPB_REQUIRE(ctx != nullptr && I > 0 && nt > 0, "design_matrix: bad arguments");
   SPB_REQUIRE(ctx->tables_count == SPB_TAB_TOTAL, "design_matrix: context has no constant tables");
-  SPB_REQUIRE(workspace != nullptr && workspace_bytes >= (size_t)I * SPB_NWIG * sizeof(double),
+  SPB_REQUIRE(workspace != nullptr &&
+                  workspace_bytes >= (size_t)I * (SPB_NWIG + 512) * sizeof(double),
               "design_matrix: workspace too small");
+  SPB_REQUIRE(((uintptr_t)A % 32) == 0 && ((uintptr_t)workspace % 16) == 0,
+              "design_matrix: A must be 32-byte aligned (workspace 16-byte)");
+  SPB_REQUIRE(I <= 65535, "design_matrix: too many inclinations for one launch");
   cudaStream_t stream = (cudaStream_t)stream_;
   SPB_CHECK_CUDA(cudaSetDevice(ctx->device));
-  double *RxInc = reinterpret_cast<double *>(workspace);
+  double *VV = reinterpret_cast<double *>(workspace);          // (I, 512), 16-byte aligned
+  double *RxInc = VV + (size_t)I * 512;                        // (I, 5456)
   rx_kernel<<<I, 256, 0, stream>>>(I, inc_rad, -1.0, RxInc);  // Rx(-i), flux.py:96
+  SPB_LAUNCH_CHECK(ctx);
+  design_v_kernel<<<I, 256, 0, stream>>>(I, rTA1, rTA1_stride, RxInc, VV);
   SPB_LAUNCH_CHECK(ctx);
   DesignParams p;
   p.I = I;
   p.nt = nt;
   p.t = t;
-  p.inc = inc_rad;
   p.period = period;
-  p.rTA1 = rTA1;
-  p.rTA1_stride = rTA1_stride;
-  p.RxInc = RxInc;
-  p.Rx90 = ctx->d_tables + SPB_TAB_RX90;
+  p.VV = VV;
+  p.RxNZ = ctx->d_tables + SPB_TAB_RX90_NZ;
   p.A = A;
-  const size_t smem = (SPB_NWIG + 256 + DM_ROWS * 256 + DM_ROWS * 32) * sizeof(double);
-  static bool attr = false;
-  if (!attr) {
-    SPB_CHECK_CUDA(cudaFuncSetAttribute(design_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)smem));
-    attr = true;
+  // row tiles per inclination; CTAs loop over tiles so that the 15 KB table prologue is amortised
+  // once there is more than enough work to fill the GPU (3 CTAs per SM resident)
+  const int ntiles = (nt + DM_THREADS - 1) / DM_THREADS;
+  const long long want = 3LL * ctx->num_sms * 4;
+  int gx = ntiles;
+  if ((long long)ntiles * I > want) {
+    gx = (int)((want + I - 1) / I);
+    if (gx < 1) gx = 1;
+    if (gx > ntiles) gx = ntiles;
   }
-  dim3 grid((nt + DM_ROWS - 1) / DM_ROWS, I);
-  SPB_REQUIRE(I <= 65535, "design_matrix: too many inclinations for one launch");
-  design_kernel<<<grid, 256, smem, stream>>>(p);
+  dim3 grid(gx, I);
+  static const int variant = getenv("SPB_DESIGN_VARIANT") ? atoi(getenv("SPB_DESIGN_VARIANT")) : 0;
+  switch (variant) {
+    case 1: design_rows_kernel<false, 3><<<grid, DM_THREADS, 0, stream>>>(p); break;
+    case 2: design_rows_kernel<true, 2><<<grid, DM_THREADS, 0, stream>>>(p); break;
+    case 3: design_rows_kernel<false, 2><<<grid, DM_THREADS, 0, stream>>>(p); break;
+    default: design_rows_kernel<true, 3><<<grid, DM_THREADS, 0, stream>>>(p); break;
+  }
   SPB_LAUNCH_CHECK(ctx);
   return 0;
 }

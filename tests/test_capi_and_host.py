@@ -159,3 +159,25 @@ def test_gather_lnlike_two_ranks_gloo(tmp_path):
     outs = [p.communicate(timeout=180)[0].decode() for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
     assert all("ok" in o for o in outs)
+
+
+def test_design_unrolled_body_in_sync():
+    """csrc/design_gen.inc (committed) is what csrc/gen_design.py generates from the product's own
+    Rx(pi/2) table, and the sparsity it bakes in is the 1372-entry pattern of that table."""
+    import importlib.util
+
+    from starry_process_b200 import _tables as T
+
+    path = os.path.join(ROOT, "starry_process_b200", "csrc", "gen_design.py")
+    spec = importlib.util.spec_from_file_location("gen_design", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    inc = open(os.path.join(ROOT, "starry_process_b200", "csrc", "design_gen.inc")).read()
+    assert inc == mod.generate()
+    rx90 = T.rx_numeric(0.5 * np.pi)
+    vals, idx = T.rx90_nonzeros(rx90)
+    assert len(vals) == 1372 == dict(T.LAYOUT)["RX90_NZ"]
+    dropped = np.abs(rx90).copy()
+    for (l, mp, j) in idx:
+        dropped[T.nwig(l - 1) + mp * (2 * l + 1) + j] = 0.0
+    assert dropped.max() < 1e-15 and np.abs(vals).min() > 1e-5
