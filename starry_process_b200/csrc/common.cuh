@@ -1,5 +1,6 @@
 // Shared device/host helpers for libspb200 (sm_100a only).
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -21,6 +22,9 @@ struct spb_context {
 };
 
 void spb_set_error(const std::string &msg);
+int spb_encode_tmap_3d_f64(CUtensorMap *out, void *base, unsigned long long d0,
+                           unsigned long long d1, unsigned long long d2, unsigned long long s1,
+                           unsigned long long s2, unsigned b0, unsigned b1, unsigned b2);
 
 #define SPB_CHECK_CUDA(expr)                                                          \
   do {                                                                                \
@@ -68,6 +72,49 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+
+// ---- mbarrier (shared::cta) helpers: asynchronous producer/consumer hand-off without CTA-wide
+// rendezvous.  cp.async completions of the executing thread arrive on the barrier (noinc: the
+// expected count is fixed at init time). ------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count) {
+  unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(a), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.shared::cta.b64 st, [%0];\n}\n" ::"r"(a) : "memory");
+}
+__device__ __forceinline__ void mbar_cp_async_arrive(uint64_t *bar) {
+  unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"(a) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
+  unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile(
+      "{\n.reg .pred p;\nLAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra LAB_DONE;\nbra LAB_WAIT;\nLAB_DONE:\n}\n" ::"r"(a),
+      "r"(parity)
+      : "memory");
+}
+
+// ---- TMA tensor store shared::cta -> global (cp.async.bulk.tensor, 3-D tensor map) ------------
+__device__ __forceinline__ void fence_proxy_async_smem() {
+  asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const void *tmap, const void *ssrc, int c0, int c1,
+                                             int c2) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(ssrc);
+  asm volatile(
+      "cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];\n" ::"l"(tmap),
+      "r"(c0), "r"(c1), "r"(c2), "r"(s)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;\n" ::"n"(N) : "memory");
 }
 
 // ---- 32-byte global store (STG.E.256, sm_100+): one full DRAM sector per lane ------------------

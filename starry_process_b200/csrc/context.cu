@@ -57,3 +57,40 @@ extern "C" int spb_launch_count(const spb_context *ctx, long long *count_host) {
   *count_host = ctx->launches;
   return 0;
 }
+
+// ---------------------------------------------------------------------------------------------
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time libcuda
+// dependency): 3-D fp64 tensor, 128-byte swizzle, used by the TMA store path of the design-matrix
+// kernel.  dim0 is the contiguous dimension; strides in bytes for dims 1 and 2.
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*spb_encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *,
+                                  const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                  const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int spb_encode_tmap_3d_f64(CUtensorMap *out, void *base, unsigned long long d0,
+                           unsigned long long d1, unsigned long long d2, unsigned long long s1,
+                           unsigned long long s2, unsigned b0, unsigned b1, unsigned b2) {
+  static spb_encode_fn fn = nullptr;
+  static std::mutex mu;
+  {
+    std::lock_guard<std::mutex> lock(mu);
+    if (!fn) {
+      void *ptr = nullptr;
+      cudaDriverEntryPointQueryResult qres;
+      SPB_CHECK_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres));
+      SPB_REQUIRE(ptr != nullptr && qres == cudaDriverEntryPointSuccess,
+                  "cuTensorMapEncodeTiled is not available in this driver");
+      fn = reinterpret_cast<spb_encode_fn>(ptr);
+    }
+  }
+  cuuint64_t dims[3] = {d0, d1, d2};
+  cuuint64_t strides[2] = {s1, s2};
+  cuuint32_t box[3] = {b0, b1, b2};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, base, dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  SPB_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (alignment / stride constraints)");
+  return 0;
+}

@@ -102,6 +102,8 @@ struct Smem {
   double Ld[NB][LS];   // diagonal block L_jj (lower), valid after potf2
   double Dv[NB][DS];   // the 8 inverses of the 8x8 diagonal blocks of L_jj: Dv[8*nb + r][c]
   double red[NTHREADS / 32];
+  uint64_t full[STAGES];   // chunk landed: 256 cp.async arrivals (one per thread)
+  uint64_t empty[STAGES];  // chunk consumed: 8 arrivals (one per warp)
   int bad;
 };
 
@@ -163,11 +165,19 @@ __device__ __forceinline__ void init_acc(const RowMap &rm, int v, int c0, int tg
 
 // ------------------------------------------------------------------------------------------
 // acc(16 rows x 64 cols per warp) -= sum_k A[v0 + rows][k] * L[c0 + cols][k],  k in [0, c0)
-// 3-stage cp.async ring, one barrier per 16-wide k-chunk; warps whose 16 rows are all beyond the
-// last virtual row keep feeding the ring but issue no tensor work.
+//
+// 3-slot cp.async ring handed off through mbarriers instead of __syncthreads: every thread's
+// copies of a chunk arrive on full[slot] when they land (cp.async.mbarrier.arrive.noinc), a warp
+// starts on a chunk as soon as that barrier flips and releases the slot on empty[slot] when its
+// fragments are read, and the copies of chunk c+1 are issued (behind empty[slot], i.e. once every
+// warp is past chunk c-2) before chunk c is consumed.  Warps therefore never rendezvous inside
+// the k-loop: one may run a full chunk ahead of the slowest.  `it` is the CTA-uniform running chunk
+// count (slot = it % 3, barrier phase = it / 3) and persists across tiles, panels and matrices.
+// Warps whose 16 rows are all beyond the last virtual row keep feeding the ring but issue no
+// tensor work.
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ void gemm_tile(Smem &sm, const RowMap &rm, int v0, int c0, int nvirt,
-                                          double (&acc)[2][8][2]) {
+                                          unsigned &it, double (&acc)[2][8][2]) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, tg = lane & 3;
   const int nchunks = c0 / KC;
   if (nchunks == 0) return;
@@ -194,12 +204,16 @@ __device__ __forceinline__ void gemm_tile(Smem &sm, const RowMap &rm, int v0, in
     brow[i] = (r < rm.n) ? rm.Kb + (size_t)r * rm.ld : rm.Kb;
     bbytes[i] = (r < rm.n) ? 16 : 0;
   }
-  auto load_chunk = [&](int ch, int st) {
+  // slot / phase of running chunk number x
+  auto issue = [&](int ch, unsigned x) {
+    const unsigned st = x % STAGES;
+    mbar_wait(&sm.empty[st], ((x / STAGES) + 1u) & 1u);  // previous user of the slot fully read
     const int k0 = ch * KC + seg * 2;
 #pragma unroll
     for (int i = 0; i < 4; ++i) cp_async16(&sm.As[st][r8 + 32 * i][sseg], arow[i] + k0, abytes[i]);
 #pragma unroll
     for (int i = 0; i < 2; ++i) cp_async16(&sm.Bs[st][r8 + 32 * i][sseg], brow[i] + k0, bbytes[i]);
+    mbar_cp_async_arrive(&sm.full[st]);
   };
 
   // per-lane fragment offsets inside a stage row: element (row g, k = 4 kk + tg)
@@ -207,20 +221,12 @@ __device__ __forceinline__ void gemm_tile(Smem &sm, const RowMap &rm, int v0, in
 #pragma unroll
   for (int kk = 0; kk < KC / 4; ++kk) koff[kk] = swz(g, kk * 4 + tg);
 
-  load_chunk(0, 0);
-  cp_async_commit();
-  if (nchunks > 1) load_chunk(1, 1);
-  cp_async_commit();
-  int st = 0;
+  issue(0, it);
+  if (nchunks > 1) issue(1, it + 1);
   for (int ch = 0; ch < nchunks; ++ch) {
-    cp_async_wait<1>();   // chunk ch landed (at most the group of chunk ch+1 still in flight)
-    __syncthreads();      // ... for everyone; everyone finished reading the stage refilled below
-    {
-      int st2 = st + 2;
-      if (st2 >= STAGES) st2 -= STAGES;
-      if (ch + 2 < nchunks) load_chunk(ch + 2, st2);
-      cp_async_commit();
-    }
+    const unsigned x = it + ch;
+    const unsigned st = x % STAGES;
+    mbar_wait(&sm.full[st], (x / STAGES) & 1u);  // chunk ch landed, for every thread's copies
     if (warp_live) {
       const double *Aw = &sm.As[st][warp * 16 + g][0];
       const double *Bw = &sm.Bs[st][g][0];
@@ -237,10 +243,12 @@ __device__ __forceinline__ void gemm_tile(Smem &sm, const RowMap &rm, int v0, in
           for (int nt = 0; nt < 8; ++nt) dmma_m8n8k4(acc[mt][nt][0], acc[mt][nt][1], a[mt], b[nt]);
       }
     }
-    if (++st == STAGES) st = 0;
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&sm.empty[st]);
+    // refill: chunk ch + 2 goes to the slot of chunk ch - 1, behind its empty barrier
+    if (ch + 2 < nchunks) issue(ch + 2, x + 2);
   }
-  cp_async_wait<0>();
-  __syncthreads();  // all reads of the stage buffers done before the next tile refills them
+  it += nchunks;
 }
 
 // Accumulator fragment (8x8, C layout) -> A fragment of its k-block q (columns 4q..4q+3).
@@ -457,6 +465,16 @@ __global__ void __launch_bounds__(NTHREADS, 2) potrf_lnlike_kernel(PotrfParams p
   if (p.mode == MODE_FACTOR) nitems = p.B;
   else nitems = (p.M + p.rows_per_cta - 1) / p.rows_per_cta;
 
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&sm.full[s], NTHREADS);
+      mbar_init(&sm.empty[s], NTHREADS / 32);
+    }
+  }
+  __syncthreads();
+  unsigned it = 0;  // running k-chunk count of this CTA (ring slot / barrier phase)
+
   for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
     RowMap rm;
     rm.n = p.n;
@@ -518,7 +536,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) potrf_lnlike_kernel(PotrfParams p
 #pragma unroll
         for (int mt = 0; mt < 2; ++mt)
           init_acc(rm, v0 + warp * 16 + mt * 8 + g, c0, tg, full_panel, acc[mt]);
-        gemm_tile(sm, rm, v0, c0, nvirt, acc);   // acc = K - L L^T = P
+        gemm_tile(sm, rm, v0, c0, nvirt, it, acc);   // acc = K - L L^T = P
         if (diag_tile) {
           if (warp < 4) {
 #pragma unroll
@@ -530,10 +548,12 @@ __global__ void __launch_bounds__(NTHREADS, 2) potrf_lnlike_kernel(PotrfParams p
                     make_double2(acc[mt][nt][0], acc[mt][nt][1]);
             }
           }
+          __syncthreads();  // every warp is out of the k-loop: the ring is idle, park there
           park_acc(sm, acc);
           __syncthreads();
           logdet_part += potf2_block(sm, min(NB, p.n - c0));
           unpark_acc(sm, acc);
+          __syncthreads();  // ring free again before the next tile's copies are issued
           // write L_jj back (lower triangle, valid rows/cols only)
           for (int idx = tid; idx < NB * NB; idx += NTHREADS) {
             const int i = idx >> 6, j = idx & 63;

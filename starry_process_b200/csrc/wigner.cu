@@ -12,6 +12,7 @@
 // of each degree (the reference walks them serially): one CTA per angle, the complex matrices
 // D[l] for all l kept in shared memory (43.6 KB).
 #include <stdlib.h>
+#include <string.h>
 
 #include "common.cuh"
 #include "spb_tables.h"
@@ -242,28 +243,48 @@ __global__ void __launch_bounds__(256) design_v_kernel(int I, const double *rTA1
   *out = make_double2(acc, m < 0 ? -vb : vb);
 }
 
-// The 1372 coefficients either come from the constant bank (c_rx90nz: they become direct c[][]
-// operands of the DFMAs, no load instructions at all) or from shared memory (warp-uniform
-// 16-byte broadcasts); the variants are otherwise identical.  DESIGN.md records the measured choice.
-__constant__ double2 c_rx90nz[RX90_NZ / 2];
+// Store path variants (DESIGN.md records the measured choice):
+//   STORE_TMA = false  four finished columns leave with one 32-byte STG.256 per lane (a full DRAM
+//                      sector); simple, but a warp-wide store touches 32 different lines and costs
+//                      ~45 LSU data-pipe wavefronts, which makes the LSU the limiter;
+//   STORE_TMA = true   the warp collects a (32 timestamps x 16 columns) tile in shared memory --
+//                      128-byte rows in the TMA 128B-swizzle layout, so the lanes' 16-byte stores
+//                      are conflict-free -- and one elected lane hands it to the TMA engine
+//                      (cp.async.bulk.tensor.3d shared -> global through a tensor map of A, which
+//                      also clips the rows past nt); double-buffered per warp, the LSU only sees
+//                      the STS.128.
+// The 1372 coefficients come from shared memory as warp-uniform broadcasts.  (A constant-bank
+// variant -- LDCU into uniform registers -- measured 13 % slower: profiles/r01_time_design_variants.log.)
+constexpr int DM_CW = 16;                        // columns per TMA box (128 bytes)
+constexpr int DM_BOX_BYTES = 32 * DM_CW * 8;     // 32 rows x 128 B = 4096
+constexpr int DM_STAGE_BYTES = (DM_THREADS / 32) * 2 * DM_BOX_BYTES;
 
-template <bool CONST_COEF, int MINB>
-__global__ void __launch_bounds__(DM_THREADS, MINB) design_rows_kernel(DesignParams p) {
-  __shared__ double2 Rs2[CONST_COEF ? 1 : RX90_NZ / 2];
-  __shared__ double2 Vs2[256];
-  const int tid = threadIdx.x, ii = blockIdx.y;
-  if (!CONST_COEF)
-    for (int k = tid; k < RX90_NZ / 2; k += DM_THREADS)
-      Rs2[k] = reinterpret_cast<const double2 *>(p.RxNZ)[k];
+template <bool STORE_TMA>
+__global__ void __launch_bounds__(DM_THREADS, 3)
+    design_rows_kernel(DesignParams p, const __grid_constant__ CUtensorMap tmapA) {
+  extern __shared__ __align__(1024) unsigned char dm_smem[];
+  // the swizzle pattern is a function of the shared-memory ADDRESS: align the tiles to its 1 KB atom
+  unsigned char *stage = dm_smem;                                          // [warp][2][4096]
+  if (STORE_TMA) {
+    const unsigned a = (unsigned)__cvta_generic_to_shared(dm_smem);
+    stage += (1024u - (a & 1023u)) & 1023u;
+  }
+  double2 *Rs2 = reinterpret_cast<double2 *>(stage + (STORE_TMA ? DM_STAGE_BYTES : 0));
+  double2 *Vs2 = Rs2 + RX90_NZ / 2;                                        // 256
+  const int tid = threadIdx.x, ii = blockIdx.y, warp = tid >> 5, lane = tid & 31;
+  for (int k = tid; k < RX90_NZ / 2; k += DM_THREADS)
+    Rs2[k] = reinterpret_cast<const double2 *>(p.RxNZ)[k];
   for (int k = tid; k < 256; k += DM_THREADS)
     Vs2[k] = reinterpret_cast<const double2 *>(p.VV)[(size_t)ii * 256 + k];
   __syncthreads();
+  unsigned char *wstage = stage + warp * 2 * DM_BOX_BYTES;
   const double per = p.period ? p.period[ii] : 1.0;
   const int ntiles = (p.nt + DM_THREADS - 1) / DM_THREADS;
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int t = tile * DM_THREADS + tid;
-    if (t >= p.nt) continue;
-    const double x = p.t[t] / per;
+    if (!STORE_TMA && t >= p.nt) continue;
+    // TMA path: rows past nt are computed on a clamped timestamp and clipped by the tensor map
+    const double x = p.t[t < p.nt ? t : p.nt - 1] / per;
     const double theta = 2.0 * 3.14159265358979323846 * (x - floor(x));  // tt.mod(t/p, 1)
     double cs[16], sn[16];
     cs[0] = 1.0;
@@ -276,25 +297,55 @@ __global__ void __launch_bounds__(DM_THREADS, MINB) design_rows_kernel(DesignPar
       sn[k] = 2.0 * sn[k - 1] * cs[1] - sn[k - 2];
     }
     double *Arow = p.A + ((size_t)ii * p.nt + t) * 256;
+    const int trow0 = tile * DM_THREADS + warp * 32;   // first timestamp of this warp's tile
     double o0, o1, o2, o3;
-    if (CONST_COEF) {
-#define RS2(q) c_rx90nz[q]
-#include "design_gen.inc"
-#undef RS2
-    } else {
 #define RS2(q) Rs2[q]
+    if (STORE_TMA) {
+      // chunk q uses buffer q & 1; before refilling it, the store issued two chunks ago must have
+      // finished reading shared memory (at most the most recent store may still be in flight)
+#define DM_BEGIN(q)                                                                 \
+  do {                                                                              \
+    if (lane == 0) bulk_wait_read<1>();                                             \
+    __syncwarp();                                                                   \
+  } while (0)
+#define DM_STORE4(c, a, b, cc, d)                                                   \
+  do {                                                                              \
+    unsigned char *b_ = wstage + (((c) >> 4) & 1) * DM_BOX_BYTES + lane * 128;      \
+    const int j_ = ((c) & 15) >> 1;                                                 \
+    *reinterpret_cast<double2 *>(b_ + ((j_ ^ (lane & 7)) << 4)) = make_double2(a, b);        \
+    *reinterpret_cast<double2 *>(b_ + (((j_ + 1) ^ (lane & 7)) << 4)) = make_double2(cc, d); \
+  } while (0)
+#define DM_FLUSH(q)                                                                 \
+  do {                                                                              \
+    fence_proxy_async_smem();                                                       \
+    __syncwarp();                                                                   \
+    if (lane == 0) {                                                                \
+      tma_store_3d(&tmapA, wstage + ((q) & 1) * DM_BOX_BYTES, (q) * DM_CW, trow0, ii); \
+      bulk_commit();                                                                \
+    }                                                                               \
+  } while (0)
 #include "design_gen.inc"
-#undef RS2
+#undef DM_BEGIN
+#undef DM_STORE4
+#undef DM_FLUSH
+    } else {
+#define DM_BEGIN(q)
+#define DM_STORE4(c, a, b, cc, d) st_global_256(Arow + (c), a, b, cc, d)
+#define DM_FLUSH(q)
+#include "design_gen.inc"
+#undef DM_BEGIN
+#undef DM_STORE4
+#undef DM_FLUSH
     }
+#undef RS2
   }
+  if (STORE_TMA && lane == 0) bulk_wait_read<0>();  // TMA must be done reading this CTA's shared memory
 }
 
 }  // namespace
 
-// called by spb_create once the table blob is resident: fills the constant-bank copy
 int spb_wigner_init(spb_context *ctx) {
-  SPB_CHECK_CUDA(cudaMemcpyToSymbol(c_rx90nz, ctx->d_tables + SPB_TAB_RX90_NZ,
-                                    RX90_NZ * sizeof(double), 0, cudaMemcpyDeviceToDevice));
+  (void)ctx;
   return 0;
 }
 
@@ -361,11 +412,25 @@ extern "C" int spb_design_matrix(spb_context *ctx, int I, int nt, const double *
   }
   dim3 grid(gx, I);
   static const int variant = getenv("SPB_DESIGN_VARIANT") ? atoi(getenv("SPB_DESIGN_VARIANT")) : 0;
-  switch (variant) {
-    case 1: design_rows_kernel<false, 3><<<grid, DM_THREADS, 0, stream>>>(p); break;
-    case 2: design_rows_kernel<true, 2><<<grid, DM_THREADS, 0, stream>>>(p); break;
-    case 3: design_rows_kernel<false, 2><<<grid, DM_THREADS, 0, stream>>>(p); break;
-    default: design_rows_kernel<true, 3><<<grid, DM_THREADS, 0, stream>>>(p); break;
+  const size_t smem_base = (RX90_NZ / 2 + 256) * sizeof(double2);
+  const size_t smem_tma = smem_base + DM_STAGE_BYTES + 1024;
+  CUtensorMap tmap;
+  memset(&tmap, 0, sizeof(tmap));
+  if (variant != 1) {
+    // 3-D view of A: (256 columns, nt timestamps, I inclinations), box = 16 columns x 32 timestamps,
+    // 128-byte swizzle (matches the kernel's shared-memory tile layout)
+    int st = spb_encode_tmap_3d_f64(&tmap, A, 256, (unsigned long long)nt, (unsigned long long)I,
+                                    256ull * 8, (unsigned long long)nt * 256 * 8, DM_CW, 32, 1);
+    if (st) return st;
+    static bool attr = false;
+    if (!attr) {
+      SPB_CHECK_CUDA(cudaFuncSetAttribute(design_rows_kernel<true>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tma));
+      attr = true;
+    }
+    design_rows_kernel<true><<<grid, DM_THREADS, smem_tma, stream>>>(p, tmap);
+  } else {
+    design_rows_kernel<false><<<grid, DM_THREADS, smem_base, stream>>>(p, tmap);
   }
   SPB_LAUNCH_CHECK(ctx);
   return 0;
