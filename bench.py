@@ -170,6 +170,53 @@ def workload_name(args):
             "one K factorisation + 1024-RHS forward solve")
 
 
+def hbm_peak():
+    """Measured HBM copy bandwidth (driver-written MEASURED_PEAKS.json), else the recipe's fallback."""
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except (OSError, KeyError, ValueError):
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def design_phase(spb, _lib, ctx, dev, torch, I=64, nt=100000, reps=5):
+    lib, h = ctx.lib, ctx.handle
+    P = lambda x: ctypes.c_void_p(x.data_ptr())  # noqa: E731
+    gp = spb.StarryProcess(r=10.0, mu=30.0, sigma=5.0, c=0.1, n=10.0)
+    rta1 = gp._rTA1(U_LD)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(5)
+    t = torch.linspace(0, 40, nt, dtype=torch.float64, device=dev)
+    inc = torch.arccos(torch.rand(I, dtype=torch.float64, device=dev, generator=gen))  # isotropic
+    per = torch.ones(I, dtype=torch.float64, device=dev)
+    A = torch.empty(I, nt, 256, dtype=torch.float64, device=dev)       # 13.1 GB >> L2
+    nb = lib.spb_design_matrix_workspace_bytes(h, I, nt)
+    ws = torch.empty(nb, dtype=torch.uint8, device=dev)
+    stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    times = []
+    for r in range(reps + 3):
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _lib.check(lib.spb_design_matrix(h, I, nt, P(t), P(inc), P(per), P(rta1), 0, P(A), P(ws), nb,
+                                         stream))
+        e1.record()
+        torch.cuda.synchronize()
+        if r >= 3:
+            times.append(e0.elapsed_time(e1))
+    ms = float(np.mean(times))
+    alg_bytes = I * nt * (2048.0 + 8.0)
+    peak, src = hbm_peak()
+    ach = alg_bytes / (ms * 1e-3) / 1e9
+    del A, ws
+    return {"bound": "hbm", "kernel": "design_rows_kernel (+ rx_kernel, design_v_kernel prologue)",
+            "workload": "configs[4]: design matrix, nt=1e5 timestamps x 64 inclinations, u=[0.4,0.26]",
+            "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "peak_source": src,
+            "ms_per_launch": ms, "rows_per_s": I * nt / (ms * 1e-3),
+            "algorithmic_bytes_per_launch": alg_bytes, "traffic": None}
+
+
 # ------------------------------------------------------------------------------------------
 def run_b200(args):
     import torch
@@ -224,7 +271,7 @@ def run_b200(args):
             gp._stage_ms = stage_ms
             ll = gp.log_likelihood(t_d, fe_d, 1e-6, p=1.0, u=U_LD).reshape(1)
         if world > 1:
-            ll = spb.gather_lnlike(ll)
+            ll = spb.gather_lnlike(ll, equal_shards=True)
         return ll
 
     def step_e2e():
@@ -317,6 +364,9 @@ def run_b200(args):
         "algorithmic_flops_per_launch": flops_total / n_launch,
         "stage_ms_total": shares,
     }
+    # ---- design-matrix phase (BASELINE configs[4]: nt = 1e5 timestamps x 64 inclinations), timed in
+    # the same process with CUDA events on the launching stream, against the measured HBM peak
+    phases = {"design_matrix": design_phase(spb, _lib, ctx, dev, torch)}
     # ---- CPU baseline: bounded sample of the same workload on the host cores
     cb_value, cb_kind, cb_out = cpu_evals(hp, t, flux, args.cpu_evals, args.workload, fens)
     parity = None
@@ -359,7 +409,7 @@ def run_b200(args):
                 "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps},
         "gpu_launches": int(launches),
         "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
-        "parity_vs_reference_golden": parity_golden,
+        "parity_vs_reference_golden": parity_golden, "phases": phases,
     }
     print(json.dumps(line))
     if world > 1:

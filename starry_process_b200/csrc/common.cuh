@@ -89,6 +89,17 @@ __device__ __forceinline__ void mbar_cp_async_arrive(uint64_t *bar) {
   unsigned a = (unsigned)__cvta_generic_to_shared(bar);
   asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"(a) : "memory");
 }
+__device__ __forceinline__ bool mbar_test(uint64_t *bar, unsigned parity) {  // non-blocking
+  unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+  unsigned ok;
+  asm volatile(
+      "{\n.reg .pred p;\nmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n}\n"
+      : "=r"(ok)
+      : "r"(a), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
   unsigned a = (unsigned)__cvta_generic_to_shared(bar);
   asm volatile(

@@ -205,15 +205,18 @@ __device__ __forceinline__ void gemm_tile(Smem &sm, const RowMap &rm, int v0, in
     bbytes[i] = (r < rm.n) ? 16 : 0;
   }
   // slot / phase of running chunk number x
-  auto issue = [&](int ch, unsigned x) {
+  auto issue = [&](int ch, unsigned x, bool blocking) -> bool {
     const unsigned st = x % STAGES;
-    mbar_wait(&sm.empty[st], ((x / STAGES) + 1u) & 1u);  // previous user of the slot fully read
+    // previous user of the slot fully read by every warp?
+    if (blocking) mbar_wait(&sm.empty[st], ((x / STAGES) + 1u) & 1u);
+    else if (!mbar_test(&sm.empty[st], ((x / STAGES) + 1u) & 1u)) return false;
     const int k0 = ch * KC + seg * 2;
 #pragma unroll
     for (int i = 0; i < 4; ++i) cp_async16(&sm.As[st][r8 + 32 * i][sseg], arow[i] + k0, abytes[i]);
 #pragma unroll
     for (int i = 0; i < 2; ++i) cp_async16(&sm.Bs[st][r8 + 32 * i][sseg], brow[i] + k0, bbytes[i]);
     mbar_cp_async_arrive(&sm.full[st]);
+    return true;
   };
 
   // per-lane fragment offsets inside a stage row: element (row g, k = 4 kk + tg)
@@ -221,11 +224,16 @@ __device__ __forceinline__ void gemm_tile(Smem &sm, const RowMap &rm, int v0, in
 #pragma unroll
   for (int kk = 0; kk < KC / 4; ++kk) koff[kk] = swz(g, kk * 4 + tg);
 
-  issue(0, it);
-  if (nchunks > 1) issue(1, it + 1);
+  issue(0, it, true);
+  if (nchunks > 1) issue(1, it + 1, true);
   for (int ch = 0; ch < nchunks; ++ch) {
     const unsigned x = it + ch;
     const unsigned st = x % STAGES;
+    // chunk ch + 2 goes to the slot of chunk ch - 1.  If every warp is already past that chunk the
+    // copies are issued NOW (two chunks of latency cover); otherwise after this chunk's math (one
+    // chunk of cover, but a warp never waits for a sibling that is at most one chunk behind).
+    bool early = false;
+    if (ch + 2 < nchunks) early = issue(ch + 2, x + 2, false);
     mbar_wait(&sm.full[st], (x / STAGES) & 1u);  // chunk ch landed, for every thread's copies
     if (warp_live) {
       const double *Aw = &sm.As[st][warp * 16 + g][0];
@@ -245,8 +253,7 @@ __device__ __forceinline__ void gemm_tile(Smem &sm, const RowMap &rm, int v0, in
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&sm.empty[st]);
-    // refill: chunk ch + 2 goes to the slot of chunk ch - 1, behind its empty barrier
-    if (ch + 2 < nchunks) issue(ch + 2, x + 2);
+    if (!early && ch + 2 < nchunks) issue(ch + 2, x + 2, true);
   }
   it += nchunks;
 }

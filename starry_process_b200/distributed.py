@@ -18,12 +18,20 @@ def shard_range(n_items, rank=None, world_size=None):
     return begin, begin + base + (1 if rank < rem else 0)
 
 
-def gather_lnlike(local, n_items=None):
+def gather_lnlike(local, n_items=None, equal_shards=False):
     """All-gather the per-element log-likelihoods of every rank's shard into the full vector
-    (ordered by rank).  ``local`` is this rank's 1-D tensor; shards may differ in length by one."""
+    (ordered by rank).  ``local`` is this rank's 1-D tensor; shards may differ in length by one.
+    ``equal_shards=True`` (every rank holds the same count, e.g. weak scaling) is a single
+    collective with no host synchronisation."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
         return local
     world = dist.get_world_size()
+    if equal_shards:
+        out = torch.empty(world * local.numel(), dtype=local.dtype, device=local.device)
+        dist.all_gather_into_tensor(out, local.contiguous())
+        if n_items is not None:
+            assert out.numel() == n_items
+        return out
     n_local = torch.tensor([local.numel()], dtype=torch.int64, device=local.device)
     sizes = [torch.zeros_like(n_local) for _ in range(world)]
     dist.all_gather(sizes, n_local)

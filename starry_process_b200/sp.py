@@ -166,7 +166,7 @@ class StarryProcess(object):
                 raise NotImplementedError("non-default `%s` is not supported" % key)
         self._normN = int(kwargs.pop("normalization_order", defaults["normalization_order"]))
         self._normzmax = float(kwargs.pop("normalization_zmax", defaults["normalization_zmax"]))
-        self._max_chunk_bytes = int(kwargs.pop("max_chunk_bytes", 24 << 30))
+        self._max_chunk_bytes = int(kwargs.pop("max_chunk_bytes", 48 << 30))
         kwargs.pop("seed", None)
         self._nylm = (self._ydeg + 1) ** 2
         self._covpts = int(covpts)

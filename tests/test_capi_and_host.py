@@ -139,6 +139,10 @@ b, e = shard_range(n)
 full = torch.arange(n, dtype=torch.float64) * 1.5 - 3.0
 out = gather_lnlike(full[b:e].clone(), n)
 assert torch.equal(out, full), (out, full)
+# equal shards (weak scaling): one collective, no host sync
+mine = torch.arange(4, dtype=torch.float64) + 10.0 * dist.get_rank()
+out2 = gather_lnlike(mine, 8, equal_shards=True)
+assert torch.equal(out2, torch.cat([torch.arange(4, dtype=torch.float64), torch.arange(4, dtype=torch.float64) + 10.0])), out2
 dist.barrier()
 dist.destroy_process_group()
 print("ok", sys.argv[1])
