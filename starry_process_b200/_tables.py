@@ -38,6 +38,8 @@ LAYOUT = [
     ("LAT_Z", N * 32),
     ("LAT_H", N * 32),
     ("LAT_R0", NWIG),
+    ("LAT_FAC", 46376),
+    ("LAT_FACOFF", 31 * 31 + 1),
     ("LON_T1", NWIG),
     ("LON_T", NEIG * NWIG),
     ("FLUX_WNP", NWIG),
@@ -371,6 +373,26 @@ def build_tables(use_pinned_longitude=True):
         H[l * l:(l + 1) ** 2, :NEIG] = (r0.astype(np.longdouble)
                                         @ Z[l * l:(l + 1) ** 2].astype(np.longdouble)).astype(
             np.float64)
+    # binomial factors of the double sum term(2a, 2b) (latitude.h:117-143), generated with the
+    # reference's own ratio recurrences (same IEEE operations, same order) so that the kernel can
+    # replace its FP64 divisions by table look-ups without changing a single bit
+    fac_tab = []
+    fac_off = np.zeros(31 * 31 + 1)
+    for a2 in range(31):
+        for b2 in range(31):
+            fac_off[a2 * 31 + b2] = len(fac_tab)
+            if a2 + b2 > 30:
+                continue
+            fac1 = 1.0
+            for k1 in range(a2 + 1):
+                fac2 = fac1
+                for k2 in range(b2 + 1):
+                    fac_tab.append(fac2)
+                    fac2 *= (k2 - b2) / (k2 + 1.0)
+                fac1 *= (a2 - k1) / (k1 + 1.0)
+    fac_off[31 * 31] = len(fac_tab)
+    put("LAT_FAC", np.array(fac_tab))
+    put("LAT_FACOFF", fac_off)
     put("LAT_Z", Zp)
     put("LAT_H", H)
     put("LAT_R0", R0)

@@ -21,6 +21,7 @@ struct AsmParams {
   spb_noise_model nm;
   double *K;              // (B,nt,ldk)
   double *rowq;           // (B,nt)  workspace: row sums, then q_i
+  double *colpart;        // (B,RS_G,nt) workspace: column-sum partials of the symmetric pass
   double *scal;           // (B,4)   workspace: s1, s2, s3
   double *z_out;
   int32_t *info;
@@ -77,13 +78,78 @@ __global__ void __launch_bounds__(256) rowsum_kernel(AsmParams p) {
   }
 }
 
+// ---- pass A', marginal kernel: the covariance is symmetric, so only the strict lower triangle is
+// interpolated (half the evaluations); every value is added to its row sum AND to the sum of its
+// column, which is the row sum of the mirrored element.  Deterministic (no atomics): a warp owns
+// whole rows (interleaved by 64 for balance), lanes own columns j = lane mod 32 and keep their
+// column sums in registers; the 8 warps are combined through shared memory in a fixed order and
+// each of the RS_G CTAs of a sample leaves one partial vector that pass S adds up.
+constexpr int RS_G = 8;      // CTAs per sample
+constexpr int RS_CB = 1024;  // columns per register block (32 per lane)
+
+__global__ void __launch_bounds__(256) rowsum_sym_kernel(AsmParams p) {
+  extern __shared__ double sh[];  // coef (4*nc) | theta (nt) | part (8 x RS_CB)
+  const int b = blockIdx.y, c = blockIdx.x;
+  const int nc = p.covpts + 1;
+  double *cf = sh, *th = sh + 4 * nc, *part = th + p.nt;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int k = tid; k < 4 * nc; k += 256) cf[k] = p.coef[(size_t)b * 4 * nc + k];
+  for (int k = tid; k < p.nt; k += 256) th[k] = phase_of(p.t[k], p.period);
+  __syncthreads();
+  const double dx = (double)p.covpts / (2.0 * 3.14159265358979323846);  // 1 / dx
+  double *rowq = p.rowq + (size_t)b * p.nt;
+  double *colp = p.colpart + ((size_t)b * RS_G + c) * p.nt;
+  for (int cb0 = 0; cb0 < p.nt; cb0 += RS_CB) {
+    double cs[32];
+#pragma unroll
+    for (int k = 0; k < 32; ++k) cs[k] = 0.0;
+    for (int i = c * 8 + warp; i < p.nt; i += RS_G * 8) {
+      if (i < cb0) continue;
+      const double thi = th[i];
+      double rs = 0.0;
+#pragma unroll
+      for (int k = 0; k < 32; ++k) {
+        const int j = cb0 + 32 * k + lane;
+        if (cb0 + 32 * k <= i) {        // warp-uniform
+          if (j < i) {
+            const double v = interp_cov(cf, nc, dx, thi, th[j]);
+            rs += v;
+            cs[k] += v;
+          } else if (j == i) {
+            rs += (p.nt == 1) ? p.var[b] : interp_cov(cf, nc, dx, thi, thi);
+          }
+        }
+      }
+      rs = warp_sum(rs);
+      if (lane == 0) rowq[i] = (cb0 == 0) ? rs : rowq[i] + rs;
+    }
+#pragma unroll
+    for (int k = 0; k < 32; ++k) part[warp * RS_CB + 32 * k + lane] = cs[k];
+    __syncthreads();
+    for (int j = tid; j < RS_CB && cb0 + j < p.nt; j += 256) {
+      double t = 0.0;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) t += part[w * RS_CB + j];
+      colp[cb0 + j] = t;
+    }
+    __syncthreads();
+  }
+}
+
 // ---- pass S: per-sample scalars of the normalisation series ---------------------------------
 __global__ void __launch_bounds__(256) norm_scalars_kernel(AsmParams p) {
   __shared__ double red[8];
   __shared__ double mshare;
   const int b = blockIdx.x, tid = threadIdx.x;
   double s = 0.0;
-  for (int i = tid; i < p.nt; i += 256) s += p.rowq[(size_t)b * p.nt + i];
+  for (int i = tid; i < p.nt; i += 256) {
+    double r = p.rowq[(size_t)b * p.nt + i];
+    if (p.marginal) {  // add the mirrored (column) contributions of the symmetric pass
+      for (int c = 0; c < RS_G; ++c) r += p.colpart[((size_t)b * RS_G + c) * p.nt + i];
+      p.rowq[(size_t)b * p.nt + i] = r;
+    }
+    s += r;
+  }
   s = warp_sum(s);
   if ((tid & 31) == 0) red[tid >> 5] = s;
   __syncthreads();
@@ -177,11 +243,12 @@ int run_assemble(spb_context *ctx, AsmParams &p, void *workspace, size_t workspa
                  cudaStream_t stream) {
   SPB_REQUIRE(p.B > 0 && p.nt > 0 && p.ldk >= p.nt, "assemble: bad arguments");
   SPB_REQUIRE(p.B <= 65535, "assemble: batch too large for one launch");
-  const size_t need = ((size_t)p.B * p.nt + (size_t)p.B * 4) * sizeof(double);
+  const size_t need = ((size_t)p.B * p.nt * (1 + RS_G) + (size_t)p.B * 4) * sizeof(double);
   SPB_REQUIRE(workspace != nullptr && workspace_bytes >= need, "assemble: workspace too small");
   SPB_CHECK_CUDA(cudaSetDevice(ctx->device));
   p.rowq = reinterpret_cast<double *>(workspace);
   p.scal = p.rowq + (size_t)p.B * p.nt;
+  p.colpart = p.scal + (size_t)p.B * 4;
   const int nc = p.covpts + 1;
   const size_t smA = (p.marginal ? (4 * nc + p.nt) : 0) * sizeof(double);
   const size_t smW = smA + (p.nm.normalized ? p.nt : 0) * sizeof(double);
@@ -195,8 +262,21 @@ int run_assemble(spb_context *ctx, AsmParams &p, void *workspace, size_t workspa
     attr = true;
   }
   if (p.nm.normalized) {
-    dim3 gridA(min((p.nt + 7) / 8, 16), p.B);
-    rowsum_kernel<<<gridA, 256, smA, stream>>>(p);
+    if (p.marginal) {
+      static bool attr2 = false;
+      if (!attr2) {
+        SPB_CHECK_CUDA(cudaFuncSetAttribute(rowsum_sym_kernel,
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr2 = true;
+      }
+      const size_t smS = smA + (size_t)8 * RS_CB * sizeof(double);
+      SPB_REQUIRE(smS <= 200 * 1024, "assemble: nt too large for the shared-memory staging");
+      dim3 gridS(RS_G, p.B);
+      rowsum_sym_kernel<<<gridS, 256, smS, stream>>>(p);
+    } else {
+      dim3 gridA(min((p.nt + 7) / 8, 16), p.B);
+      rowsum_kernel<<<gridA, 256, smA, stream>>>(p);
+    }
     SPB_LAUNCH_CHECK(ctx);
     norm_scalars_kernel<<<p.B, 256, 0, stream>>>(p);
     SPB_LAUNCH_CHECK(ctx);
@@ -213,7 +293,7 @@ int run_assemble(spb_context *ctx, AsmParams &p, void *workspace, size_t workspa
 
 extern "C" size_t spb_assemble_workspace_bytes(const spb_context *ctx, int B, int nt) {
   (void)ctx;
-  return ((size_t)B * nt + (size_t)B * 4) * sizeof(double) + 256;
+  return ((size_t)B * nt * (1 + RS_G) + (size_t)B * 4) * sizeof(double) + 256;
 }
 
 extern "C" int spb_assemble_marginal(spb_context *ctx, int B, int nt, const double *t, double period,

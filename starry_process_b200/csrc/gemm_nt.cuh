@@ -70,10 +70,14 @@ __global__ void __launch_bounds__(NTHREADS, 2) gemm_nt_kernel(Desc d) {
   // k-range of this split, in chunks of KC
   int nch_total = (d.K + KC - 1) / KC;
   int kstep = KC;          // distance between consecutive chunk starts
+  int rk4 = 32;            // kept eigen-columns of this batch element, rounded up to 4
   if (d.rkeep) {
-    // sqrtC_lon rows are laid out [e2 (31)][e (32)]; only the first r[b] e-columns are non-zero:
-    // with r <= 16 every second 16-wide chunk is identically zero and is skipped.
-    if (d.rkeep[b] <= 16) {
+    // sqrtC_lon rows are laid out [e2 (31)][e (32)] and only the first rk4 e-columns of every
+    // 32-wide group exist: with rk4 <= 16 every second 16-wide chunk is skipped altogether, and
+    // otherwise the second chunk of each pair is only (rk4 - 16) wide -- its copies and its
+    // DMMA steps are trimmed accordingly (the kernel is L2-bandwidth-bound on these operands).
+    rk4 = (d.rkeep[b] + 3) & ~3;
+    if (rk4 <= 16) {
       nch_total = d.K / 32;
       kstep = 32;
     }
@@ -105,9 +109,16 @@ __global__ void __launch_bounds__(NTHREADS, 2) gemm_nt_kernel(Desc d) {
     bok[i] = r < d.N;
     brow[i] = Bb + (size_t)(bok[i] ? r : 0) * d.ldb;
   }
+  // live width of chunk ch (multiple of 4, <= 16)
+  auto chunk_width = [&](int ch) -> int {
+    if (!d.rkeep) return KC;
+    const int base = (kstep == 32) ? 0 : 16 * (ch & 1);
+    const int wdt = rk4 - base;
+    return wdt > 16 ? 16 : wdt;
+  };
   auto load_chunk = [&](int ch, int st) {
     const int k = ch * kstep + seg * 2;
-    const bool kok = k < d.K;
+    const bool kok = (k < d.K) && (seg * 2 < chunk_width(ch));
     const int kk = kok ? k : 0;
 #pragma unroll
     for (int i = 0; i < 4; ++i)
@@ -117,6 +128,14 @@ __global__ void __launch_bounds__(NTHREADS, 2) gemm_nt_kernel(Desc d) {
       cp_async16(&sm.Bs[st][(tid >> 3) + 32 * i][seg * 2], brow[i] + kk, (bok[i] && kok) ? 16 : 0);
   };
 
+  // lower_only: this warp's 16 rows only need the 8-column groups that reach the diagonal
+  // (columns n0 + 8 nt <= last row); groups strictly above it are neither multiplied nor stored.
+  int nt_lim = 8;
+  if (d.lower_only) {
+    const int last_row = m0 + warp * 16 + 15;
+    nt_lim = (last_row - n0) / 8 + 1;       // may be <= 0: the whole warp tile is above the diagonal
+    nt_lim = nt_lim < 0 ? 0 : (nt_lim > 8 ? 8 : nt_lim);
+  }
   const int nch = ch_end - ch_begin;
   // prologue: STAGES-1 chunks in flight (empty commit groups keep the accounting uniform)
 #pragma unroll
@@ -130,17 +149,37 @@ __global__ void __launch_bounds__(NTHREADS, 2) gemm_nt_kernel(Desc d) {
     __syncthreads();
     if (c + STAGES - 1 < nch) load_chunk(ch_begin + c + STAGES - 1, (c + STAGES - 1) % STAGES);
     cp_async_commit();
+    const int kk_lim = chunk_width(ch_begin + c) >> 2;
+    if (nt_lim == 8) {
 #pragma unroll
-    for (int kk = 0; kk < KC / 4; ++kk) {
-      double a[2], bf[8];
+      for (int kk = 0; kk < KC / 4; ++kk) {
+        if (kk >= kk_lim) break;
+        double a[2], bf[8];
 #pragma unroll
-      for (int mt = 0; mt < 2; ++mt) a[mt] = sm.As[st][warp * 16 + mt * 8 + g][kk * 4 + tg];
+        for (int mt = 0; mt < 2; ++mt) a[mt] = sm.As[st][warp * 16 + mt * 8 + g][kk * 4 + tg];
 #pragma unroll
-      for (int nt = 0; nt < 8; ++nt) bf[nt] = sm.Bs[st][nt * 8 + g][kk * 4 + tg];
+        for (int nt = 0; nt < 8; ++nt) bf[nt] = sm.Bs[st][nt * 8 + g][kk * 4 + tg];
 #pragma unroll
-      for (int mt = 0; mt < 2; ++mt)
+        for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-        for (int nt = 0; nt < 8; ++nt) dmma_m8n8k4(acc[mt][nt][0], acc[mt][nt][1], a[mt], bf[nt]);
+          for (int nt = 0; nt < 8; ++nt) dmma_m8n8k4(acc[mt][nt][0], acc[mt][nt][1], a[mt], bf[nt]);
+      }
+    } else if (nt_lim > 0) {
+#pragma unroll
+      for (int kk = 0; kk < KC / 4; ++kk) {
+        if (kk >= kk_lim) break;
+        double a[2];
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) a[mt] = sm.As[st][warp * 16 + mt * 8 + g][kk * 4 + tg];
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+          if (nt < nt_lim) {
+            const double bfv = sm.Bs[st][nt * 8 + g][kk * 4 + tg];
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) dmma_m8n8k4(acc[mt][nt][0], acc[mt][nt][1], a[mt], bfv);
+          }
+        }
+      }
     }
   }
 

@@ -116,21 +116,26 @@ __global__ void __launch_bounds__(NT1, 2) moments_k1(K1Params p) {
   __syncthreads();
 
   // ---- term(2a, 2b) = sum_k1 sum_k2 C(a,k1) (-1)^k2 C(b,k2) B(k1+k2), latitude.h:112-143
-  for (int idx = tid; idx < 31 * 31; idx += NT1) {
-    const int a2 = idx / 31, b2 = idx % 31;
-    double acc = 0.0;
-    if (a2 + b2 <= 30) {
-      double fac1 = 1.0;
-      for (int k1 = 0; k1 < a2 + 1; ++k1) {
-        double fac2 = fac1;
-        for (int k2 = 0; k2 < b2 + 1; ++k2) {
-          acc += fac2 * sm.Bk[k1 + k2];
-          fac2 *= (k2 - b2) / (k2 + 1.0);
+  // The signed binomial products come from the LAT_FAC table (built on the host with the
+  // reference's ratio recurrences, bit-identical to evaluating them here); the accumulation order
+  // is the reference's.  The heavy (a, b) pairs are dealt out first so the tail is short.
+  {
+    const double *fac = p.tab + SPB_TAB_LAT_FAC;
+    const double *facoff = p.tab + SPB_TAB_LAT_FACOFF;
+    for (int idx = tid; idx < 31 * 31; idx += NT1) {
+      const int a2 = idx / 31, b2 = idx % 31;
+      double acc = 0.0;
+      if (a2 + b2 <= 30) {
+        const double *f = fac + (int)facoff[idx];
+        for (int k1 = 0; k1 < a2 + 1; ++k1) {
+          const double *bk = sm.Bk + k1;
+#pragma unroll 4
+          for (int k2 = 0; k2 < b2 + 1; ++k2) acc += f[k2] * bk[k2];
+          f += b2 + 1;
         }
-        fac1 *= (a2 - k1) / (k1 + 1.0);
       }
+      sm.tt[a2][b2] = acc;
     }
-    sm.tt[a2][b2] = acc;
   }
   __syncthreads();
 
@@ -352,52 +357,63 @@ struct K2Params {
 };
 
 constexpr int K2_GROUP = 32;
+constexpr int K2_NRP = 256;  // row pitch of the transposed T tile
 
+// Thread tile: 4 rows x 4 kept eigen-columns (16 accumulators).  Per m the thread reads 4 T values
+// (one 32-byte run of the TRANSPOSED tile) and 4 S values and issues 16 FMAs, i.e. one shared-memory
+// wavefront per ~4 FMAs instead of one per FMA (the row-per-thread form was LSU-bound).  Only
+// the first rk4 = 4 ceil(rkeep / 4) columns are computed and written; the SYRK never reads the rest.
 __global__ void __launch_bounds__(256, 2) moments_k2(K2Params p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  double *Tsh = reinterpret_cast<double *>(smem_raw);   // [256][w]
+  double *Tt = reinterpret_cast<double *>(smem_raw);    // [w][K2_NRP]  T_lon tile, transposed
   const K2Item it = k2_items[blockIdx.x];
   const int w = 2 * it.l + 1;
-  double *Ssh = Tsh + 256 * 31;                          // [2][31][32]
+  double *Ssh = Tt + 31 * K2_NRP;                        // [2][31][32]
   const int tid = threadIdx.x;
   const double *Tl = p.tab + SPB_TAB_LON_T + it.toff + (size_t)it.row0 * w;
-  for (int idx = tid; idx < it.nrows * w; idx += 256) Tsh[idx] = Tl[idx];
+  const int nq = (it.nrows + 3) >> 2;
+  for (int idx = tid; idx < w * K2_NRP; idx += 256) {
+    const int m = idx >> 8, r = idx & (K2_NRP - 1);
+    Tt[idx] = (r < it.nrows) ? Tl[(size_t)r * w + m] : 0.0;
+  }
   const int b0 = blockIdx.y * K2_GROUP;
   const int b1 = min(p.B, b0 + K2_GROUP);
-  const bool live = tid < it.nrows;
   for (int b = b0; b < b1; ++b) {
     double *Sb = Ssh + ((b - b0) & 1) * (31 * 32);
     const double *src = p.S_lat + ((size_t)b * 256 + it.l * it.l) * 32;
     for (int idx = tid; idx < w * 32; idx += 256) Sb[idx] = src[idx];
     __syncthreads();
-    const int ncol = (p.rkeep[b] <= 16) ? 16 : 32;
-    if (live) {
-      double acc[32];
+    const int ng = (p.rkeep[b] + 3) >> 2;   // groups of 4 kept columns
+    double *Xb = p.X + (size_t)b * (256 * 992) + ((size_t)it.l * it.l * 31 + it.row0) * 32;
+    for (int tile = tid; tile < nq * ng; tile += 256) {
+      const int rq = tile / ng, eg = tile - rq * ng;
+      double acc[4][4];
 #pragma unroll
-      for (int e = 0; e < 32; ++e) acc[e] = 0.0;
-      const double *trow = Tsh + tid * w;
-      if (ncol == 16) {
-        for (int m = 0; m < w; ++m) {
-          const double tv = trow[m];
-          const double *sr = Sb + m * 32;
+      for (int i = 0; i < 4; ++i)
 #pragma unroll
-          for (int e = 0; e < 16; ++e) acc[e] = fma(tv, sr[e], acc[e]);
-        }
-      } else {
-        for (int m = 0; m < w; ++m) {
-          const double tv = trow[m];
-          const double *sr = Sb + m * 32;
+        for (int e = 0; e < 4; ++e) acc[i][e] = 0.0;
+      const double *tp = Tt + 4 * rq;
+      const double *sp = Sb + 4 * eg;
+      for (int m = 0; m < w; ++m) {
+        const double2 t01 = *reinterpret_cast<const double2 *>(tp + m * K2_NRP);
+        const double2 t23 = *reinterpret_cast<const double2 *>(tp + m * K2_NRP + 2);
+        const double2 s01 = *reinterpret_cast<const double2 *>(sp + m * 32);
+        const double2 s23 = *reinterpret_cast<const double2 *>(sp + m * 32 + 2);
+        const double tv[4] = {t01.x, t01.y, t23.x, t23.y};
+        const double sv[4] = {s01.x, s01.y, s23.x, s23.y};
 #pragma unroll
-          for (int e = 0; e < 32; ++e) acc[e] = fma(tv, sr[e], acc[e]);
-        }
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) acc[i][e] = fma(tv[i], sv[e], acc[i][e]);
       }
-      double2 *dst = reinterpret_cast<double2 *>(
-          p.X + (size_t)b * (256 * 992) + ((size_t)it.l * it.l * 31 + it.row0 + tid) * 32);
 #pragma unroll
-      for (int e = 0; e < 16; e += 2) dst[e >> 1] = make_double2(acc[e], acc[e + 1]);
-      if (ncol == 32) {
-#pragma unroll
-        for (int e = 16; e < 32; e += 2) dst[e >> 1] = make_double2(acc[e], acc[e + 1]);
+      for (int i = 0; i < 4; ++i) {
+        const int r = 4 * rq + i;
+        if (r < it.nrows) {
+          double2 *dst = reinterpret_cast<double2 *>(Xb + (size_t)r * 32 + 4 * eg);
+          dst[0] = make_double2(acc[i][0], acc[i][1]);
+          dst[1] = make_double2(acc[i][2], acc[i][3]);
+        }
       }
     }
     // the double-buffered Ssh makes one barrier per sample sufficient
@@ -510,7 +526,7 @@ extern "C" int spb_ylm_moments(spb_context *ctx, int B, const double *r_deg, con
     SPB_CHECK_CUDA(cudaFuncSetAttribute(moments_k1, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)sizeof(K1Smem)));
     SPB_CHECK_CUDA(cudaFuncSetAttribute(moments_k2, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)((256 * 31 + 2 * 31 * 32) * sizeof(double))));
+                                        (int)((K2_NRP * 31 + 2 * 31 * 32) * sizeof(double))));
     attr1 = true;
   }
   K1Params p1;
@@ -541,7 +557,7 @@ extern "C" int spb_ylm_moments(spb_context *ctx, int B, const double *r_deg, con
     p2.X = ws.X;
     p2.B = Bc;
     dim3 grid2(nitems, (Bc + K2_GROUP - 1) / K2_GROUP);
-    moments_k2<<<grid2, 256, (256 * 31 + 2 * 31 * 32) * sizeof(double), stream>>>(p2);
+    moments_k2<<<grid2, 256, (K2_NRP * 31 + 2 * 31 * 32) * sizeof(double), stream>>>(p2);
     SPB_LAUNCH_CHECK(ctx);
 
     gnt::Desc d = {};

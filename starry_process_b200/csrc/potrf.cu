@@ -176,8 +176,10 @@ __device__ __forceinline__ void init_acc(const RowMap &rm, int v, int c0, int tg
 // Warps whose 16 rows are all beyond the last virtual row keep feeding the ring but issue no
 // tensor work.
 // ------------------------------------------------------------------------------------------
+// nt_lim < 8 (rows of the diagonal block): only the first nt_lim 8-column groups reach the
+// diagonal, the rest of the warp tile is never consumed and is not multiplied.
 __device__ __forceinline__ void gemm_tile(Smem &sm, const RowMap &rm, int v0, int c0, int nvirt,
-                                          unsigned &it, double (&acc)[2][8][2]) {
+                                          int nt_lim, unsigned &it, double (&acc)[2][8][2]) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, tg = lane & 3;
   const int nchunks = c0 / KC;
   if (nchunks == 0) return;
@@ -238,17 +240,34 @@ __device__ __forceinline__ void gemm_tile(Smem &sm, const RowMap &rm, int v0, in
     if (warp_live) {
       const double *Aw = &sm.As[st][warp * 16 + g][0];
       const double *Bw = &sm.Bs[st][g][0];
+      if (nt_lim >= 8) {
 #pragma unroll
-      for (int kk = 0; kk < KC / 4; ++kk) {
-        double a[2], b[8];
+        for (int kk = 0; kk < KC / 4; ++kk) {
+          double a[2], b[8];
 #pragma unroll
-        for (int mt = 0; mt < 2; ++mt) a[mt] = negate(Aw[mt * 8 * KC + koff[kk]]);
+          for (int mt = 0; mt < 2; ++mt) a[mt] = negate(Aw[mt * 8 * KC + koff[kk]]);
 #pragma unroll
-        for (int nt = 0; nt < 8; ++nt) b[nt] = Bw[nt * 8 * KC + koff[kk]];
+          for (int nt = 0; nt < 8; ++nt) b[nt] = Bw[nt * 8 * KC + koff[kk]];
 #pragma unroll
-        for (int mt = 0; mt < 2; ++mt)
+          for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-          for (int nt = 0; nt < 8; ++nt) dmma_m8n8k4(acc[mt][nt][0], acc[mt][nt][1], a[mt], b[nt]);
+            for (int nt = 0; nt < 8; ++nt) dmma_m8n8k4(acc[mt][nt][0], acc[mt][nt][1], a[mt], b[nt]);
+        }
+      } else {
+#pragma unroll
+        for (int kk = 0; kk < KC / 4; ++kk) {
+          double a[2];
+#pragma unroll
+          for (int mt = 0; mt < 2; ++mt) a[mt] = negate(Aw[mt * 8 * KC + koff[kk]]);
+#pragma unroll
+          for (int nt = 0; nt < 8; ++nt) {
+            if (nt < nt_lim) {
+              const double b = Bw[nt * 8 * KC + koff[kk]];
+#pragma unroll
+              for (int mt = 0; mt < 2; ++mt) dmma_m8n8k4(acc[mt][nt][0], acc[mt][nt][1], a[mt], b);
+            }
+          }
+        }
       }
     }
     __syncwarp();
@@ -543,7 +562,8 @@ __global__ void __launch_bounds__(NTHREADS, 2) potrf_lnlike_kernel(PotrfParams p
 #pragma unroll
         for (int mt = 0; mt < 2; ++mt)
           init_acc(rm, v0 + warp * 16 + mt * 8 + g, c0, tg, full_panel, acc[mt]);
-        gemm_tile(sm, rm, v0, c0, nvirt, it, acc);   // acc = K - L L^T = P
+        gemm_tile(sm, rm, v0, c0, nvirt, (diag_tile && warp < 4) ? 2 * warp + 2 : 8, it,
+                  acc);   // acc = K - L L^T = P
         if (diag_tile) {
           if (warp < 4) {
 #pragma unroll
