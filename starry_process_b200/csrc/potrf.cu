@@ -401,7 +401,7 @@ __device__ __forceinline__ void unpark_acc(const Smem &sm, double (&acc)[2][8][2
       acc[mt][nt][1] = v.y;
     }
 }
-static_assert(sizeof(double) * (STAGES * (TM + NB) * KC) >= 65536 + 2 * NB * sizeof(double),
+static_assert(sizeof(double) * (STAGES * (TM + NB) * KC) >= 65536 + 2 * (NB + 2) * sizeof(double),
               "stage buffers too small to park the accumulators");
 
 // 64x64 Cholesky of sm.Ld (lower triangle), scalar FP64, register-resident: thread t owns row
@@ -415,12 +415,13 @@ __device__ __forceinline__ double potf2_block(Smem &sm, int nvalid) {
   const int tid = threadIdx.x;
   const int i = tid >> 2, cg = tid & 3;
   // pivot-column broadcast buffers (double-buffered) live in the idle stage buffers, behind the
-  // 64 KB used to park the accumulators (see park_acc)
-  double(*col)[NB] = reinterpret_cast<double(*)[NB]>(&sm.As[0][0][0] + 8192);
+  // 64 KB used to park the accumulators (see park_acc); slot NB of each buffer carries 1 / pivot
+  double(*col)[NB + 2] = reinterpret_cast<double(*)[NB + 2]>(&sm.As[0][0][0] + 8192);
   double a[16];
   double dpiv = 1.0;
 #pragma unroll
   for (int jj = 0; jj < 16; ++jj) a[jj] = sm.Ld[i][cg * 16 + jj];
+  if (tid == 0) col[0][NB] = 1.0 / a[0];
 #pragma unroll 1
   for (int cgc = 0; cgc < 4; ++cgc) {
 #pragma unroll
@@ -431,7 +432,14 @@ __device__ __forceinline__ double potf2_block(Smem &sm, int nvalid) {
       __syncthreads();
       const double d = colb[c];
       if (c == i) dpiv = d;  // every thread of row i sees its pivot go by at step c == i
-      const double li = colb[i] * (1.0 / d);
+      // 1 / d_c was computed by the owner of the pivot during the PREVIOUS step, off this step's
+      // critical path (and once, not by all 256 threads on the FP64 pipe the other CTA's DMMAs use)
+      const double li = colb[i] * colb[NB];
+      {
+        const int jn = (cc + 1) & 15;              // compile-time: next pivot's slot ...
+        const int cgn = cgc + (cc == 15 ? 1 : 0);  // ... and column group
+        if (i == c + 1 && cg == cgn) col[(c + 1) & 1][NB] = 1.0 / (a[jn] - li * colb[c + 1]);
+      }
       if (c < NB - 1 && i > c) {
 #pragma unroll
         for (int jj = 0; jj < 16; ++jj) {
@@ -442,14 +450,15 @@ __device__ __forceinline__ double potf2_block(Smem &sm, int nvalid) {
     }
   }
   // pivots: thread (i, cg = i / 16) holds d_i in a[i % 16]
-  double logpart = 0.0;
+  double logpart = 0.0, sqd = 1.0;
   if (cg == (i >> 4)) {
     double di = dpiv;
     if (!(di > 0.0)) {  // also catches NaN
       sm.bad = 1;
       di = 1.0;
     }
-    col[0][i] = di;   // col[1] was the last buffer written by the loop (c = 63)
+    sqd = sqrt(di);
+    col[0][i] = 1.0 / sqd;   // col[1] was the last buffer written by the loop (c = 63)
     if (i < nvalid) logpart = 0.5 * log(di);
   }
   __syncthreads();
@@ -459,8 +468,8 @@ __device__ __forceinline__ double potf2_block(Smem &sm, int nvalid) {
     const int j = cg * 16 + jj;
     double v = 0.0;
     if (j <= i) {
-      const double sj = sqrt(col[0][j]);
-      v = (j == i) ? sj : a[jj] / sj;
+      const double rsj = col[0][j];
+      v = (j == i) ? sqd : a[jj] * rsj;
     }
     sm.Ld[i][j] = v;
   }
