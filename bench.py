@@ -100,24 +100,70 @@ class ClockSampler(object):
 # reference arm / CPU baseline: the oracle (reference C++ compiled in place when oracle/_ref is
 # available, else the plain-C restatement) + NumPy/SciPy LAPACK on the host cores
 # ------------------------------------------------------------------------------------------
+_POOL = None
+
+
+def _worker_init():
+    # one LAPACK thread per worker process: the host cores are used by evaluating independent
+    # hyperparameter samples in parallel (the reference itself is single-threaded per evaluation)
+    for k in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[k] = "1"
+    try:
+        from threadpoolctl import threadpool_limits
+
+        threadpool_limits(1)
+    except Exception:
+        pass
+    from oracle import sp_oracle  # noqa: F401  (load the shared objects once per worker)
+
+
+def _eval_one(job):
+    from oracle import sp_oracle as so
+
+    r, mu, sigma, c, n, t, flux, native = job
+    o = so.OracleProcess(r=r, mu=mu, sigma=sigma, c=c, n=n, native=native)
+    return o.log_likelihood(t, flux, 1e-6, p=1.0, u=U_LD)
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
 def cpu_evals(hp, t, flux, n_eval, workload, flux_ens=None):
+    """The reference's CPU implementation of the path (oracle/_ref: its own compiled C++ + NumPy /
+    SciPy LAPACK) on the host cores.  sweep: independent evaluations spread over one worker
+    process per core.  ensemble: one joint evaluation (LAPACK multithreaded)."""
+    global _POOL
     from oracle import sp_oracle as so
 
     native = "ref" if so.ref_available(15, 2) else "port"
     kind = "reference" if native == "ref" else "port"
-    t0 = time.perf_counter()
     out = []
     if workload == "sweep":
-        for s in range(n_eval):
-            o = so.OracleProcess(r=hp["r"][s], mu=hp["mu"][s], sigma=hp["sigma"][s], c=hp["c"][s],
-                                 n=hp["n"][s], native=native)
-            out.append(o.log_likelihood(t, flux, 1e-6, p=1.0, u=U_LD))
+        cores = host_cores()
+        if _POOL is None and cores > 1:
+            import multiprocessing as mp
+            from concurrent.futures import ProcessPoolExecutor
+
+            _POOL = ProcessPoolExecutor(max_workers=cores, mp_context=mp.get_context("spawn"),
+                                        initializer=_worker_init)
+            list(_POOL.map(_eval_one, [(hp["r"][0], hp["mu"][0], hp["sigma"][0], hp["c"][0],
+                                        hp["n"][0], t[:50], flux[:50], native)] * cores))  # spin up
+        jobs = [(hp["r"][s], hp["mu"][s], hp["sigma"][s], hp["c"][s], hp["n"][s], t, flux, native)
+                for s in range(n_eval)]
+        t0 = time.perf_counter()
+        out = list(_POOL.map(_eval_one, jobs)) if _POOL is not None else [_eval_one(j) for j in jobs]
+        dt = time.perf_counter() - t0
         n_done = n_eval
     else:
+        t0 = time.perf_counter()
         o = so.OracleProcess(r=10.0, mu=30.0, sigma=5.0, c=0.1, n=10.0, native=native)
         out.append(o.log_likelihood(t, flux_ens, 1e-6, p=1.0, u=U_LD))
+        dt = time.perf_counter() - t0
         n_done = flux_ens.shape[0]
-    dt = time.perf_counter() - t0
     return n_done / dt, kind, out
 
 
@@ -141,10 +187,10 @@ def run_reference(args):
         rates.append(r_)
     total = time.perf_counter() - t0
     value = float(np.mean(rates))
-    cores = os.cpu_count()
+    cores = host_cores()
     sample = ("%d lnlike evaluations per step of the same workload (each: Ylm moments + marginal "
-              "kernel + 1000x1000 Cholesky), oracle on the host, LAPACK threads = all cores"
-              % n_eval) if args.workload == "sweep" else \
+              "kernel + 1000x1000 Cholesky), reference C++ + NumPy/SciPy on the host, one worker "
+              "process per core" % n_eval) if args.workload == "sweep" else \
         "one joint lnlike of 1024 light curves per step (1 factorisation + 1024-RHS solve)"
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "evals/s", "n_gpus": args.gpus,
@@ -157,7 +203,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -168,6 +214,16 @@ def workload_name(args):
                 % args.batch)
     return ("configs[1]: ensemble of 1024 light curves (nt=1000) sharing one hyperparameter set: "
             "one K factorisation + 1024-RHS forward solve")
+
+
+def ncu_traffic(kernel, units):
+    """DRAM bytes (read + write) per launch from the committed ncu --set full capture of the same
+    kernel (profiles/ncu_traffic.json, scripts/ncu_traffic.py), scaled by the units in this launch."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as fh:
+            return float(json.load(fh)[kernel]["dram_bytes_per_unit"]) * units
+    except (OSError, KeyError, ValueError):
+        return None
 
 
 def hbm_peak():
@@ -214,7 +270,8 @@ def design_phase(spb, _lib, ctx, dev, torch, I=64, nt=100000, reps=5):
             "workload": "configs[4]: design matrix, nt=1e5 timestamps x 64 inclinations, u=[0.4,0.26]",
             "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "peak_source": src,
             "ms_per_launch": ms, "rows_per_s": I * nt / (ms * 1e-3),
-            "algorithmic_bytes_per_launch": alg_bytes, "traffic": None}
+            "algorithmic_bytes_per_launch": alg_bytes,
+            "traffic": ncu_traffic("design_rows_kernel", float(I) * nt)}
 
 
 # ------------------------------------------------------------------------------------------
@@ -356,7 +413,11 @@ def run_b200(args):
         "bound": "tensor", "kernel": "potrf_lnlike_kernel (DMMA m8n8k4.f64 left-looking Cholesky + "
                                      "augmented forward solve)",
         "achieved": achieved, "peak": dmma_peak, "unit": "TFLOP/s",
-        "frac": (achieved / dmma_peak) if achieved else None, "traffic": None,
+        "frac": (achieved / dmma_peak) if achieved else None,
+        "traffic": ncu_traffic("potrf_lnlike_kernel", flops_total / n_launch / (NT ** 3 / 3.0 + NT ** 2)
+                               if args.workload == "sweep" else 1.0),
+        "traffic_note": "DRAM read+write bytes per launch: per-matrix figure of the ncu capture "
+                        "profiles/r01_ncu_potrf_mbarrier.txt x matrices in the launch",
         "peak_source": "FP64 mma.sync peak measured in this run by spb_dmma_peak "
                        "(MEASURED_PEAKS.json has no fp64 entry; cuBLAS DGEMM 8192^3 on this pool: "
                        "35.5 TFLOP/s)",
@@ -390,9 +451,9 @@ def run_b200(args):
                 "max_rel": float(np.max(np.abs(llall[:64][gfin] - gref[gfin]) / np.abs(gref[gfin]))),
                 "n": 64, "neg_inf_pattern_equal": same_inf, "tolerance": 1e-8}
     cpu_baseline = {
-        "value": cb_value, "unit": "evals/s", "cores": os.cpu_count(), "kind": cb_kind,
-        "sample": "%d evaluations of the same workload, oracle on the host (LAPACK multithreaded)"
-                  % (args.cpu_evals if args.workload == "sweep" else 1024),
+        "value": cb_value, "unit": "evals/s", "cores": host_cores(), "kind": cb_kind,
+        "sample": "%d evaluations of the same workload, reference C++ + NumPy/SciPy on the host, one "
+                  "worker process per core" % (args.cpu_evals if args.workload == "sweep" else 1024),
         "max_rel_lnlike_diff_vs_gpu_on_sample": parity,
         "note": "live oracle on THIS host; the reference algorithm moves by up to ~3e-6 between "
                 "CPUs (LAPACK kernel selection), see parity_vs_reference_golden for the pinned check",
@@ -411,10 +472,32 @@ def run_b200(args):
         "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
         "parity_vs_reference_golden": parity_golden, "phases": phases,
     }
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """Anything a library prints on fd 1 (e.g. NCCL's version banner) goes to stderr; the one JSON
+    line is written to the original stdout by emit()."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
 
 
 def main():
@@ -425,9 +508,10 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="sweep", choices=["sweep", "ensemble"])
     ap.add_argument("--batch", type=int, default=4096, help="hyperparameter samples per GPU")
-    ap.add_argument("--cpu-evals", type=int, default=48, help="CPU-baseline sample size")
-    ap.add_argument("--ref-evals", type=int, default=24, help="reference arm: evaluations per step")
+    ap.add_argument("--cpu-evals", type=int, default=64, help="CPU-baseline sample size")
+    ap.add_argument("--ref-evals", type=int, default=96, help="reference arm: evaluations per step")
     args = ap.parse_args()
+    quiet_stdout()
     if args.impl == "reference":
         return run_reference(args)
     return run_b200(args)
