@@ -63,6 +63,12 @@ int spb_device(const spb_context *ctx);
 int spb_gauss2beta(spb_context *ctx, int B, const double *mu_deg, const double *sigma_deg,
                    double *a, double *b, void *stream);
 
+/* log-Jacobian of the (a, b) -> (mu, sigma) transform of the latitude prior, one value per element:
+ * LatitudeIntegral._log_jac, latitude.py:221-241, 281-316 (used by calibrate/log_prob.py:87-90);
+ * -inf where sigma > sigma_max (degrees, defaults.py: 45).                                      */
+int spb_log_jac(spb_context *ctx, int B, const double *a, const double *b, double sigma_max_deg,
+                double *log_jac, void *stream);
+
 /* ---------------------------------------------------------------------------------------------
  * (a2-a9) Ylm moment integrals: size -> latitude -> longitude -> contrast.
  * Replaces SizeIntegral/LatitudeIntegral/LongitudeIntegral/ContrastIntegral

@@ -726,6 +726,21 @@ class OracleProcess(object):
         tmp = np.ascontiguousarray(self._dotRx(mom2y, self._rx90).T)
         self.Ez = self._dotRx(tmp, self._rx90)
 
+    # latitude.py:221-241 (_compute_mu_and_sigma) and 281-316 (_log_jac); sigma_max of latitude.py:194
+    def log_jac(self, sigma_max=DEFAULTS["sigma_max"]):
+        al, be = self.alpha, self.beta
+        term = 4 * al ** 2 - 8 * al - 6 * be + 4 * al * be + be ** 2 + 5
+        mu = 2 * np.arctan(np.sqrt(2 * al + be - 2 - np.sqrt(term)))
+        term = 1 - al + be + (be - 1) * np.cos(mu) + (al - 1) / np.cos(mu) ** 2
+        sigma = np.sqrt(np.sin(mu) ** 2 / term)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            lj = np.log(np.abs(
+                (al * be * (1 + np.cos(mu)) ** 3 * np.sin(2 * mu) ** 3)
+                / (sigma * (-3 + 2 * al + be + (-1 + 2 * al + be) * np.cos(mu))
+                   * (2 * (-1 + al + be) + 3 * (-1 + be) * np.cos(mu)
+                      - 2 * (-1 + al - be) * np.cos(2 * mu) + (-1 + be) * np.cos(3 * mu)) ** 2)))
+        return -np.inf if sigma > sigma_max * np.pi / 180 else float(lj)
+
     # sp.py:265-271
     @property
     def cho_cov_ylm(self):

@@ -491,7 +491,42 @@ __global__ void gauss2beta_kernel(int B, const double *mu, const double *sigma, 
   b[i] = fmax(0.0, (log(beta) - log(0.5)) / (10.0 - log(0.5)));
 }
 
+// log |d(a, b) / d(mu, sigma)|, latitude.py:221-241 (mode and width of the latitude pdf from the
+// Beta shape parameters) and 281-316; -inf when sigma > sigma_max.
+__global__ void log_jac_kernel(int B, const double *a, const double *b, double sigma_max_rad,
+                               double *out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B) return;
+  double aa = a[i], bb = b[i];
+  if (aa < 1e-12) aa = 1e-12;  // latitude.py:178-182 (abmin)
+  if (bb < 1e-12) bb = 1e-12;
+  const double al = exp(aa * 10.0);
+  const double be = exp(log(0.5) + bb * (10.0 - log(0.5)));
+  double term = 4 * al * al - 8 * al - 6 * be + 4 * al * be + be * be + 5;
+  const double mu = 2 * atan(sqrt(2 * al + be - 2 - sqrt(term)));
+  const double cm = cos(mu), sn = sin(mu);
+  term = 1 - al + be + (be - 1) * cm + (al - 1) / (cm * cm);
+  const double sigma = sqrt(sn * sn / term);
+  const double c1 = 1 + cm, s2 = sin(2 * mu);
+  const double num = al * be * (c1 * c1 * c1) * (s2 * s2 * s2);
+  const double f1 = -3 + 2 * al + be + (-1 + 2 * al + be) * cm;
+  const double f2 = 2 * (-1 + al + be) + 3 * (-1 + be) * cm - 2 * (-1 + al - be) * cos(2 * mu) +
+                    (-1 + be) * cos(3 * mu);
+  const double lj = log(fabs(num / (sigma * f1 * (f2 * f2))));
+  out[i] = (sigma > sigma_max_rad) ? -INFINITY : lj;
+}
+
 }  // namespace
+
+extern "C" int spb_log_jac(spb_context *ctx, int B, const double *a, const double *b,
+                           double sigma_max_deg, double *log_jac, void *stream) {
+  SPB_REQUIRE(ctx != nullptr && B > 0, "log_jac: bad arguments");
+  SPB_CHECK_CUDA(cudaSetDevice(ctx->device));
+  log_jac_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+      B, a, b, sigma_max_deg * 3.14159265358979323846 / 180.0, log_jac);
+  SPB_LAUNCH_CHECK(ctx);
+  return 0;
+}
 
 extern "C" int spb_gauss2beta(spb_context *ctx, int B, const double *mu_deg,
                               const double *sigma_deg, double *a, double *b, void *stream) {

@@ -167,6 +167,7 @@ class StarryProcess(object):
         self._normN = int(kwargs.pop("normalization_order", defaults["normalization_order"]))
         self._normzmax = float(kwargs.pop("normalization_zmax", defaults["normalization_zmax"]))
         self._max_chunk_bytes = int(kwargs.pop("max_chunk_bytes", 48 << 30))
+        self._sigma_max = float(kwargs.pop("sigma_max", defaults["sigma_max"]))
         kwargs.pop("seed", None)
         self._nylm = (self._ydeg + 1) ** 2
         self._covpts = int(covpts)
@@ -264,6 +265,15 @@ class StarryProcess(object):
     def _mark_end(ev):
         if ev is not None:
             ev.record()
+
+    def log_jac(self):
+        """sp.py:1004-1050 -> LatitudeIntegral._log_jac (latitude.py:281-316): log-Jacobian of the
+        ``(a, b) -> (mu, sigma)`` transform, ``-inf`` where ``sigma > sigma_max``."""
+        out = torch.empty(self._B, dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.spb_log_jac(self._ctx.handle, self._B, _ptr(self._a), _ptr(self._b),
+                                             self._sigma_max, _ptr(out), _stream()))
+        return self._out(out)
 
     # ------------------------------------------------------------------ Ylm moments
     def _compute_moments(self):
@@ -379,7 +389,7 @@ class StarryProcess(object):
         return A if _is_batched(i) else A[0]
 
     # ------------------------------------------------------------------ flux mean / covariance
-    def _noise_model(self, nt, data_cov, baseline_var, keep, lower_only=False):
+    def _noise_model(self, nt, data_cov, baseline_var, keep, lower_only=False, b0=0):
         nm = _lib.NoiseModel()
         nm.lower_only = 1 if lower_only else 0
         nm.normalized = 1 if self._normalized else 0
@@ -407,6 +417,13 @@ class StarryProcess(object):
             bv = torch.as_tensor(baseline_var, dtype=torch.float64).to(self.device).contiguous()
             if bv.ndim == 0:
                 nm.base_kind, bv = 0, bv.reshape(1)
+            elif bv.ndim == 1:
+                # extension: one baseline variance per batch element (the free `v` of
+                # calibrate/log_prob.py:70-74)
+                if bv.numel() != self._B:
+                    raise ValueError("a 1-D baseline_var must have one entry per batch element")
+                nm.base_kind, nm.base_stride = 0, 1
+                bv = bv[b0:].contiguous()
             else:
                 if tuple(bv.shape) != (nt, nt):
                     raise ValueError("baseline_var must be a scalar or an (nt, nt) matrix")
@@ -423,7 +440,7 @@ class StarryProcess(object):
         Bc, nt = b1 - b0, t.numel()
         dev = self.device
         keep = []
-        nm = self._noise_model(nt, data_cov, baseline_var, keep, lower_only and marg)
+        nm = self._noise_model(nt, data_cov, baseline_var, keep, lower_only and marg, b0=b0)
         mean_ylm = self._mean_ylm[b0:b1]
         cov_ylm = self._cov_ylm[b0:b1]
         info = self._info[b0:b1]
@@ -523,7 +540,9 @@ class StarryProcess(object):
                        baseline_var=defaults["baseline_var"], marginalize_over_inclination=None):
         """sp.py:1052-1188.  ``flux`` is ``(nt,)`` or ``(M, nt)`` (M light curves sharing period,
         limb darkening, inclination and noise, scored jointly); returns a scalar, or ``(B,)`` for a
-        batch of hyperparameter samples."""
+        batch of hyperparameter samples.  Extension: ``flux`` of shape ``(B, M, nt)`` gives every
+        batch element its own light curve(s) (the light-curve x sample x inclination batches of
+        calibrate/inclination.py:63-74)."""
         marg, t, inc, rta1 = self._prep(t, i, p, u, marginalize_over_inclination)
         nt = t.numel()
         ldk = nt + (nt & 1)
@@ -531,10 +550,15 @@ class StarryProcess(object):
         f = torch.as_tensor(flux, dtype=torch.float64).to(dev)
         if f.ndim == 1:
             f = f[None]
-        if f.shape[1] != nt:
-            raise ValueError("flux must have shape (nt,) or (M, nt)")
-        M = f.shape[0]
+        per_element = f.ndim == 3
+        if per_element and f.shape[0] != self._B:
+            raise ValueError("per-element flux must have shape (B, M, nt)")
+        if f.shape[-1] != nt:
+            raise ValueError("flux must have shape (nt,), (M, nt) or (B, M, nt)")
+        M = f.shape[-2]
         bm = torch.as_tensor(baseline_mean, dtype=torch.float64).to(dev)
+        if bm.ndim == 1 and bm.numel() != self._B:
+            raise ValueError("a 1-D baseline_mean must have one entry per batch element")
         bvar = None
         if isinstance(baseline_var, (torch.Tensor, np.ndarray)) or baseline_var != 0.0:
             bvar = baseline_var
@@ -549,10 +573,12 @@ class StarryProcess(object):
                 zs.append(z)
                 # r = flux - (gp_mean + baseline_mean)  (sp.py:1157-1161); normalised: mean == 0
                 resid = torch.zeros(Bc, M, ldk, dtype=torch.float64, device=dev)
+                fc = f[b0:b1] if per_element else f[None]
+                bmc = bm[b0:b1, None, None] if bm.ndim == 1 else bm   # (B,) baseline means
                 if self._normalized:
-                    resid[:, :, :nt] = (f - bm)[None]
+                    resid[:, :, :nt] = fc - bmc
                 else:
-                    resid[:, :, :nt] = f[None] - (gp_mean[:, None, None] + bm)
+                    resid[:, :, :nt] = fc - (gp_mean[:, None, None] + bmc)
                 ev = self._mark("cholesky")
                 if Bc == 1 and M >= 64:
                     # one factorisation + many right-hand sides (ensemble of light curves sharing

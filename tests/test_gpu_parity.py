@@ -310,6 +310,43 @@ def test_bench_workload_against_reference_golden(spb, golden):
         assert err.max() <= RTOL
 
 
+def test_calibrate_callers_against_reference(spb, golden):
+    """get_log_prob (calibrate/log_prob.py:7-106), log_jac (latitude.py:281-316) and the inclination
+    grid of calibrate/inclination.py:63-74, batched, against values produced by the unmodified
+    reference (oracle/gen_golden_calibrate.py): 1e-8 relative."""
+    from starry_process_b200 import calibrate
+
+    g = golden("calibrate_log_prob.npz")
+    t, fl = g["t"], g["flux"]
+    T = lambda x: torch.tensor(np.asarray(x), dtype=torch.float64)  # noqa: E731
+    gp = spb.StarryProcess(r=T(g["r"]), a=T(g["a"]), b=T(g["b"]), c=T(g["c"]), n=T(g["n"]))
+    lj = gp.log_jac().cpu().numpy()
+    assert rel(lj, g["log_jac"]).max() <= 1e-11
+    assert spb.StarryProcess(r=10.0, mu=30.0, sigma=46.0, c=0.1, n=10.0).log_jac().item() == -np.inf
+    # marginalised, three light curves scored jointly, fixed baseline, Jacobian applied
+    f = calibrate.get_log_prob(t, flux=fl, ferr=1e-3, p=1.0, u=U_LD)
+    lp = f(T(g["r"]), T(g["a"]), T(g["b"]), T(g["c"]), T(g["n"])).cpu().numpy()
+    e1 = rel(lp, g["log_prob_marg"]).max()
+    # scalar call == the reference's calling convention
+    lp0 = f(float(g["r"][0]), float(g["a"][0]), float(g["b"][0]), float(g["c"][0]), float(g["n"][0]))
+    assert rel(lp0.item(), g["log_prob_marg"][0]) <= RTOL
+    # conditional, free flux / baseline mean / baseline log-variance / inclination, all per element
+    f2 = calibrate.get_log_prob(t, flux=None, ferr=1e-3, p=1.0, marginalize_over_inclination=False,
+                                baseline_mean=None, baseline_log_var=None, u=U_LD)
+    lp2 = f2(fl[:1], T(g["r"]), T(g["a"]), T(g["b"]), T(g["c"]), T(g["n"]), T(g["m"]), T(g["v"]),
+             T(g["inc_cond"])).cpu().numpy()
+    e2 = rel(lp2, g["log_prob_cond"]).max()
+    grid = calibrate.inclination_log_prob(
+        t, fl[:2], np.stack([g["r"][:2], g["a"][:2], g["b"][:2], g["c"][:2], g["n"][:2]], axis=1),
+        g["inc_grid"], ferr=1e-3, p=1.0).cpu().numpy()
+    e3 = rel(grid, g["lp_grid"]).max()
+    print("calibrate callers: max rel err marg %.2e cond %.2e grid %.2e" % (e1, e2, e3))
+    # The grid uses the reference defaults baseline_log_var = 0, i.e. + 1.0 on every entry of a
+    # covariance whose other eigenvalues are ~1e-6: cond(K) = 2.5e8, so two correct fp64
+    # factorisations differ by ~cond * eps = 3e-8 (the pole-on column, i = 0, is rank one on top).
+    assert e1 <= RTOL and e2 <= RTOL and e3 <= 1e-7
+
+
 def test_long_baseline_limb_darkened(spb, golden):
     lb = golden("longbaseline_nt4096.npz")
     gp = spb.StarryProcess(r=lb["r"], mu=lb["mu"], sigma=lb["sigma"], c=lb["c"], n=lb["n"],
