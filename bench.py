@@ -125,6 +125,13 @@ def _eval_one(job):
     return o.log_likelihood(t, flux, 1e-6, p=1.0, u=U_LD)
 
 
+def close_pool():
+    global _POOL
+    if _POOL is not None:
+        _POOL.shutdown(wait=True)
+        _POOL = None
+
+
 def host_cores():
     try:
         return len(os.sched_getaffinity(0))
@@ -512,9 +519,12 @@ def main():
     ap.add_argument("--ref-evals", type=int, default=96, help="reference arm: evaluations per step")
     args = ap.parse_args()
     quiet_stdout()
-    if args.impl == "reference":
-        return run_reference(args)
-    return run_b200(args)
+    try:
+        if args.impl == "reference":
+            return run_reference(args)
+        return run_b200(args)
+    finally:
+        close_pool()
 
 
 if __name__ == "__main__":

@@ -163,9 +163,15 @@ typedef struct {
   long long base_stride;
   int lower_only;            /* marginal assembly: write only K[i][j], j <= i (what the Cholesky
                                 kernel reads); the strict upper triangle is left untouched */
+  int defer;                 /* leave K RAW (lower triangle) and only produce the normalisation
+                                scalars / row-sum vector in the workspace: the affine map and the
+                                noise terms are applied by spb_cholesky_lnlike_affine.  Requires
+                                lower_only and no full-matrix data_cov / baseline_var.            */
 } spb_noise_model;
 
 size_t spb_assemble_workspace_bytes(const spb_context *ctx, int B, int nt);
+/* Where spb_assemble_* leaves q (B,nt) and scal (B,4) inside `workspace` (for spb_affine). */
+void spb_assemble_workspace_layout(int B, int nt, void *workspace, double **q, double **scal);
 int spb_assemble_marginal(spb_context *ctx, int B, int nt, const double *t, double period, int covpts,
                           const double *coef, const double *var, const double *gp_mean,
                           const spb_noise_model *noise, double *K, int ldk, double *z_out,
@@ -188,6 +194,31 @@ int spb_assemble_conditional(spb_context *ctx, int B, int nt, const double *gp_m
 int spb_cholesky_lnlike(spb_context *ctx, int B, int nt, double *K, int ldk, long long K_stride,
                         int M, double *resid, int ldr, long long resid_stride, double *lnlike,
                         double *quad, double *logdet, int32_t *info, void *stream);
+
+/* Same factorisation with the LAST ASSEMBLY STEP FUSED INTO ITS LOADS: the kernel reads every entry
+ * of the raw covariance exactly once (to initialise its accumulators) and applies there
+ *     K'_ij = s1 K_ij + s2 (1 - q_i)(1 - q_j) - s3 q_i q_j + offset + [i == j] diag_i
+ * i.e. the normalisation of sp.py:705-727 (s1 = alpha/mu^2, s2 = z (alpha+beta), s3 = z alpha, q the
+ * scaled row sums; all produced by spb_assemble_* with noise->defer = 1), the scalar / per-point
+ * data covariance and the scalar baseline variance of sp.py:1135-1151.  The dense matrix is then
+ * written once (raw) and never re-read or re-written by an assembly pass.
+ *   scal: (B,4) [s1, s2, s3, -] or NULL (identity);  q: (B,nt) or NULL
+ *   diag: NULL | one value per batch element (diag_kind 0, diag_stride 0 or 1) | (nt) values
+ *         (diag_kind 1, diag_stride 0 or nt);  offset: NULL | one value (offset_stride 0 or 1)   */
+typedef struct {
+  const double *scal;
+  const double *q;
+  const double *diag;
+  int diag_kind;
+  long long diag_stride;
+  const double *offset;
+  long long offset_stride;
+} spb_affine;
+
+int spb_cholesky_lnlike_affine(spb_context *ctx, int B, int nt, double *K, int ldk,
+                               long long K_stride, const spb_affine *affine, int M, double *resid,
+                               int ldr, long long resid_stride, double *lnlike, double *quad,
+                               double *logdet, int32_t *info, void *stream);
 
 /* Forward solve y = L^{-1} r for many right-hand sides against ONE factor, the RHS rows split
  * across the whole GPU (config "1 factorisation + 1024 RHS").  quad: (M) out.               */

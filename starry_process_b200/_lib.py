@@ -21,7 +21,15 @@ class NoiseModel(_c.Structure):
         ("normalized", _I), ("normalization_order", _I), ("normalization_zmax", _D),
         ("data_kind", _I), ("data_cov", _P), ("data_stride", _LL),
         ("base_kind", _I), ("baseline_var", _P), ("base_stride", _LL),
-        ("lower_only", _I),
+        ("lower_only", _I), ("defer", _I),
+    ]
+
+
+class Affine(_c.Structure):
+    """spb_affine (include/spb200.h)."""
+    _fields_ = [
+        ("scal", _P), ("q", _P), ("diag", _P), ("diag_kind", _I), ("diag_stride", _LL),
+        ("offset", _P), ("offset_stride", _LL),
     ]
 
 
@@ -53,6 +61,9 @@ PROTOTYPES = {
     "spb_assemble_conditional": (_I, [_P, _I, _I, _P, _c.POINTER(NoiseModel), _P, _I, _P, _P,
                                       _P, _SZ, _P]),
     "spb_cholesky_lnlike": (_I, [_P, _I, _I, _P, _I, _LL, _I, _P, _I, _LL, _P, _P, _P, _P, _P]),
+    "spb_cholesky_lnlike_affine": (_I, [_P, _I, _I, _P, _I, _LL, _c.POINTER(Affine), _I, _P, _I, _LL,
+                                        _P, _P, _P, _P, _P]),
+    "spb_assemble_workspace_layout": (None, [_I, _I, _P, _c.POINTER(_P), _c.POINTER(_P)]),
     "spb_cholesky_solve_rows": (_I, [_P, _I, _P, _I, _I, _P, _I, _P, _P]),
     "spb_dmma_peak": (_I, [_P, _I, _c.POINTER(_D), _c.POINTER(_D)]),
     "spb_launch_count": (_I, [_P, _c.POINTER(_LL)]),

@@ -106,6 +106,7 @@ __global__ void __launch_bounds__(256) rowsum_sym_kernel(AsmParams p) {
     for (int i = c * 8 + warp; i < p.nt; i += RS_G * 8) {
       if (i < cb0) continue;
       const double thi = th[i];
+      double *Krow = p.K + ((size_t)b * p.nt + i) * p.ldk;
       double rs = 0.0;
 #pragma unroll
       for (int k = 0; k < 32; ++k) {
@@ -115,8 +116,11 @@ __global__ void __launch_bounds__(256) rowsum_sym_kernel(AsmParams p) {
             const double v = interp_cov(cf, nc, dx, thi, th[j]);
             rs += v;
             cs[k] += v;
+            if (p.nm.defer) Krow[j] = v;   // raw covariance, written once (coalesced along j)
           } else if (j == i) {
-            rs += (p.nt == 1) ? p.var[b] : interp_cov(cf, nc, dx, thi, thi);
+            const double v = (p.nt == 1) ? p.var[b] : interp_cov(cf, nc, dx, thi, thi);
+            rs += v;
+            if (p.nm.defer) Krow[j] = v;
           }
         }
       }
@@ -283,6 +287,18 @@ int run_assemble(spb_context *ctx, AsmParams &p, void *workspace, size_t workspa
   } else if (p.z_out) {
     SPB_CHECK_CUDA(cudaMemsetAsync(p.z_out, 0, (size_t)p.B * sizeof(double), stream));
   }
+  if (p.nm.defer) {
+    SPB_REQUIRE(p.marginal && p.nm.lower_only && p.nm.data_kind != 2 && p.nm.base_kind != 2,
+                "assemble: defer needs the marginal lower-only path without full-matrix noise terms");
+    if (p.nm.normalized) return 0;   // rowsum_sym_kernel already wrote the raw lower triangle
+    AsmParams raw = p;               // raw interpolant only; the Cholesky kernel adds the noise
+    raw.nm.data_cov = nullptr;
+    raw.nm.baseline_var = nullptr;
+    dim3 gridR(min(p.nt, 32), p.B);
+    write_kernel<<<gridR, 256, smW, stream>>>(raw);
+    SPB_LAUNCH_CHECK(ctx);
+    return 0;
+  }
   dim3 gridW(min(p.nt, 32), p.B);
   write_kernel<<<gridW, 256, smW, stream>>>(p);
   SPB_LAUNCH_CHECK(ctx);
@@ -294,6 +310,13 @@ int run_assemble(spb_context *ctx, AsmParams &p, void *workspace, size_t workspa
 extern "C" size_t spb_assemble_workspace_bytes(const spb_context *ctx, int B, int nt) {
   (void)ctx;
   return ((size_t)B * nt * (1 + RS_G) + (size_t)B * 4) * sizeof(double) + 256;
+}
+
+extern "C" void spb_assemble_workspace_layout(int B, int nt, void *workspace, double **q,
+                                              double **scal) {
+  double *rowq = reinterpret_cast<double *>(workspace);
+  if (q) *q = rowq;
+  if (scal) *scal = rowq + (size_t)B * nt;
 }
 
 extern "C" int spb_assemble_marginal(spb_context *ctx, int B, int nt, const double *t, double period,

@@ -53,6 +53,8 @@ struct PotrfParams {
   int B;
   int mode;
   int rows_per_cta;  // MODE_SOLVE: RHS rows per work item
+  spb_affine aff;    // fused last assembly step (scal == q == diag == offset == NULL: none)
+  int aff_on;
 };
 
 struct RowMap {
@@ -102,6 +104,7 @@ struct Smem {
   double Ld[NB][LS];   // diagonal block L_jj (lower), valid after potf2
   double Dv[NB][DS];   // the 8 inverses of the 8x8 diagonal blocks of L_jj: Dv[8*nb + r][c]
   double red[NTHREADS / 32];
+  double af[4];            // fused affine map of this matrix: s1, s2, s3, offset
   uint64_t full[STAGES];   // chunk landed: 256 cp.async arrivals (one per thread)
   uint64_t empty[STAGES];  // chunk consumed: 8 arrivals (one per warp)
   int bad;
@@ -125,17 +128,55 @@ __device__ __forceinline__ double negate(double x) {  // sign flip on the intege
 // last virtual row load a dummy row (never stored); the strictly upper part of the diagonal block
 // may be uninitialised memory (lower-only assembly) and is never consumed.
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void init_acc(const RowMap &rm, int v, int c0, int tg, bool full,
-                                         double (&accrow)[8][2]) {
+// The fused affine map (spb_affine): applied to covariance rows only, never to residual rows.
+struct AffRow {
+  const double *q;   // (nt) scaled row sums of this matrix, or nullptr
+  const double *dg;  // diagonal add: pointer to this matrix' value(s), or nullptr
+  int dg_vec;        // dg is an (nt) vector
+  bool norm;         // s1, s2, s3 present
+};
+
+// K' = s1 K + s2 (1 - q_i)(1 - q_j) - s3 q_i q_j + offset  ==  s1 K + C_i - D_i q_j  with the per-row
+// constants C_i = s2 (1 - q_i) + offset and D_i = s2 (1 - q_i) + s3 q_i: two FMAs per entry on the
+// accumulator-load path (the re-association moves K' by a few 1e-16 of the rank-one terms, which are
+// themselves ~1e-3 of K: far below the 1e-8 lnlike tolerance).
+__device__ __forceinline__ double aff_apply(const Smem &sm, const AffRow &af, double k, double Ci,
+                                            double Di, bool diag_row, int gi, int gc) {
+  if (af.norm) k = fma(sm.af[0], k, fma(-Di, af.q[gc], Ci));
+  else k += Ci;
+  if (diag_row && gc == gi && af.dg) k += af.dg_vec ? af.dg[gi] : af.dg[0];  // sp.py:1135-1144
+  return k;
+}
+
+__device__ __forceinline__ void init_acc(const Smem &sm, const RowMap &rm, const AffRow &af, bool aff_on,
+                                         int v, int c0, int tg, bool full, double (&accrow)[8][2]) {
   int kind;
   const double *p = rm.row(v, kind);
+  const bool cov_row = aff_on && (kind == KIND_DIAG || kind == KIND_BELOW);
+  const int gi = c0 + v;  // global row of a covariance row (diagonal-block and below rows alike)
+  double Ci = 0.0, Di = 0.0;
+  if (cov_row) {
+    Ci = sm.af[3];
+    if (af.norm) {
+      const double qi = af.q[gi];
+      const double a = sm.af[1] * (1.0 - qi);
+      Ci += a;
+      Di = a + sm.af[2] * qi;
+    }
+  }
+  const bool diag_row = (kind == KIND_DIAG);
   if (full) {
     if (p == nullptr) p = rm.Kb;
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
-      const double2 kv = *reinterpret_cast<const double2 *>(p + c0 + nt * 8 + 2 * tg);
+      const int gc = c0 + nt * 8 + 2 * tg;
+      const double2 kv = *reinterpret_cast<const double2 *>(p + gc);
       accrow[nt][0] = kv.x;
       accrow[nt][1] = kv.y;
+      if (cov_row) {
+        accrow[nt][0] = aff_apply(sm, af, kv.x, Ci, Di, diag_row, gi, gc);
+        accrow[nt][1] = aff_apply(sm, af, kv.y, Ci, Di, diag_row, gi, gc + 1);
+      }
     }
     return;
   }
@@ -153,6 +194,10 @@ __device__ __forceinline__ void init_acc(const RowMap &rm, int v, int c0, int tg
       const double2 kv = *reinterpret_cast<const double2 *>(p + gc);
       k0 = kv.x;
       k1 = (gc + 1 < rm.n) ? kv.y : 0.0;
+      if (cov_row) {
+        k0 = aff_apply(sm, af, k0, Ci, Di, diag_row, gi, gc);
+        if (gc + 1 < rm.n) k1 = aff_apply(sm, af, k1, Ci, Di, diag_row, gi, gc + 1);
+      }
       if (kind == KIND_DIAG) {
         if (col > v) k0 = 0.0;
         if (col + 1 > v) k1 = 0.0;
@@ -178,11 +223,19 @@ __device__ __forceinline__ void init_acc(const RowMap &rm, int v, int c0, int tg
 // ------------------------------------------------------------------------------------------
 // nt_lim < 8 (rows of the diagonal block): only the first nt_lim 8-column groups reach the
 // diagonal, the rest of the warp tile is never consumed and is not multiplied.
+// `init` loads (and, on the fused path, transforms) the accumulators; it runs AFTER the first two
+// chunks have been requested so that its global-load latency -- and the dependent affine FMAs --
+// overlap the cp.async prologue instead of preceding it.
+template <class Init>
 __device__ __forceinline__ void gemm_tile(Smem &sm, const RowMap &rm, int v0, int c0, int nvirt,
-                                          int nt_lim, unsigned &it, double (&acc)[2][8][2]) {
+                                          int nt_lim, unsigned &it, double (&acc)[2][8][2],
+                                          Init init) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, tg = lane & 3;
   const int nchunks = c0 / KC;
-  if (nchunks == 0) return;
+  if (nchunks == 0) {
+    init();
+    return;
+  }
   const bool warp_live = (v0 + warp * 16) < nvirt;
 
   // this thread's cp.async assignments: A: 4 x 16B, B: 2 x 16B per chunk
@@ -228,6 +281,7 @@ __device__ __forceinline__ void gemm_tile(Smem &sm, const RowMap &rm, int v0, in
 
   issue(0, it, true);
   if (nchunks > 1) issue(1, it + 1, true);
+  init();
   for (int ch = 0; ch < nchunks; ++ch) {
     const unsigned x = it + ch;
     const unsigned st = x % STAGES;
@@ -532,6 +586,25 @@ __global__ void __launch_bounds__(NTHREADS, 2) potrf_lnlike_kernel(PotrfParams p
       rm.nrhs = min(p.rows_per_cta, p.M - rm.rb);
       quad_out = p.quad;
     }
+    AffRow af;
+    af.q = nullptr;
+    af.dg = nullptr;
+    af.dg_vec = 0;
+    af.norm = false;
+    if (p.aff_on && p.mode == MODE_FACTOR) {
+      af.norm = (p.aff.scal != nullptr) && (p.aff.q != nullptr);
+      if (af.norm) af.q = p.aff.q + (size_t)item * p.n;
+      if (p.aff.diag) {
+        af.dg = p.aff.diag + (size_t)item * p.aff.diag_stride;
+        af.dg_vec = (p.aff.diag_kind == 1);
+      }
+      if (tid == 0) {
+        sm.af[0] = af.norm ? p.aff.scal[4 * (size_t)item + 0] : 1.0;
+        sm.af[1] = af.norm ? p.aff.scal[4 * (size_t)item + 1] : 0.0;
+        sm.af[2] = af.norm ? p.aff.scal[4 * (size_t)item + 2] : 0.0;
+        sm.af[3] = p.aff.offset ? p.aff.offset[(size_t)item * p.aff.offset_stride] : 0.0;
+      }
+    }
     if (tid == 0) sm.bad = 0;
     if (quad_out) {
       if (p.mode == MODE_FACTOR) {
@@ -568,11 +641,12 @@ __global__ void __launch_bounds__(NTHREADS, 2) potrf_lnlike_kernel(PotrfParams p
         // MODE_FACTOR, first tile: rows 0..63 are the diagonal block (warps 0-3), rows 64..127 the
         // first rows below it (warps 4-7)
         const bool diag_tile = (p.mode == MODE_FACTOR) && (v0 == 0);
+        gemm_tile(sm, rm, v0, c0, nvirt, (diag_tile && warp < 4) ? 2 * warp + 2 : 8, it, acc, [&]() {
 #pragma unroll
-        for (int mt = 0; mt < 2; ++mt)
-          init_acc(rm, v0 + warp * 16 + mt * 8 + g, c0, tg, full_panel, acc[mt]);
-        gemm_tile(sm, rm, v0, c0, nvirt, (diag_tile && warp < 4) ? 2 * warp + 2 : 8, it,
-                  acc);   // acc = K - L L^T = P
+          for (int mt = 0; mt < 2; ++mt)
+            init_acc(sm, rm, af, p.aff_on != 0, v0 + warp * 16 + mt * 8 + g, c0, tg, full_panel,
+                     acc[mt]);
+        });   // acc = K - L L^T = P
         if (diag_tile) {
           if (warp < 4) {
 #pragma unroll
@@ -691,6 +765,37 @@ extern "C" int spb_cholesky_lnlike(spb_context *ctx, int B, int nt, double *K, i
   p.B = B;
   p.mode = MODE_FACTOR;
   p.rows_per_cta = 0;
+  p.aff = spb_affine{};
+  p.aff_on = 0;
+  return potrf_launch(ctx, p, stream);
+}
+
+extern "C" int spb_cholesky_lnlike_affine(spb_context *ctx, int B, int nt, double *K, int ldk,
+                                          long long K_stride, const spb_affine *affine, int M,
+                                          double *resid, int ldr, long long resid_stride,
+                                          double *lnlike, double *quad, double *logdet,
+                                          int32_t *info, void *stream) {
+  SPB_REQUIRE(ctx != nullptr && affine != nullptr, "cholesky_lnlike_affine: null argument");
+  SPB_REQUIRE((affine->scal == nullptr) == (affine->q == nullptr),
+              "cholesky_lnlike_affine: scal and q must be given together");
+  PotrfParams p;
+  p.K = K;
+  p.n = nt;
+  p.ld = ldk;
+  p.strideK = K_stride;
+  p.R = (M > 0) ? resid : nullptr;
+  p.M = M;
+  p.ldr = ldr;
+  p.strideR = resid_stride;
+  p.lnlike = lnlike;
+  p.quad = quad;
+  p.logdet = logdet;
+  p.info = info;
+  p.B = B;
+  p.mode = MODE_FACTOR;
+  p.rows_per_cta = 0;
+  p.aff = *affine;
+  p.aff_on = 1;
   return potrf_launch(ctx, p, stream);
 }
 
@@ -712,6 +817,8 @@ extern "C" int spb_cholesky_solve_rows(spb_context *ctx, int nt, const double *L
   p.logdet = nullptr;
   p.info = nullptr;
   p.B = 1;
+  p.aff = spb_affine{};
+  p.aff_on = 0;
   p.mode = MODE_SOLVE;
   // spread the RHS rows over the whole GPU in multiples of 16 rows (one warp's share)
   // one full 128-row tile per work item (a tile costs the same DMMA time however many of its

@@ -392,6 +392,7 @@ class StarryProcess(object):
     def _noise_model(self, nt, data_cov, baseline_var, keep, lower_only=False, b0=0):
         nm = _lib.NoiseModel()
         nm.lower_only = 1 if lower_only else 0
+        nm.defer = 0
         nm.normalized = 1 if self._normalized else 0
         nm.normalization_order = self._normN
         nm.normalization_zmax = self._normzmax
@@ -433,14 +434,18 @@ class StarryProcess(object):
         return nm
 
     def _flux_cov_chunk(self, b0, b1, t, inc, p, rta1, marg, data_cov, baseline_var, ldk,
-                        lower_only=False):
+                        lower_only=False, defer=False):
         """GP mean (scalar per element) and the (noise-augmented) covariance for elements b0:b1.
-        Returns (gp_mean, K, z)."""
+        Returns (gp_mean, K, z), or with ``defer`` (marginal branch, scalar / per-point noise terms)
+        (gp_mean, K_raw, z, affine, keepalive): the covariance is left raw and the normalisation +
+        noise are applied inside the Cholesky kernel (``spb_cholesky_lnlike_affine``)."""
         lib, h = self._lib, self._ctx.handle
         Bc, nt = b1 - b0, t.numel()
         dev = self.device
         keep = []
         nm = self._noise_model(nt, data_cov, baseline_var, keep, lower_only and marg, b0=b0)
+        defer = bool(defer and marg and lower_only and nm.data_kind != 2 and nm.base_kind != 2)
+        nm.defer = 1 if defer else 0
         mean_ylm = self._mean_ylm[b0:b1]
         cov_ylm = self._cov_ylm[b0:b1]
         info = self._info[b0:b1]
@@ -483,6 +488,19 @@ class StarryProcess(object):
             _lib.check(lib.spb_assemble_conditional(h, Bc, nt, _ptr(gp_mean), ctypes.byref(nm),
                                                     _ptr(K), ldk, _ptr(z), _ptr(info), _ptr(ws_as),
                                                     nb_as, _stream()))
+        if defer:
+            af = _lib.Affine()
+            if self._normalized:
+                qp, sp_ = ctypes.c_void_p(), ctypes.c_void_p()
+                lib.spb_assemble_workspace_layout(Bc, nt, _ptr(ws_as), ctypes.byref(qp),
+                                                  ctypes.byref(sp_))
+                af.q, af.scal = qp, sp_
+            af.diag = nm.data_cov
+            af.diag_kind = nm.data_kind
+            af.diag_stride = 0
+            af.offset = nm.baseline_var
+            af.offset_stride = nm.base_stride
+            return gp_mean, K, z, af, (keep, ws_as)
         return gp_mean, K, z
 
     def _chunks(self, nt, ldk):
@@ -568,8 +586,10 @@ class StarryProcess(object):
         with torch.cuda.device(dev):
             for b0, b1 in self._chunks(nt, ldk):
                 Bc = b1 - b0
-                gp_mean, K, z = self._flux_cov_chunk(b0, b1, t, inc, p, rta1, marg, data_cov, bvar,
-                                                     ldk, lower_only=True)
+                out = self._flux_cov_chunk(b0, b1, t, inc, p, rta1, marg, data_cov, bvar, ldk,
+                                           lower_only=True, defer=True)
+                gp_mean, K, z = out[:3]
+                affine = out[3] if len(out) > 3 else None
                 zs.append(z)
                 # r = flux - (gp_mean + baseline_mean)  (sp.py:1157-1161); normalised: mean == 0
                 resid = torch.zeros(Bc, M, ldk, dtype=torch.float64, device=dev)
@@ -585,19 +605,29 @@ class StarryProcess(object):
                     # K): factor on one CTA, then spread the RHS rows over the whole GPU
                     logdet = torch.empty(1, dtype=torch.float64, device=dev)
                     quad = torch.empty(M, dtype=torch.float64, device=dev)
-                    _lib.check(lib.spb_cholesky_lnlike(
-                        h, 1, nt, _ptr(K), ldk, nt * ldk, 0, None, ldk, 0, None, None,
-                        _ptr(logdet), _ptr(self._info[b0:b1]), _stream()))
+                    if affine is not None:
+                        _lib.check(lib.spb_cholesky_lnlike_affine(
+                            h, 1, nt, _ptr(K), ldk, nt * ldk, ctypes.byref(affine), 0, None, ldk, 0,
+                            None, None, _ptr(logdet), _ptr(self._info[b0:b1]), _stream()))
+                    else:
+                        _lib.check(lib.spb_cholesky_lnlike(
+                            h, 1, nt, _ptr(K), ldk, nt * ldk, 0, None, ldk, 0, None, None,
+                            _ptr(logdet), _ptr(self._info[b0:b1]), _stream()))
                     _lib.check(lib.spb_cholesky_solve_rows(h, nt, _ptr(K), ldk, M, _ptr(resid), ldk,
                                                            _ptr(quad), _stream()))
                     ll = -0.5 * quad.sum() - M * logdet[0] - 0.5 * nt * M * math.log(2 * math.pi)
                     flagged = (self._info[b0:b1] != 0) | torch.isnan(ll)
                     lnlike[b0:b1] = torch.where(flagged, torch.full_like(ll, -float("inf")), ll)
+                elif affine is not None:
+                    _lib.check(lib.spb_cholesky_lnlike_affine(
+                        h, Bc, nt, _ptr(K), ldk, nt * ldk, ctypes.byref(affine), M, _ptr(resid), ldk,
+                        M * ldk, _ptr(lnlike[b0:b1]), None, None, _ptr(self._info[b0:b1]),
+                        _stream()))
                 else:
                     _lib.check(lib.spb_cholesky_lnlike(
                         h, Bc, nt, _ptr(K), ldk, nt * ldk, M, _ptr(resid), ldk, M * ldk,
                         _ptr(lnlike[b0:b1]), None, None, _ptr(self._info[b0:b1]), _stream()))
                 self._mark_end(ev)
-                del K, resid
+                del K, resid, out
         self._z = torch.cat(zs)
         return self._out(lnlike)
