@@ -144,18 +144,25 @@ __global__ void __launch_bounds__(NT1, 2) moments_k1(K1Params p) {
   lm_of(tid, l1, m1);
   const int j1 = m1 + l1, i1 = l1 - m1;
   {
-    double y[31];
+    double y[32];   // column 31 of the padded basis is zero
 #pragma unroll
-    for (int a = 0; a < 31; ++a) y[a] = 0.0;
+    for (int a = 0; a < 32; ++a) y[a] = 0.0;
     const double *Z = tab + SPB_TAB_LAT_Z;
     int l2 = 0, m2 = 0;
     for (int n2 = 0; n2 < 256; ++n2) {
       const int J = j1 + m2 + l2, I = i1 + l2 - m2;
-      double qv = 0.0;
-      if (!(I & 1)) qv = ldexp(sm.tt[J >> 1][I >> 1], -(l1 + l2));
-      const double *zr = Z + n2 * 32;
+      // Q(n1, n2) vanishes unless l+m has the same parity for both indices (latitude.h:146-172):
+      // the warp-uniform row of Z is only fetched (as 16-byte loads) when this thread needs it
+      if (!(I & 1)) {
+        const double qv = ldexp(sm.tt[J >> 1][I >> 1], -(l1 + l2));
+        const double2 *zr = reinterpret_cast<const double2 *>(Z + n2 * 32);
 #pragma unroll
-      for (int a = 0; a < 31; ++a) y[a] = fma(qv, zr[a], y[a]);
+        for (int a = 0; a < 16; ++a) {
+          const double2 z2 = __ldg(zr + a);
+          y[2 * a] = fma(qv, z2.x, y[2 * a]);
+          y[2 * a + 1] = fma(qv, z2.y, y[2 * a + 1]);
+        }
+      }
       if (++m2 > l2) {
         ++l2;
         m2 = -l2;

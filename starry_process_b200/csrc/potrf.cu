@@ -167,15 +167,51 @@ __device__ __forceinline__ void init_acc(const Smem &sm, const RowMap &rm, const
   const bool diag_row = (kind == KIND_DIAG);
   if (full) {
     if (p == nullptr) p = rm.Kb;
+    // all global loads first (no dependent instruction or branch in between: one batch of
+    // outstanding requests per tile), then the branch-free affine arithmetic
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
-      const int gc = c0 + nt * 8 + 2 * tg;
-      const double2 kv = *reinterpret_cast<const double2 *>(p + gc);
+      const double2 kv = *reinterpret_cast<const double2 *>(p + c0 + nt * 8 + 2 * tg);
       accrow[nt][0] = kv.x;
       accrow[nt][1] = kv.y;
-      if (cov_row) {
-        accrow[nt][0] = aff_apply(sm, af, kv.x, Ci, Di, diag_row, gi, gc);
-        accrow[nt][1] = aff_apply(sm, af, kv.y, Ci, Di, diag_row, gi, gc + 1);
+    }
+    if (cov_row) {
+      if (af.norm) {
+        const double s1 = sm.af[0];
+        const double *qp = af.q + c0 + 2 * tg;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {   // two batches of 8 loads: bounded register footprint
+          double q0[4], q1[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            q0[k] = __ldg(qp + (4 * h + k) * 8);
+            q1[k] = __ldg(qp + (4 * h + k) * 8 + 1);
+          }
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int nt = 4 * h + k;
+            accrow[nt][0] = fma(s1, accrow[nt][0], fma(-Di, q0[k], Ci));
+            accrow[nt][1] = fma(s1, accrow[nt][1], fma(-Di, q1[k], Ci));
+          }
+        }
+      } else {
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+          accrow[nt][0] += Ci;
+          accrow[nt][1] += Ci;
+        }
+      }
+      if (diag_row && af.dg) {   // data_cov on the diagonal (sp.py:1135-1144): column v of row v
+        const double dgv = af.dg_vec ? af.dg[gi] : af.dg[0];
+        const bool mine = ((v & 7) >> 1) == tg;
+        // unconditional adds of a selected operand: a guarded `accrow[nt] += dgv` is turned into a
+        // dynamically indexed access by the compiler, which sends the accumulators to local memory
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+          const bool hit = mine && nt == (v >> 3);
+          accrow[nt][0] += (hit && !(v & 1)) ? dgv : 0.0;
+          accrow[nt][1] += (hit && (v & 1)) ? dgv : 0.0;
+        }
       }
     }
     return;
