@@ -38,19 +38,30 @@ def _digest():
     return h.hexdigest()
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, defines=(), lib=None):
+    """``defines``/``lib``: instrumented debug variants (e.g. the phase-timer build used by
+    scripts/gpu_potrf_prof.py, loaded through SPB200_LIB); the product library takes neither."""
     nvcc = os.environ.get("NVCC", "nvcc")
+    if lib is not None:
+        return _compile(nvcc, lib, os.path.join(HERE, "build_" + os.path.basename(lib)), verbose,
+                        ["-D" + d for d in defines])
     dig = _digest()
     if (not force and os.path.exists(LIB) and os.path.exists(STAMP)
             and open(STAMP).read().strip() == dig):
         return LIB
-    objdir = os.path.join(HERE, "build")
+    _compile(nvcc, LIB, os.path.join(HERE, "build"), verbose, [])
+    with open(STAMP, "w") as fh:
+        fh.write(dig)
+    return LIB
+
+
+def _compile(nvcc, LIB, objdir, verbose, extra):
     os.makedirs(objdir, exist_ok=True)
     objs = []
     procs = []
     for src in _sources():
         obj = os.path.join(objdir, os.path.basename(src)[:-3] + ".o")
-        flags = list(NVCC_FLAGS)
+        flags = list(NVCC_FLAGS) + list(extra)
         if os.path.basename(src) in NO_FMA:
             flags += ["-fmad=false"]
         if verbose:
@@ -70,10 +81,12 @@ def build(force=False, verbose=False):
     cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a",
                                                 "-cudart", "static"]
     subprocess.check_call(cmd)
-    with open(STAMP, "w") as fh:
-        fh.write(dig)
     return LIB
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    if "--prof" in sys.argv:
+        print(build(defines=["SPB_POTRF_PROF"], lib=os.path.join(HERE, "libspb200_prof.so"),
+                    verbose="-v" in sys.argv))
+    else:
+        print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

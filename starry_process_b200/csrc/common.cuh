@@ -9,6 +9,7 @@
 #include "../../include/spb200.h"
 
 #define SPB_LMAX 15
+#define SPB_NUM_COUNTERS 256
 #define SPB_NSM_DEFAULT 148
 
 struct spb_context {
@@ -17,6 +18,10 @@ struct spb_context {
   double *d_tables;       // device copy of the packed constant blob
   size_t tables_count;
   long long launches;     // number of kernels launched through this context
+  // ring of work counters for kernels that claim their work items dynamically (one per launch,
+  // zeroed in-stream before the launch, so that concurrent streams never share one)
+  unsigned int *d_counters;
+  unsigned int counter_next;
   // offsets (in doubles) into d_tables, see spb_tables.h
   const double *tab(size_t off) const { return d_tables + off; }
 };

@@ -29,6 +29,10 @@ extern "C" int spb_create(int device, const double *tables_host, size_t tables_c
   ctx->d_tables = nullptr;
   ctx->tables_count = tables_count;
   ctx->launches = 0;
+  ctx->d_counters = nullptr;
+  ctx->counter_next = 0;
+  SPB_CHECK_CUDA(cudaMalloc(&ctx->d_counters, SPB_NUM_COUNTERS * sizeof(unsigned int)));
+  SPB_CHECK_CUDA(cudaMemset(ctx->d_counters, 0, SPB_NUM_COUNTERS * sizeof(unsigned int)));
   if (tables_count > 0) {
     SPB_REQUIRE(tables_host != nullptr, "spb_create: null table blob");
     SPB_CHECK_CUDA(cudaMalloc(&ctx->d_tables, tables_count * sizeof(double)));
@@ -47,6 +51,7 @@ extern "C" void spb_destroy(spb_context *ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   if (ctx->d_tables) cudaFree(ctx->d_tables);
+  if (ctx->d_counters) cudaFree(ctx->d_counters);
   delete ctx;
 }
 

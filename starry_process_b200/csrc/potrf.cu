@@ -53,6 +53,7 @@ struct PotrfParams {
   int B;
   int mode;
   int rows_per_cta;  // MODE_SOLVE: RHS rows per work item
+  unsigned int *counter;  // zeroed before the launch: work items beyond the first wave are claimed here
   spb_affine aff;    // fused last assembly step (scal == q == diag == offset == NULL: none)
   int aff_on;
 };
@@ -104,11 +105,33 @@ struct Smem {
   double Ld[NB][LS];   // diagonal block L_jj (lower), valid after potf2
   double Dv[NB][DS];   // the 8 inverses of the 8x8 diagonal blocks of L_jj: Dv[8*nb + r][c]
   double red[NTHREADS / 32];
+  double dpiv[NB];         // pivots L_ii^2 of the current diagonal block
   double af[4];            // fused affine map of this matrix: s1, s2, s3, offset
   uint64_t full[STAGES];   // chunk landed: 256 cp.async arrivals (one per thread)
   uint64_t empty[STAGES];  // chunk consumed: 8 arrivals (one per warp)
   int bad;
+  int next_item;
+#ifdef SPB_POTRF_PROF
+  unsigned long long prof[2][16];
+#endif
 };
+
+#ifdef SPB_POTRF_PROF
+// Phase timers (debug build only, scripts/gpu_potrf_prof.py): lane 0 of warp 0 (diagonal rows) and of
+// warp 4 (rows below) accumulate clock64 deltas per phase in shared memory.
+__device__ unsigned long long g_potrf_prof[2][16];
+__device__ unsigned long long g_potrf_clk[4];  // CTA 0: clock64 and globaltimer at start / end
+__device__ __forceinline__ unsigned long long gtimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define PROF_DECL unsigned long long _pt = clock64(); const int _pw = (threadIdx.x == 0) ? 0 : ((threadIdx.x == 96) ? 1 : -1)
+#define PROF_MARK(sm, k) do { if (_pw >= 0) { unsigned long long _n = clock64(); (sm).prof[_pw][k] += _n - _pt; _pt = _n; } } while (0)
+#else
+#define PROF_DECL
+#define PROF_MARK(sm, k)
+#endif
 
 __device__ __forceinline__ int swz(int row, int k) {  // element index inside a stage row
   return (((k >> 1) ^ ((row & 3) << 1)) << 1) | (k & 1);
@@ -268,8 +291,10 @@ __device__ __forceinline__ void gemm_tile(Smem &sm, const RowMap &rm, int v0, in
                                           Init init) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, tg = lane & 3;
   const int nchunks = c0 / KC;
+  PROF_DECL;
   if (nchunks == 0) {
     init();
+    PROF_MARK(sm, 1);
     return;
   }
   const bool warp_live = (v0 + warp * 16) < nvirt;
@@ -315,9 +340,12 @@ __device__ __forceinline__ void gemm_tile(Smem &sm, const RowMap &rm, int v0, in
 #pragma unroll
   for (int kk = 0; kk < KC / 4; ++kk) koff[kk] = swz(g, kk * 4 + tg);
 
+  PROF_MARK(sm, 9);
   issue(0, it, true);
   if (nchunks > 1) issue(1, it + 1, true);
+  PROF_MARK(sm, 0);
   init();
+  PROF_MARK(sm, 1);
   for (int ch = 0; ch < nchunks; ++ch) {
     const unsigned x = it + ch;
     const unsigned st = x % STAGES;
@@ -327,6 +355,9 @@ __device__ __forceinline__ void gemm_tile(Smem &sm, const RowMap &rm, int v0, in
     bool early = false;
     if (ch + 2 < nchunks) early = issue(ch + 2, x + 2, false);
     mbar_wait(&sm.full[st], (x / STAGES) & 1u);  // chunk ch landed, for every thread's copies
+#ifdef SPB_POTRF_PROF
+    if (ch == 0) PROF_MARK(sm, 2);
+#endif
     if (warp_live) {
       const double *Aw = &sm.As[st][warp * 16 + g][0];
       const double *Bw = &sm.Bs[st][g][0];
@@ -365,6 +396,7 @@ __device__ __forceinline__ void gemm_tile(Smem &sm, const RowMap &rm, int v0, in
     if (!early && ch + 2 < nchunks) issue(ch + 2, x + 2, true);
   }
   it += nchunks;
+  PROF_MARK(sm, 3);
 }
 
 // Accumulator fragment (8x8, C layout) -> A fragment of its k-block q (columns 4q..4q+3).
@@ -467,105 +499,165 @@ __device__ __forceinline__ void diag_inverses(Smem &sm) {
   __syncthreads();
 }
 
-// The accumulators of the rows below the diagonal block (warps 4-7 of the diagonal tile) must
-// survive potf2_block, whose 16 register-resident matrix elements per thread would otherwise push
-// the kernel past 128 registers (ptxas then demotes those 16 values -- the critical path of the
-// factorisation -- to local memory).  The cp.async stage buffers are idle at that point, so the
-// accumulators are parked there: [k][tid] double2 slots, conflict-free.
-__device__ __forceinline__ void park_acc(Smem &sm, const double (&acc)[2][8][2]) {
-  double2 *slot = reinterpret_cast<double2 *>(&sm.As[0][0][0]) + threadIdx.x;
-#pragma unroll
-  for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-    for (int nt = 0; nt < 8; ++nt)
-      slot[(mt * 8 + nt) * NTHREADS] = make_double2(acc[mt][nt][0], acc[mt][nt][1]);
+// ---- reciprocal / reciprocal square root for the pivot chain ---------------------------------
+// MUFU seed (~2^-20) + two Newton steps on the FMA pipe: 1 + 4 dependent instructions instead of the
+// ~12 of an IEEE division, ~1 ulp.  The pivot recurrence d_{k+1} = a - v^2 / d_k is the serial
+// spine of the whole factorisation, and its FP64 instructions queue behind the sibling CTA's DMMAs.
+__device__ __forceinline__ double fast_rcp(double d) {
+  double x;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(d));
+  double e = fma(-d, x, 1.0);
+  x = fma(x, e, x);
+  e = fma(-d, x, 1.0);
+  return fma(x, e, x);
 }
-__device__ __forceinline__ void unpark_acc(const Smem &sm, double (&acc)[2][8][2]) {
-  const double2 *slot = reinterpret_cast<const double2 *>(&sm.As[0][0][0]) + threadIdx.x;
-#pragma unroll
-  for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
-      const double2 v = slot[(mt * 8 + nt) * NTHREADS];
-      acc[mt][nt][0] = v.x;
-      acc[mt][nt][1] = v.y;
-    }
+__device__ __forceinline__ double fast_rsqrt(double d) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+  double e = fma(-d * y, y, 1.0);
+  y = fma(0.5 * y, e, y);
+  e = fma(-d * y, y, 1.0);
+  return fma(0.5 * y, e, y);
 }
-static_assert(sizeof(double) * (STAGES * (TM + NB) * KC) >= 65536 + 2 * (NB + 2) * sizeof(double),
-              "stage buffers too small to park the accumulators");
 
-// 64x64 Cholesky of sm.Ld (lower triangle), scalar FP64, register-resident: thread t owns row
-// i = t / 4 and the 16 columns [16 (t % 4), 16 (t % 4) + 16).  Per column step the owners publish
-// the pivot column through a double-buffered shared vector (ONE barrier per step), everybody
-// applies the rank-1 update to its registers; the column scaling by 1/sqrt(d_j) is deferred to
-// the end (LDL^T-style), so the dependent chain per step is barrier -> LDS -> 1/d -> FMA.
-// Produces Ld (lower, upper zeroed), Dv, and returns this thread's share of sum(log L_ii) over
-// the valid columns.
-__device__ __forceinline__ double potf2_block(Smem &sm, int nvalid) {
-  const int tid = threadIdx.x;
-  const int i = tid >> 2, cg = tid & 3;
-  // pivot-column broadcast buffers (double-buffered) live in the idle stage buffers, behind the
-  // 64 KB used to park the accumulators (see park_acc); slot NB of each buffer carries 1 / pivot
-  double(*col)[NB + 2] = reinterpret_cast<double(*)[NB + 2]>(&sm.As[0][0][0] + 8192);
-  double a[16];
-  double dpiv = 1.0;
+__device__ __forceinline__ void bar_diag() {  // warps 0-3 only (named barrier 1)
+  asm volatile("bar.sync 1, 128;\n" ::: "memory");
+}
+
+// Cholesky of ONE 8x8 tile held in the accumulator layout of a warp (lane (g, tg): row g, columns
+// 2 tg, 2 tg + 1), entirely with shuffles: no shared memory, no barrier.  Gaussian elimination
+// without scaling (v_ik = L_ik sqrt(d_k)), the same row operations applied to an identity tile, so
+// that L = V diag(d^-1/2) and L^-1 = diag(d^-1/2) W come out together.  The strictly upper part of
+// the tile may be garbage (lower-only assembly): it is never read.
+//   on exit: (v0, v1) = L tile, (w0, w1) = L^-1 tile (upper triangle exactly 0), returns d_g
+__device__ __forceinline__ double potf2_tile8(double &v0, double &v1, double &w0, double &w1, int lane,
+                                              bool &bad) {
+  const int g = lane >> 2, tg = lane & 3;
+  w0 = (2 * tg == g) ? 1.0 : 0.0;
+  w1 = (2 * tg + 1 == g) ? 1.0 : 0.0;
+  double dmine = 1.0, rs_row = 1.0, rs_c0 = 1.0, rs_c1 = 1.0;
 #pragma unroll
-  for (int jj = 0; jj < 16; ++jj) a[jj] = sm.Ld[i][cg * 16 + jj];
-  if (tid == 0) col[0][NB] = 1.0 / a[0];
-#pragma unroll 1
-  for (int cgc = 0; cgc < 4; ++cgc) {
-#pragma unroll
-    for (int cc = 0; cc < 16; ++cc) {
-      const int c = cgc * 16 + cc;
-      double *colb = col[c & 1];
-      if (cg == cgc) colb[i] = a[cc];
-      __syncthreads();
-      const double d = colb[c];
-      if (c == i) dpiv = d;  // every thread of row i sees its pivot go by at step c == i
-      // 1 / d_c was computed by the owner of the pivot during the PREVIOUS step, off this step's
-      // critical path (and once, not by all 256 threads on the FP64 pipe the other CTA's DMMAs use)
-      const double li = colb[i] * colb[NB];
-      {
-        const int jn = (cc + 1) & 15;              // compile-time: next pivot's slot ...
-        const int cgn = cgc + (cc == 15 ? 1 : 0);  // ... and column group
-        if (i == c + 1 && cg == cgn) col[(c + 1) & 1][NB] = 1.0 / (a[jn] - li * colb[c + 1]);
+  for (int k = 0; k < 8; ++k) {
+    // pivot d_k: element (k, k) = lane 4k + k/2, register k & 1
+    double d = __shfl_sync(0xffffffffu, (k & 1) ? v1 : v0, 4 * k + (k >> 1));
+    if (!(d > 0.0)) {  // also NaN
+      bad = true;
+      d = 1.0;
+    }
+    const double r = fast_rcp(d);
+    // off the chain: d_k^-1/2 for whoever needs it (row scaling of W, column scaling of V)
+    const double rs = fast_rsqrt(d);
+    if (g == k) {
+      dmine = d;
+      rs_row = rs;
+    }
+    if (2 * tg == k) rs_c0 = rs;
+    if (2 * tg + 1 == k) rs_c1 = rs;
+    if (k < 7) {
+      // column k of V: v_ik from the lane of my row, v_jk for my two columns j
+      const double vk = (k & 1) ? v1 : v0;
+      const double vik = __shfl_sync(0xffffffffu, vk, (lane & ~3) | (k >> 1));
+      const double vj0 = __shfl_sync(0xffffffffu, vk, 8 * tg + (k >> 1));
+      const double vj1 = __shfl_sync(0xffffffffu, vk, 8 * tg + 4 + (k >> 1));
+      const double wk0 = __shfl_sync(0xffffffffu, w0, 4 * k + tg);
+      const double wk1 = __shfl_sync(0xffffffffu, w1, 4 * k + tg);
+      const double m = vik * r;
+      if (g > k) {
+        if (2 * tg > k) v0 = fma(-m, vj0, v0);
+        if (2 * tg + 1 > k) v1 = fma(-m, vj1, v1);
+        w0 = fma(-m, wk0, w0);
+        w1 = fma(-m, wk1, w1);
       }
-      if (c < NB - 1 && i > c) {
+    }
+  }
+  v0 *= rs_c0;
+  v1 *= rs_c1;
+  w0 *= rs_row;
+  w1 *= rs_row;
+  return dmine;
+}
+
+// 64x64 Cholesky of the diagonal block, IN THE ACCUMULATOR REGISTERS of warps 0-3 (warp w holds
+// rows 16 w .. 16 w + 15 of P = K_jj - L L^T as 2 x 8 accumulator tiles).  Two-level: for each of the
+// 8 sub-panels s the owner warp factors the 8x8 diagonal tile with shuffles (potf2_tile8) and
+// publishes L_ss and L_ss^-1; every warp solves its tiles below on the tensor pipe
+// (X = P L_ss^-T, two DMMAs per tile) and publishes X; the trailing update P_ij -= X_i X_j^T is DMMA
+// again.  Only column s + 1 is updated on the critical path; the update of the later columns is
+// deferred until after the next diagonal tile has been factored, so the serial spine per sub-panel
+// is  8 pivots -> barrier -> 2 DMMAs -> barrier -> 2 DMMAs.  Warps 4-7 (rows below the block) keep
+// their accumulators in registers and wait at the CTA barrier that follows.
+// Produces sm.Ld (lower; strictly-upper 8x8 tiles untouched), sm.Dv and the pivots sm.dpiv = L_ii^2.
+__device__ __forceinline__ void potf2_regs(Smem &sm, double (&acc)[2][8][2], int warp, int lane) {
+  const int g = lane >> 2, tg = lane & 3;
+  bool bad = false;
+  PROF_DECL;
 #pragma unroll
-        for (int jj = 0; jj < 16; ++jj) {
-          const int j = cg * 16 + jj;
-          if (j > c && j <= i) a[jj] -= li * colb[j];
+  for (int s = 0; s < 8; ++s) {
+    PROF_MARK(sm, 14);
+    if (warp == (s >> 1)) {
+      double w0, w1;
+      const double dg = potf2_tile8(acc[s & 1][s][0], acc[s & 1][s][1], w0, w1, lane, bad);
+      *reinterpret_cast<double2 *>(&sm.Ld[8 * s + g][8 * s + 2 * tg]) =
+          make_double2(acc[s & 1][s][0], acc[s & 1][s][1]);
+      *reinterpret_cast<double2 *>(&sm.Dv[8 * s + g][2 * tg]) = make_double2(w0, w1);
+      if (tg == 0) sm.dpiv[8 * s + g] = dg;
+      PROF_MARK(sm, 11);
+    }
+    // deferred part of the previous sub-panel's update: columns beyond s.  The A fragments are
+    // re-read from the published X (no registers held across the barriers).
+    if (s > 0) {
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        double xq[2];
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+          xq[mt] = negate(sm.Ld[16 * warp + 8 * mt + g][8 * (s - 1) + 4 * q + tg]);
+#pragma unroll
+        for (int nt = s + 1; nt < 8; ++nt) {
+          const double b = sm.Ld[8 * nt + g][8 * (s - 1) + 4 * q + tg];
+#pragma unroll
+          for (int mt = 0; mt < 2; ++mt)
+            if (nt <= 2 * warp + mt) dmma_m8n8k4(acc[mt][nt][0], acc[mt][nt][1], xq[mt], b);
         }
       }
     }
-  }
-  // pivots: thread (i, cg = i / 16) holds d_i in a[i % 16]
-  double logpart = 0.0, sqd = 1.0;
-  if (cg == (i >> 4)) {
-    double di = dpiv;
-    if (!(di > 0.0)) {  // also catches NaN
-      sm.bad = 1;
-      di = 1.0;
-    }
-    sqd = sqrt(di);
-    col[0][i] = 1.0 / sqd;   // col[1] was the last buffer written by the loop (c = 63)
-    if (i < nvalid) logpart = 0.5 * log(di);
-  }
-  __syncthreads();
-  // scale columns: L[i][j] = v[i][j] / sqrt(d_j); zero the strict upper triangle
+    bar_diag();  // L_ss^-1 published
+    PROF_MARK(sm, 12);
+    double xa[2][2] = {{0.0, 0.0}, {0.0, 0.0}};  // -X fragments of this sub-panel
+    {
+      const double d0 = sm.Dv[8 * s + g][tg], d1 = sm.Dv[8 * s + g][4 + tg];
 #pragma unroll
-  for (int jj = 0; jj < 16; ++jj) {
-    const int j = cg * 16 + jj;
-    double v = 0.0;
-    if (j <= i) {
-      const double rsj = col[0][j];
-      v = (j == i) ? sqd : a[jj] * rsj;
+      for (int mt = 0; mt < 2; ++mt) {
+        if (2 * warp + mt > s) {
+          const double a0 = c_to_a(acc[mt][s][0], acc[mt][s][1], 0, lane);
+          const double a1 = c_to_a(acc[mt][s][0], acc[mt][s][1], 1, lane);
+          double x0 = 0.0, x1 = 0.0;
+          dmma_m8n8k4(x0, x1, a0, d0);
+          dmma_m8n8k4(x0, x1, a1, d1);
+          acc[mt][s][0] = x0;
+          acc[mt][s][1] = x1;
+          *reinterpret_cast<double2 *>(&sm.Ld[16 * warp + 8 * mt + g][8 * s + 2 * tg]) =
+              make_double2(x0, x1);
+          xa[mt][0] = negate(c_to_a(x0, x1, 0, lane));
+          xa[mt][1] = negate(c_to_a(x0, x1, 1, lane));
+        }
+      }
     }
-    sm.Ld[i][j] = v;
+    bar_diag();  // column block s of L_jj published
+    PROF_MARK(sm, 13);
+    if (s < 7) {  // critical path: column s + 1 only
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const double b = sm.Ld[8 * (s + 1) + g][8 * s + 4 * q + tg];
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+          if (s + 1 <= 2 * warp + mt)
+            dmma_m8n8k4(acc[mt][s + 1][0], acc[mt][s + 1][1], xa[mt][q], b);
+      }
+    }
   }
-  __syncthreads();
-  diag_inverses(sm);
-  return logpart;
+  if (bad) sm.bad = 1;
+  PROF_MARK(sm, 14);
 }
 
 __device__ __forceinline__ double block_sum(Smem &sm, double v) {
@@ -597,10 +689,21 @@ __global__ void __launch_bounds__(NTHREADS, 2) potrf_lnlike_kernel(PotrfParams p
       mbar_init(&sm.empty[s], NTHREADS / 32);
     }
   }
+#ifdef SPB_POTRF_PROF
+  if (tid < 32) sm.prof[tid / 16][tid % 16] = 0;
+  if (tid == 0 && blockIdx.x == 0) {
+    g_potrf_clk[0] = clock64();
+    g_potrf_clk[1] = gtimer();
+  }
+#endif
   __syncthreads();
   unsigned it = 0;  // running k-chunk count of this CTA (ring slot / barrier phase)
+  PROF_DECL;
 
-  for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+  // Work items (matrices) beyond the first wave are claimed from a global counter: the two CTAs of
+  // an SM drift in and out of phase (tensor-pipe phases overlapping or not), so CTA run times for
+  // the same number of matrices differ by +-15 %; a static split would wait for the slowest.
+  for (int item = blockIdx.x; item < nitems;) {
     RowMap rm;
     rm.n = p.n;
     rm.ld = p.ld;
@@ -683,38 +786,35 @@ __global__ void __launch_bounds__(NTHREADS, 2) potrf_lnlike_kernel(PotrfParams p
             init_acc(sm, rm, af, p.aff_on != 0, v0 + warp * 16 + mt * 8 + g, c0, tg, full_panel,
                      acc[mt]);
         });   // acc = K - L L^T = P
+#ifdef SPB_POTRF_PROF
+        _pt = clock64();
+#endif
         if (diag_tile) {
-          if (warp < 4) {
-#pragma unroll
-            for (int mt = 0; mt < 2; ++mt) {
-              const int lr = warp * 16 + mt * 8 + g;
-#pragma unroll
-              for (int nt = 0; nt < 8; ++nt)
-                *reinterpret_cast<double2 *>(&sm.Ld[lr][nt * 8 + 2 * tg]) =
-                    make_double2(acc[mt][nt][0], acc[mt][nt][1]);
-            }
-          }
-          __syncthreads();  // every warp is out of the k-loop: the ring is idle, park there
-          park_acc(sm, acc);
-          __syncthreads();
-          logdet_part += potf2_block(sm, min(NB, p.n - c0));
-          unpark_acc(sm, acc);
-          __syncthreads();  // ring free again before the next tile's copies are issued
+          if (warp < 4) potf2_regs(sm, acc, warp, lane);
+#ifdef SPB_POTRF_PROF
+          _pt = clock64();
+#endif
+          __syncthreads();  // L_jj and the inverses of its diagonal tiles are in shared memory
+          if (tid < min(NB, p.n - c0)) logdet_part += 0.5 * log(sm.dpiv[tid]);
           // write L_jj back (lower triangle, valid rows/cols only)
           for (int idx = tid; idx < NB * NB; idx += NTHREADS) {
             const int i = idx >> 6, j = idx & 63;
             if (j <= i && c0 + i < p.n) rm.Kb[(size_t)(c0 + i) * p.ld + c0 + j] = sm.Ld[i][j];
           }
+          PROF_MARK(sm, 4);
         }
         if (!(diag_tile && warp < 4) && (v0 + warp * 16) < nvirt) {
           trsm_warp(sm, acc, lane);
+          PROF_MARK(sm, 5);
 #pragma unroll
           for (int mt = 0; mt < 2; ++mt)
             store_rows(rm, v0 + warp * 16 + mt * 8 + g, c0, tg, acc[mt], quad_part, quad_out);
+          PROF_MARK(sm, 6);
         }
       }
       __syncthreads();  // Ld/Dv are rewritten by the next panel; global writes of this panel done
       __threadfence_block();
+      PROF_MARK(sm, 7);
     }
 
     // ---- reductions -> lnlike
@@ -731,8 +831,22 @@ __global__ void __launch_bounds__(NTHREADS, 2) potrf_lnlike_kernel(PotrfParams p
       if (p.logdet) p.logdet[item] = bad ? NAN : logdet;
       if (p.info) p.info[item] = prev | (bad ? SPB_INFO_NOT_PD : 0);
     }
+    if (tid == 0) sm.next_item = (int)gridDim.x + (int)atomicAdd(p.counter, 1u);
     __syncthreads();
+    item = sm.next_item;
+    PROF_MARK(sm, 8);
+#ifdef SPB_POTRF_PROF
+    if (_pw >= 0) sm.prof[_pw][10] += 1;
+#endif
   }
+#ifdef SPB_POTRF_PROF
+  __syncthreads();
+  if (tid < 32) atomicAdd(&g_potrf_prof[tid / 16][tid % 16], sm.prof[tid / 16][tid % 16]);
+  if (tid == 0 && blockIdx.x == 0) {
+    g_potrf_clk[2] = clock64();
+    g_potrf_clk[3] = gtimer();
+  }
+#endif
 }
 
 // ------------------------------------------------------------------------------------------
@@ -775,6 +889,9 @@ static int potrf_launch(spb_context *ctx, PotrfParams &p, void *stream) {
   }
   int nitems = (p.mode == MODE_FACTOR) ? p.B : (p.M + p.rows_per_cta - 1) / p.rows_per_cta;
   int grid = nitems < 2 * ctx->num_sms ? nitems : 2 * ctx->num_sms;
+  p.counter = ctx->d_counters +
+      (__atomic_fetch_add(&ctx->counter_next, 1u, __ATOMIC_RELAXED) % SPB_NUM_COUNTERS);
+  SPB_CHECK_CUDA(cudaMemsetAsync(p.counter, 0, sizeof(unsigned int), (cudaStream_t)stream));
   potrf_lnlike_kernel<<<grid, NTHREADS, smem, (cudaStream_t)stream>>>(p);
   SPB_LAUNCH_CHECK(ctx);
   return 0;
@@ -862,6 +979,18 @@ extern "C" int spb_cholesky_solve_rows(spb_context *ctx, int nt, const double *L
   p.rows_per_cta = TM;
   return potrf_launch(ctx, p, stream);
 }
+
+#ifdef SPB_POTRF_PROF
+// debug build only: read (and reset) the phase timers; out[2][16]
+extern "C" int spb_potrf_prof(unsigned long long *out_host) {
+  SPB_CHECK_CUDA(cudaDeviceSynchronize());
+  SPB_CHECK_CUDA(cudaMemcpyFromSymbol(out_host, g_potrf_prof, sizeof(unsigned long long) * 32));
+  unsigned long long z[32] = {0};
+  SPB_CHECK_CUDA(cudaMemcpyToSymbol(g_potrf_prof, z, sizeof(z)));
+  SPB_CHECK_CUDA(cudaMemcpyFromSymbol(out_host + 32, g_potrf_clk, sizeof(unsigned long long) * 4));
+  return 0;
+}
+#endif
 
 extern "C" int spb_dmma_peak(spb_context *ctx, int iters, double *tflops_host, double *ms_host) {
   SPB_REQUIRE(ctx != nullptr, "null context");
