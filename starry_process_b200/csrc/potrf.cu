@@ -525,51 +525,48 @@ __device__ __forceinline__ void bar_diag() {  // warps 0-3 only (named barrier 1
 }
 
 // Cholesky of ONE 8x8 tile held in the accumulator layout of a warp (lane (g, tg): row g, columns
-// 2 tg, 2 tg + 1), entirely with shuffles: no shared memory, no barrier.  Gaussian elimination
-// without scaling (v_ik = L_ik sqrt(d_k)), the same row operations applied to an identity tile, so
-// that L = V diag(d^-1/2) and L^-1 = diag(d^-1/2) W come out together.  The strictly upper part of
-// the tile may be garbage (lower-only assembly): it is never read.
+// 2 tg, 2 tg + 1), entirely with shuffles: no shared memory, no barrier, no branch.  Gaussian
+// elimination without scaling (v_ik = L_ik sqrt(d_k)), the same row operations applied to an
+// identity tile, so that L = V diag(d^-1/2) and L^-1 = diag(d^-1/2) W come out together.
+// The serial spine is the pivot recurrence d_{k+1} = a_{k+1,k+1} - v_{k+1,k}^2 / d_k; every lane
+// carries it redundantly from two values broadcast BEFORE 1/d_k is known, so one pivot costs
+// rcp -> mul -> fma and no shuffle or select sits on the chain.  The square roots are taken once,
+// lane-parallel, at the end.  The strictly upper part of the tile may be garbage (lower-only
+// assembly): it is never used (selects, not multiplications by zero, mask it).
 //   on exit: (v0, v1) = L tile, (w0, w1) = L^-1 tile (upper triangle exactly 0), returns d_g
 __device__ __forceinline__ double potf2_tile8(double &v0, double &v1, double &w0, double &w1, int lane,
                                               bool &bad) {
   const int g = lane >> 2, tg = lane & 3;
   w0 = (2 * tg == g) ? 1.0 : 0.0;
   w1 = (2 * tg + 1 == g) ? 1.0 : 0.0;
-  double dmine = 1.0, rs_row = 1.0, rs_c0 = 1.0, rs_c1 = 1.0;
+  double d = __shfl_sync(0xffffffffu, v0, 0);  // d_0
+  double dmine = 1.0;
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
-    // pivot d_k: element (k, k) = lane 4k + k/2, register k & 1
-    double d = __shfl_sync(0xffffffffu, (k & 1) ? v1 : v0, 4 * k + (k >> 1));
-    if (!(d > 0.0)) {  // also NaN
-      bad = true;
-      d = 1.0;
-    }
-    const double r = fast_rcp(d);
-    // off the chain: d_k^-1/2 for whoever needs it (row scaling of W, column scaling of V)
-    const double rs = fast_rsqrt(d);
-    if (g == k) {
-      dmine = d;
-      rs_row = rs;
-    }
-    if (2 * tg == k) rs_c0 = rs;
-    if (2 * tg + 1 == k) rs_c1 = rs;
+    bad = bad || !(d > 0.0);  // also NaN; the matrix is flagged, its numbers are left to rot
+    dmine = (g == k) ? d : dmine;
     if (k < 7) {
-      // column k of V: v_ik from the lane of my row, v_jk for my two columns j
-      const double vk = (k & 1) ? v1 : v0;
-      const double vik = __shfl_sync(0xffffffffu, vk, (lane & ~3) | (k >> 1));
-      const double vj0 = __shfl_sync(0xffffffffu, vk, 8 * tg + (k >> 1));
-      const double vj1 = __shfl_sync(0xffffffffu, vk, 8 * tg + 4 + (k >> 1));
+      const double vk = (k & 1) ? v1 : v0;             // register holding column k
+      const double vn = ((k + 1) & 1) ? v1 : v0;       // register holding column k + 1
+      const double vik = __shfl_sync(0xffffffffu, vk, (lane & ~3) | (k >> 1));  // v_{g,k}
+      const double vj0 = __shfl_sync(0xffffffffu, vk, 8 * tg + (k >> 1));       // v_{2tg,k}
+      const double vj1 = __shfl_sync(0xffffffffu, vk, 8 * tg + 4 + (k >> 1));   // v_{2tg+1,k}
       const double wk0 = __shfl_sync(0xffffffffu, w0, 4 * k + tg);
       const double wk1 = __shfl_sync(0xffffffffu, w1, 4 * k + tg);
-      const double m = vik * r;
-      if (g > k) {
-        if (2 * tg > k) v0 = fma(-m, vj0, v0);
-        if (2 * tg + 1 > k) v1 = fma(-m, vj1, v1);
-        w0 = fma(-m, wk0, w0);
-        w1 = fma(-m, wk1, w1);
-      }
+      const double pk = __shfl_sync(0xffffffffu, vk, 4 * (k + 1) + (k >> 1));        // v_{k+1,k}
+      const double qk = __shfl_sync(0xffffffffu, vn, 4 * (k + 1) + ((k + 1) >> 1));  // a_{k+1,k+1}
+      const double r = fast_rcp(d);
+      d = fma(-(pk * r), pk, qk);
+      const double m = (g > k) ? vik * r : 0.0;
+      v0 = fma(-m, (2 * tg > k) ? vj0 : 0.0, v0);
+      v1 = fma(-m, (2 * tg + 1 > k) ? vj1 : 0.0, v1);
+      w0 = fma(-m, wk0, w0);
+      w1 = fma(-m, wk1, w1);
     }
   }
+  const double rs_row = fast_rsqrt(dmine);
+  const double rs_c0 = __shfl_sync(0xffffffffu, rs_row, 8 * tg);
+  const double rs_c1 = __shfl_sync(0xffffffffu, rs_row, 8 * tg + 4);
   v0 *= rs_c0;
   v1 *= rs_c1;
   w0 *= rs_row;
