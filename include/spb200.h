@@ -226,6 +226,33 @@ int spb_cholesky_solve_rows(spb_context *ctx, int nt, const double *L, int ldk, 
                             int ldr, double *quad, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * (f-2) building blocks of predict / sample / sample_conditional / sample_ylm_conditional
+ * (sp.py:518-641, 729-765, 767-1002).  Together with spb_cholesky_lnlike (whose "residual" rows are
+ * any set of right-hand sides: out = L^{-1} rhs, one per row) they cover
+ *   K_ts_t        spb_cross_marginal (marginalised, sp.py:887-902) | two spb_gemm_nt (sp.py:903-906)
+ *   mu, K         mu = mean + V w,  K = K_ts_ts - V V^T  with V = (L^{-1} K_t_ts)^T, w = L^{-1}(y - mean)
+ *   draws         spb_tril + spb_gemm_nt:  x = mu + L u
+ *
+ * spb_gemm_nt : C[b] = alpha A[b] Bm[b]^T + beta C[b];  A: (M, K) row-major (lda), Bm: (N, K)
+ *               row-major (ldb), C: (M, N) (ldc); K, lda, ldb even, operands 16-byte aligned;
+ *               batch strides in elements (0 = shared operand).
+ * spb_tril    : zero the strict upper triangle of B (n x n) matrices (the Cholesky kernel leaves the
+ *               upper triangle of its in-place factor untouched).
+ * spb_cross_marginal : K_ts_t[b][i][j] = k_b(|theta(ts_i) - theta(t_j)|) + offset[b], the cubic
+ *               interpolant of flux.py:256-276 on the coef table of spb_flux_marginal; columns
+ *               nt..ld-1 are zeroed (ld even: the rows are right-hand sides of the solve); K_stride
+ *               elements between batch entries.
+ * ------------------------------------------------------------------------------------------- */
+int spb_gemm_nt(spb_context *ctx, int batch, int M, int N, int K, double alpha, const double *A,
+                int lda, long long strideA, const double *Bm, int ldb, long long strideB,
+                double beta, double *C, int ldc, long long strideC, void *stream);
+int spb_tril(spb_context *ctx, int B, int n, double *L, int ld, long long stride, void *stream);
+int spb_cross_marginal(spb_context *ctx, int B, int nts, int nt, const double *ts, const double *t,
+                       double period, int covpts, const double *coef, const double *offset,
+                       long long offset_stride, double *K_ts_t, int ld, long long K_stride,
+                       void *stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Measurement helpers (not part of the reference interface): FP64 tensor-pipe (DMMA) peak
  * micro-benchmark used as the roofline denominator; returns achieved TFLOP/s via *tflops_host.
  * ------------------------------------------------------------------------------------------- */

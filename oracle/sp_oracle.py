@@ -802,6 +802,7 @@ class OracleProcess(object):
             a2 = 0.5 * (y0 + y2) - y1
             a3 = 0.5 * ((y1 - y2) + (y3 - y0) / 3.0)
             self._kernel_grid = (xp, yp)
+            self._interp = (dx, xp, a0, a1, a2, a3, p)
             # flux.py:256-276
             theta = 2 * np.pi * np.mod(t / p, 1.0)
             x = np.abs(theta[:, None] - theta[None, :]).reshape(-1)
@@ -878,3 +879,85 @@ class OracleProcess(object):
     # sp.py:489-509 with an explicit standard-normal matrix `u` of shape (N, nsamples)
     def sample_ylm(self, unit_normals):
         return np.transpose(self.mean_ylm[:, None] + np.dot(self.cho_cov_ylm, unit_normals))
+
+    # ---------------------------------------------------------------- SURVEY 8(f) rank 2
+    # sp.py:729-765 with the standard-normal matrix `unit_normals` (nt, nsamples) given
+    def sample(self, t, unit_normals, i=DEFAULTS["i"], p=DEFAULTS["p"], u=(0.0, 0.0), eps=1e-8):
+        t = np.asarray(t, dtype=float).reshape(-1)
+        cho_cov = cho_factor(self.cov(t, i, p, u) + eps * np.eye(t.shape[0]))
+        return np.transpose(self.mean(t, i, p, u)[:, None] + np.dot(cho_cov, unit_normals))
+
+    # sp.py:767-922
+    def predict(self, t, flux, data_cov, t_sample=None, i=DEFAULTS["i"], p=DEFAULTS["p"],
+                u=(0.0, 0.0), baseline_mean=0.0, baseline_var=0.0):
+        if self.normalized:
+            raise NotImplementedError("Method not implemented when the flux is normalized.")
+        t = np.asarray(t, dtype=float).reshape(-1)
+        cov_t = self.cov(t, i, p, u)
+        if t_sample is None:
+            ts, cov_ts = t, cov_t
+        else:
+            ts = np.asarray(t_sample, dtype=float).reshape(-1)
+            cov_ts = self.cov(ts, i, p, u)
+        y = np.asarray(flux, dtype=float) - baseline_mean
+        data_cov = np.asarray(data_cov, dtype=float)
+        if data_cov.ndim == 0:
+            data_cov = data_cov * np.eye(t.shape[0])
+        elif data_cov.ndim == 1:
+            data_cov = np.diag(data_cov)
+        mean, _ = self._flux_mean_cov(np.array([0.0]), i, p, u)
+        K_t_t = cov_t + data_cov + baseline_var
+        K_ts_ts = cov_ts + baseline_var
+        if self.marg:
+            self._flux_mean_cov(t, i, p, u)
+            dx, xp, a0, a1, a2, a3, per = self._interp
+            theta_t = 2 * np.pi * np.mod(t / per, 1.0)
+            theta_ts = 2 * np.pi * np.mod(ts / per, 1.0)
+            x = np.abs(theta_ts[:, None] - theta_t[None, :]).reshape(-1)
+            inds = np.floor(x / dx).astype("int64")
+            x0 = (x - xp[inds + 1]) / dx
+            K_ts_t = (a0[inds] + a1[inds] * x0 + a2[inds] * x0 ** 2
+                      + a3[inds] * x0 ** 3).reshape(theta_ts.shape[0], theta_t.shape[0])
+        else:
+            A_ts = self.design_matrix(ts, i, p, u)
+            A_t = self.design_matrix(t, i, p, u)
+            K_ts_t = np.dot(np.dot(A_ts, self.cov_ylm), A_t.T)
+        K_ts_t = K_ts_t + baseline_var
+        cho_K = cho_factor(K_t_t)
+        mu = mean + np.dot(K_ts_t, cho_solve(cho_K, y - mean))
+        K = K_ts_ts - np.dot(K_ts_t, cho_solve(cho_K, K_ts_t.T))
+        return mu, K
+
+    # sp.py:924-1002 with `ts = t_sample` (the reference body uses an undefined name `ts`) and the
+    # standard-normal matrix `unit_normals` (nts, nsamples) given
+    def sample_conditional(self, t, flux, data_cov, unit_normals, t_sample=None, eps=1e-8, **kw):
+        mu, K = self.predict(t, flux, data_cov, t_sample=t_sample, **kw)
+        cho_K = cho_factor(K + eps * np.eye(K.shape[0]))
+        return np.transpose(mu[:, None] + np.dot(cho_K, unit_normals))
+
+    # sp.py:518-641 with the standard-normal matrix `unit_normals` (N, nsamples) given
+    def sample_ylm_conditional(self, t, flux, data_cov, unit_normals, i=DEFAULTS["i"],
+                               p=DEFAULTS["p"], u=(0.0, 0.0), baseline_mean=0.0, baseline_var=0.0):
+        if self.normalized:
+            raise NotImplementedError("Method not implemented when the flux is normalized.")
+        flux = np.asarray(flux, dtype=float)
+        data_cov = np.asarray(data_cov, dtype=float)
+        if data_cov.ndim == 0:
+            C = data_cov * np.eye(flux.shape[0])
+        elif data_cov.ndim == 1:
+            C = np.diag(data_cov)
+        else:
+            C = np.array(data_cov)
+        C = C + baseline_var
+        cho_C = cho_factor(C)
+        A = self.design_matrix(t, i, p, u)
+        CInvA = cho_solve(cho_C, A)
+        LInv = cho_solve(self.cho_cov_ylm, np.eye(self.N))      # sp.py:267-270
+        LInvmu = cho_solve(self.cho_cov_ylm, self.mean_ylm)     # sp.py:271
+        W = np.dot(A.T, CInvA) + LInv
+        cho_W = cho_factor(W)
+        M = cho_solve(cho_W, CInvA.T)
+        ymu = np.dot(M, flux - baseline_mean) + cho_solve(cho_W, LInvmu)
+        ycov = cho_solve(cho_W, np.eye(self.N))
+        cho_ycov = cho_factor(ycov)
+        return np.transpose(ymu[:, None] + np.dot(cho_ycov, unit_normals))

@@ -66,6 +66,9 @@ PROTOTYPES = {
                                         _P, _P, _P, _P, _P]),
     "spb_assemble_workspace_layout": (None, [_I, _I, _P, _c.POINTER(_P), _c.POINTER(_P)]),
     "spb_cholesky_solve_rows": (_I, [_P, _I, _P, _I, _I, _P, _I, _P, _P]),
+    "spb_gemm_nt": (_I, [_P, _I, _I, _I, _I, _D, _P, _I, _LL, _P, _I, _LL, _D, _P, _I, _LL, _P]),
+    "spb_tril": (_I, [_P, _I, _I, _P, _I, _LL, _P]),
+    "spb_cross_marginal": (_I, [_P, _I, _I, _I, _P, _P, _D, _I, _P, _P, _LL, _P, _I, _LL, _P]),
     "spb_dmma_peak": (_I, [_P, _I, _c.POINTER(_D), _c.POINTER(_D)]),
     "spb_launch_count": (_I, [_P, _c.POINTER(_LL)]),
 }

@@ -307,6 +307,53 @@ int run_assemble(spb_context *ctx, AsmParams &p, void *workspace, size_t workspa
 
 }  // namespace
 
+namespace {
+// Rectangular marginal kernel K(ts, t) of predict (sp.py:887-902): the same cubic interpolant as
+// flux.py:256-276 evaluated at |theta_ts,i - theta_t,j|, one output row per warp pass.
+__global__ void __launch_bounds__(256) cross_marginal_kernel(int nts, int nt, int covpts,
+                                                             const double *ts, const double *t,
+                                                             double period, const double *coef,
+                                                             const double *offset,
+                                                             long long offset_stride, double *out,
+                                                             int ld, long long out_stride) {
+  extern __shared__ double sh[];  // coef (4*nc) | theta_t (nt)
+  const int b = blockIdx.y;
+  const int nc = covpts + 1;
+  double *cf = sh, *th = sh + 4 * nc;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int k = tid; k < 4 * nc; k += 256) cf[k] = coef[(size_t)b * 4 * nc + k];
+  for (int k = tid; k < nt; k += 256) th[k] = phase_of(t[k], period);
+  __syncthreads();
+  const double inv_dx = (double)covpts / (2.0 * 3.14159265358979323846);
+  const double off = offset ? offset[(size_t)b * offset_stride] : 0.0;
+  for (int i = blockIdx.x * 8 + warp; i < nts; i += gridDim.x * 8) {
+    const double thi = phase_of(ts[i], period);
+    double *row = out + (size_t)b * out_stride + (size_t)i * ld;
+    for (int j = lane; j < ld; j += 32)
+      row[j] = (j < nt) ? interp_cov(cf, nc, inv_dx, thi, th[j]) + off : 0.0;
+  }
+}
+}  // namespace
+
+extern "C" int spb_cross_marginal(spb_context *ctx, int B, int nts, int nt, const double *ts,
+                                  const double *t, double period, int covpts, const double *coef,
+                                  const double *offset, long long offset_stride, double *K_ts_t,
+                                  int ld, long long K_stride, void *stream) {
+  SPB_REQUIRE(ctx != nullptr && B > 0 && nts > 0 && nt > 0 && ld >= nt, "cross_marginal: bad arguments");
+  SPB_REQUIRE(B <= 65535, "cross_marginal: batch too large for one launch");
+  SPB_CHECK_CUDA(cudaSetDevice(ctx->device));
+  const size_t smem = (size_t)(4 * (covpts + 1) + nt) * sizeof(double);
+  SPB_REQUIRE(smem <= 200 * 1024, "cross_marginal: nt too large for the shared-memory phase table");
+  SPB_CHECK_CUDA(cudaFuncSetAttribute(cross_marginal_kernel,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int gx = (nts + 7) / 8;
+  if (gx > 4 * ctx->num_sms) gx = 4 * ctx->num_sms;
+  cross_marginal_kernel<<<dim3(gx, B), 256, smem, (cudaStream_t)stream>>>(
+      nts, nt, covpts, ts, t, period, coef, offset, offset_stride, K_ts_t, ld, K_stride);
+  SPB_LAUNCH_CHECK(ctx);
+  return 0;
+}
+
 extern "C" size_t spb_assemble_workspace_bytes(const spb_context *ctx, int B, int nt) {
   (void)ctx;
   return ((size_t)B * nt * (1 + RS_G) + (size_t)B * 4) * sizeof(double) + 256;

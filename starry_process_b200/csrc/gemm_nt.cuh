@@ -18,7 +18,7 @@ namespace gnt {
 
 constexpr int TM = 128, TN = 64, KC = 16, KS = KC + 4, STAGES = 3, NTHREADS = 256;
 
-enum Epilogue { EPI_STORE = 0, EPI_SYRK_COV = 1, EPI_MIRROR = 2, EPI_ADD_ROWVEC = 3 };
+enum Epilogue { EPI_STORE = 0, EPI_SYRK_COV = 1, EPI_MIRROR = 2, EPI_ADD_ROWVEC = 3, EPI_AXPBY = 4 };
 
 struct Desc {
   const double *A;
@@ -41,6 +41,7 @@ struct Desc {
   const double *diag;      // (M)
   const int *rkeep;        // optional (batch): sqrtC chunk-skip rule, see k-loop
   double alpha;
+  double beta;             // EPI_AXPBY: C = alpha acc + beta C (C is not read when beta == 0)
 };
 
 struct Smem {
@@ -198,6 +199,9 @@ __global__ void __launch_bounds__(NTHREADS, 2) gemm_nt_kernel(Desc d) {
         double v = acc[mt][nt][e];
         if (EPI == EPI_STORE) {
           Cb[(size_t)m * d.ldc + n] = d.alpha * v;
+        } else if (EPI == EPI_AXPBY) {
+          double *c = Cb + (size_t)m * d.ldc + n;
+          *c = (d.beta == 0.0) ? d.alpha * v : fma(d.alpha, v, d.beta * *c);
         } else if (EPI == EPI_ADD_ROWVEC) {
           Cb[(size_t)m * d.ldc + n] = v + d.vec[(size_t)b * d.strideVec + n];
         } else if (EPI == EPI_MIRROR) {

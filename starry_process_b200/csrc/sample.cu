@@ -10,7 +10,55 @@ __global__ void zero_upper_kernel(int B, double *L) {
   const int ij = (int)(idx & 65535);
   if ((ij & 255) > (ij >> 8)) L[idx] = 0.0;
 }
+// generalised: zero the strict upper triangle of B (n x n) matrices with leading dimension ld
+__global__ void tril_kernel(int B, int n, int ld, long long stride, double *L) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t per = (size_t)n * n;
+  if (idx >= (size_t)B * per) return;
+  const size_t b = idx / per;
+  const int ij = (int)(idx - b * per);
+  const int i = ij / n, j = ij - i * n;
+  if (j > i) L[b * (size_t)stride + (size_t)i * ld + j] = 0.0;
+}
 }  // namespace
+
+// C = alpha A Bm^T + beta C on the FP64 tensor pipe (the contractions of predict / conditional
+// sampling, sp.py:767-1002: K_ts_t = (A_ts Sigma) A_t^T, mu = mean + V w, K = K_ts_ts - V V^T, ...)
+extern "C" int spb_gemm_nt(spb_context *ctx, int batch, int M, int N, int K, double alpha,
+                           const double *A, int lda, long long strideA, const double *Bm, int ldb,
+                           long long strideB, double beta, double *C, int ldc, long long strideC,
+                           void *stream) {
+  SPB_REQUIRE(ctx != nullptr && A != nullptr && Bm != nullptr && C != nullptr, "gemm_nt: null argument");
+  SPB_CHECK_CUDA(cudaSetDevice(ctx->device));
+  gnt::Desc d = {};
+  d.A = A;
+  d.strideA = strideA;
+  d.lda = lda;
+  d.Bm = Bm;
+  d.strideB = strideB;
+  d.ldb = ldb;
+  d.C = C;
+  d.strideC = strideC;
+  d.ldc = ldc;
+  d.M = M;
+  d.N = N;
+  d.K = K;
+  d.batch = batch;
+  d.ksplit = 1;
+  d.alpha = alpha;
+  d.beta = beta;
+  return gnt::launch<gnt::EPI_AXPBY>(ctx, d, (cudaStream_t)stream);
+}
+
+extern "C" int spb_tril(spb_context *ctx, int B, int n, double *L, int ld, long long stride,
+                        void *stream) {
+  SPB_REQUIRE(ctx != nullptr && L != nullptr && B > 0 && n > 0 && ld >= n, "tril: bad arguments");
+  SPB_CHECK_CUDA(cudaSetDevice(ctx->device));
+  const size_t total = (size_t)B * n * n;
+  tril_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(B, n, ld, stride, L);
+  SPB_LAUNCH_CHECK(ctx);
+  return 0;
+}
 
 extern "C" int spb_cho_cov_ylm(spb_context *ctx, int B, const double *cov_ylm, double *L_ylm,
                                int32_t *info, void *stream_) {

@@ -11,9 +11,13 @@ path; inputs/outputs are ``torch.float64`` CUDA tensors and evaluation is eager.
 behind ``include/spb200.h``) -- there is no CPU or PyTorch fallback: without the library (or without
 a CUDA device) construction raises.
 
+SURVEY.md section 8(f) rank 2 is covered as well: ``sample``, ``predict``, ``sample_conditional``
+and ``sample_ylm_conditional`` (sp.py:518-641, 729-765, 767-1002), composed from the same Cholesky
+/ GEMM / assembly kernels.
+
 Out of scope in this drop-in (callers, listed under "next"): the uniform
-spot-size prior (``dr``), time-variable surfaces (``tau``), ``predict``/conditional sampling,
-pixel-space moments and visualisation.  They raise ``NotImplementedError``.
+spot-size prior (``dr``), time-variable surfaces (``tau``), pixel-space moments and visualisation.
+They raise ``NotImplementedError``.
 """
 import ctypes
 import math
@@ -31,6 +35,7 @@ defaults = dict(
     u=[0.0, 0.0], tau=None, normalized=True, normalization_order=20, normalization_zmax=0.023,
     marginalize_over_inclination=True, baseline_mean=0.0, baseline_var=0.0, covpts=300,
     log_alpha_max=10, log_beta_max=10, abmin=1e-12, sigma_max=45.0, epsy=1e-12, epsy15=1e-9,
+    eps=1e-8,
 )
 
 _CTX = {}
@@ -465,6 +470,7 @@ class StarryProcess(object):
                                              self._covpts, _ptr(gp_mean), _ptr(var), _ptr(coef),
                                              _ptr(ws), nb, _stream()))
             self._mark_end(ev)
+            self._last_coef = coef   # (Bc, 4, covpts + 1): predict's cross-covariance re-uses it
             ev = self._mark("assemble")
             _lib.check(lib.spb_assemble_marginal(h, Bc, nt, _ptr(t), float(p), self._covpts,
                                                  _ptr(coef), _ptr(var), _ptr(gp_mean),
@@ -631,3 +637,268 @@ class StarryProcess(object):
                 del K, resid, out
         self._z = torch.cat(zs)
         return self._out(lnlike)
+
+    # ------------------------------------------------------------------ SURVEY 8(f) rank 2
+    def _factor_rows(self, K, n, ldk, rows=None, diag_add=None):
+        """In-place batched Cholesky of ``K (Bq, n, ldk)`` (lower triangle read, ``L`` written over
+        it; ``diag_add`` is added to the diagonal inside the kernel's loads); ``rows (Bq, M, ldr)``
+        are replaced by ``L^-1 row`` (math.py:20-38 forward substitution).  Returns ``info``."""
+        lib, h = self._lib, self._ctx.handle
+        Bq = K.shape[0]
+        info = torch.zeros(Bq, dtype=torch.int32, device=self.device)
+        if rows is None:
+            M, rp, ldr, rstride = 0, None, ldk, 0
+        else:
+            M, ldr = rows.shape[1], rows.shape[2]
+            rp, rstride = _ptr(rows), M * ldr
+        if diag_add is None:
+            _lib.check(lib.spb_cholesky_lnlike(h, Bq, n, _ptr(K), ldk, n * ldk, M, rp, ldr, rstride,
+                                               None, None, None, _ptr(info), _stream()))
+        else:
+            af = _lib.Affine()
+            dg = torch.full((1,), float(diag_add), dtype=torch.float64, device=self.device)
+            af.diag, af.diag_kind, af.diag_stride = dg.data_ptr(), 0, 0
+            _lib.check(lib.spb_cholesky_lnlike_affine(h, Bq, n, _ptr(K), ldk, n * ldk,
+                                                      ctypes.byref(af), M, rp, ldr, rstride, None,
+                                                      None, None, _ptr(info), _stream()))
+        return info
+
+    def _gemm(self, batch, M, N, K, A, lda, sA, Bm, ldb, sB, C, ldc, sC, alpha=1.0, beta=0.0):
+        """``C = alpha A Bm^T + beta C`` (spb_gemm_nt); tensors or raw device addresses."""
+        ad = lambda x: ctypes.c_void_p(x) if isinstance(x, int) else _ptr(x)   # noqa: E731
+        _lib.check(self._lib.spb_gemm_nt(self._ctx.handle, batch, M, N, K, float(alpha), ad(A), lda,
+                                         sA, ad(Bm), ldb, sB, float(beta), ad(C), ldc, sC,
+                                         _stream()))
+
+    def _draw(self, mu, L, n, ld, nsamples, unit_normals, generator):
+        """``mu[:, None] + L u`` for ``u ~ N(0, 1)`` of shape ``(n, nsamples)`` (or ``(B, n,
+        nsamples)``), returned as ``(B, nsamples, n)``.  ``L (B, n, ld)`` must be clean lower."""
+        B, dev = L.shape[0], self.device
+        if unit_normals is None:
+            un = torch.zeros(B, nsamples, ld, dtype=torch.float64, device=dev)
+            un[:, :, :n] = torch.randn(B, nsamples, n, dtype=torch.float64, device=dev,
+                                       generator=generator)
+        else:
+            u_ = torch.as_tensor(unit_normals, dtype=torch.float64).to(dev)
+            if u_.ndim == 2:
+                u_ = u_[None].expand(B, u_.shape[0], u_.shape[1])
+            if u_.shape[1] != n:
+                raise ValueError("unit normals must have shape (%d, nsamples)" % n)
+            nsamples = u_.shape[2]
+            un = torch.zeros(B, nsamples, ld, dtype=torch.float64, device=dev)
+            un[:, :, :n] = u_.transpose(1, 2)
+        out = mu[:, None, :].expand(B, nsamples, n).contiguous()
+        self._gemm(B, nsamples, n, ld, un, ld, nsamples * ld, L, ld, n * ld, out, n, nsamples * n,
+                   alpha=1.0, beta=1.0)
+        return out
+
+    def sample(self, t, i=defaults["i"], p=defaults["p"], u=None, nsamples=1, eps=defaults["eps"],
+               unit_normals=None, generator=None, marginalize_over_inclination=None):
+        """sp.py:729-765: draws from the prior over light curves, ``(nsamples, nt)`` (or
+        ``(B, nsamples, nt)``).  ``unit_normals`` optionally supplies the reference's
+        ``random_normal(self.random, (nt, nsamples))``."""
+        marg, t, inc, rta1 = self._prep(t, i, p, u, marginalize_over_inclination)
+        nt = t.numel()
+        ldk = nt + (nt & 1)
+        B = self._B
+        with torch.cuda.device(self.device):
+            # eps I is the scalar "data covariance" of the assembly (added after the normalisation,
+            # as sp.py:762 adds it to the output of cov())
+            gp_mean, K, _ = self._flux_cov_chunk(0, B, t, inc, p, rta1, marg, float(eps), None, ldk)
+            info = self._factor_rows(K, nt, ldk)
+            _lib.check(self._lib.spb_tril(self._ctx.handle, B, nt, _ptr(K), ldk, nt * ldk,
+                                          _stream()))
+            if nt & 1:
+                K[:, :, nt:] = 0.0
+            mu = torch.zeros(B, nt, dtype=torch.float64, device=self.device)
+            if not self._normalized:
+                mu += gp_mean[:, None]
+            out = self._draw(mu, K, nt, ldk, nsamples, unit_normals, generator)
+            out = torch.where(((info & 1) != 0)[:, None, None], torch.full_like(out, float("nan")),
+                              out)
+        return self._out(out)
+
+    def predict(self, t, flux, data_cov, t_sample=None, i=defaults["i"], p=defaults["p"], u=None,
+                baseline_mean=defaults["baseline_mean"], baseline_var=defaults["baseline_var"],
+                marginalize_over_inclination=None):
+        """sp.py:767-922: mean ``(nts,)`` and covariance ``(nts, nts)`` of the light-curve
+        distribution conditioned on ``flux`` (leading ``B`` axis for batched hyperparameters).
+
+        One augmented factorisation does the work: the rows ``[K(ts, t); y - mean]`` are appended
+        to ``K(t, t)``, the Cholesky kernel returns ``V = (L^-1 K(t, ts))^T`` and ``w = L^-1 (y -
+        mean)``, and ``mu = mean + V w``, ``K = K(ts, ts) - V V^T`` are two tensor-core GEMMs."""
+        if self._normalized:
+            raise NotImplementedError("Method not implemented when the flux is normalized.")
+        marg, t, inc, rta1 = self._prep(t, i, p, u, marginalize_over_inclination)
+        dev, B = self.device, self._B
+        nt = t.numel()
+        ldk = nt + (nt & 1)
+        ts = t if t_sample is None else self._t(t_sample)
+        nts = ts.numel()
+        lds = nts + (nts & 1)
+        bvar = None
+        if isinstance(baseline_var, (torch.Tensor, np.ndarray)) or baseline_var != 0.0:
+            bvar = torch.as_tensor(baseline_var, dtype=torch.float64).to(dev)
+        # scalar (or one value per batch element) vs. a full (nt, nt) matrix of extra covariance
+        scalar_bvar = bvar is None or bvar.ndim <= 1
+        f = torch.as_tensor(flux, dtype=torch.float64).to(dev).reshape(-1)
+        if f.numel() != nt:
+            raise ValueError("flux must have shape (nt,)")
+        bm = torch.as_tensor(baseline_mean, dtype=torch.float64).to(dev)
+        lib, h = self._lib, self._ctx.handle
+        with torch.cuda.device(dev):
+            # K(ts, ts) + baseline_var first (the marginal kernel table is shared by both calls)
+            _, Kss, _ = self._flux_cov_chunk(0, B, ts, inc, p, rta1, marg, None,
+                                             bvar if (scalar_bvar or nts == nt) else None, lds)
+            gp_mean, Ktt, _ = self._flux_cov_chunk(0, B, t, inc, p, rta1, marg, data_cov, bvar, ldk)
+            # right-hand sides: rows 0..nts-1 = K(ts, t) + baseline_var, row nts = y - mean
+            R = torch.zeros(B, nts + 1, ldk, dtype=torch.float64, device=dev)
+            rstride = (nts + 1) * ldk
+            off = None
+            if bvar is not None and scalar_bvar:
+                off = bvar.reshape(-1).contiguous()
+            if marg:
+                _lib.check(lib.spb_cross_marginal(
+                    h, B, nts, nt, _ptr(ts), _ptr(t), float(p), self._covpts,
+                    _ptr(self._last_coef), _ptr(off), 0 if off is None or off.numel() == 1 else 1,
+                    _ptr(R), ldk, rstride, _stream()))
+            else:
+                I = inc.numel()
+                per = torch.full((I,), float(p), dtype=torch.float64, device=dev)
+                A2 = []
+                for tt_, n_ in ((ts, nts), (t, nt)):
+                    A_ = torch.empty(I, n_, 256, dtype=torch.float64, device=dev)
+                    nbd = lib.spb_design_matrix_workspace_bytes(h, I, n_)
+                    wsd = torch.empty(nbd, dtype=torch.uint8, device=dev)
+                    _lib.check(lib.spb_design_matrix(h, I, n_, _ptr(tt_), _ptr(inc), _ptr(per),
+                                                     _ptr(rta1), 0, _ptr(A_), _ptr(wsd), nbd,
+                                                     _stream()))
+                    A2.append(A_)
+                A_ts, A_t = A2
+                T = torch.empty(B, nts, 256, dtype=torch.float64, device=dev)
+                # T = A_ts Sigma (Sigma symmetric), K(ts, t) = T A_t^T   (sp.py:903-906)
+                self._gemm(B, nts, 256, 256, A_ts, 256, 0 if I == 1 else nts * 256, self._cov_ylm,
+                           256, 65536, T, 256, nts * 256)
+                if off is not None:
+                    R[:, :nts, :nt] = off.reshape(-1, 1, 1)
+                self._gemm(B, nts, nt, 256, T, 256, nts * 256, A_t, 256, 0 if I == 1 else nt * 256,
+                           R, ldk, rstride, alpha=1.0, beta=1.0)
+            if bvar is not None and not scalar_bvar:
+                R[:, :nts, :nt] += bvar
+            R[:, nts, :nt] = (f - bm)[None, :] - gp_mean[:, None]
+            info = self._factor_rows(Ktt, nt, ldk, rows=R)
+            # mu = mean + V w ; K = K(ts, ts) - V V^T
+            mu = gp_mean[:, None].expand(B, nts).contiguous()
+            wrow = R.data_ptr() + nts * ldk * 8
+            self._gemm(B, nts, 1, ldk, R, ldk, rstride, wrow, ldk, rstride, mu, 1, nts,
+                       alpha=1.0, beta=1.0)
+            self._gemm(B, nts, nts, ldk, R, ldk, rstride, R, ldk, rstride, Kss, lds, nts * lds,
+                       alpha=-1.0, beta=1.0)
+            bad = ((info & 1) != 0)
+            mu = torch.where(bad[:, None], torch.full_like(mu, float("nan")), mu)
+            Kc = Kss[:, :, :nts]
+            Kc = torch.where(bad[:, None, None], torch.full_like(Kc, float("nan")), Kc)
+        return self._out(mu), self._out(Kc)
+
+    def sample_conditional(self, t, flux, data_cov, t_sample=None, i=defaults["i"],
+                           p=defaults["p"], u=None, baseline_mean=defaults["baseline_mean"],
+                           baseline_var=defaults["baseline_var"], nsamples=1, eps=defaults["eps"],
+                           unit_normals=None, generator=None, marginalize_over_inclination=None):
+        """sp.py:924-1002: draws ``(nsamples, nts)`` from the conditional light-curve distribution.
+        (The reference body reads an undefined name ``ts``; the intended ``ts = t_sample or t`` is
+        what is implemented.)"""
+        mu, K = self.predict(t, flux, data_cov, t_sample=t_sample, i=i, p=p, u=u,
+                             baseline_mean=baseline_mean, baseline_var=baseline_var,
+                             marginalize_over_inclination=marginalize_over_inclination)
+        if not self._batched:
+            mu, K = mu[None], K[None]
+        B, nts = mu.shape
+        lds = nts + (nts & 1)
+        with torch.cuda.device(self.device):
+            Kp = torch.zeros(B, nts, lds, dtype=torch.float64, device=self.device)
+            Kp[:, :, :nts] = K
+            info = self._factor_rows(Kp, nts, lds, diag_add=eps)
+            _lib.check(self._lib.spb_tril(self._ctx.handle, B, nts, _ptr(Kp), lds, nts * lds,
+                                          _stream()))
+            out = self._draw(mu.contiguous(), Kp, nts, lds, nsamples, unit_normals, generator)
+            out = torch.where(((info & 1) != 0)[:, None, None], torch.full_like(out, float("nan")),
+                              out)
+        return self._out(out)
+
+    def sample_ylm_conditional(self, t, flux, data_cov, i=defaults["i"], p=defaults["p"], u=None,
+                               baseline_mean=defaults["baseline_mean"],
+                               baseline_var=defaults["baseline_var"], nsamples=1,
+                               unit_normals=None, generator=None):
+        """sp.py:518-641: draws ``(nsamples, 256)`` of the Ylm coefficients conditioned on the
+        observed flux (the inclination is always used).
+
+        With ``C = data_cov + baseline_var = L_C L_C^T``, ``G = (L_C^-1 A)^T`` and ``Y = L_y^-T``
+        (``cov_ylm = L_y L_y^T``):  ``W = G G^T + Y Y^T``,  ``rhs = G L_C^-1 (f - b) + Y L_y^-1 mu``,
+        ``ymu = W^-1 rhs``, ``ycov = W^-1 = Y_W Y_W^T`` -- every product a tensor-core GEMM, every
+        inverse a forward substitution on appended rows of the Cholesky kernel."""
+        if self._normalized:
+            raise NotImplementedError("Method not implemented when the flux is normalized.")
+        self._compute_moments()
+        dev, B = self.device, self._B
+        t = self._t(t)
+        nt = t.numel()
+        ldk = nt + (nt & 1)
+        f = torch.as_tensor(flux, dtype=torch.float64).to(dev).reshape(-1)
+        if f.numel() != nt:
+            raise ValueError("flux must have shape (nt,)")
+        bm = torch.as_tensor(baseline_mean, dtype=torch.float64).to(dev)
+        lib, h = self._lib, self._ctx.handle
+        with torch.cuda.device(dev):
+            A = self.design_matrix(t, i, p, u)
+            A = A if A.ndim == 3 else A[None]
+            I = A.shape[0]
+            if I not in (1, B):
+                raise ValueError("`i` must be a scalar or have one entry per batch element")
+            # C = data_cov (+ baseline_var on every entry): input assembly, sp.py:594-607
+            d = torch.as_tensor(data_cov, dtype=torch.float64).to(dev)
+            C = torch.zeros(1, nt, ldk, dtype=torch.float64, device=dev)
+            if d.ndim == 0:
+                C[0, :, :nt].diagonal().fill_(float(d))
+            elif d.ndim == 1:
+                C[0, :, :nt].diagonal().copy_(d)
+            else:
+                C[0, :, :nt] = d
+            C[0, :, :nt] += torch.as_tensor(baseline_var, dtype=torch.float64).to(dev)
+            infoC = self._factor_rows(C, nt, ldk)
+            # rows: A^T (256 per inclination) and the residual, all against the one factor of C
+            R = torch.zeros(I * 256 + 1, ldk, dtype=torch.float64, device=dev)
+            R[: I * 256, :nt] = A.transpose(1, 2).reshape(I * 256, nt)
+            R[I * 256, :nt] = f - bm
+            quad = torch.empty(I * 256 + 1, dtype=torch.float64, device=dev)
+            _lib.check(lib.spb_cholesky_solve_rows(h, nt, _ptr(C), ldk, I * 256 + 1, _ptr(R), ldk,
+                                                   _ptr(quad), _stream()))
+            grow = R.data_ptr() + I * 256 * ldk * 8
+            # cov_ylm = L_y L_y^T with rows [I; mu] appended: Y = L_y^-T (as rows), wmu = L_y^-1 mu
+            Ly = self._cov_ylm.clone()
+            Ry = torch.zeros(B, 257, 256, dtype=torch.float64, device=dev)
+            Ry[:, :256, :] = torch.eye(256, dtype=torch.float64, device=dev)
+            Ry[:, 256, :] = self._mean_ylm
+            infoY = self._factor_rows(Ly, 256, 256, rows=Ry)
+            sY = 257 * 256
+            W = torch.empty(B, 256, 256, dtype=torch.float64, device=dev)
+            sG = 0 if I == 1 else 256 * ldk
+            self._gemm(B, 256, 256, ldk, R, ldk, sG, R, ldk, sG, W, 256, 65536)
+            self._gemm(B, 256, 256, 256, Ry, 256, sY, Ry, 256, sY, W, 256, 65536, beta=1.0)
+            # rhs = Y wmu + G g, appended (with the identity) to the factorisation of W
+            Rw = torch.zeros(B, 257, 256, dtype=torch.float64, device=dev)
+            Rw[:, :256, :] = torch.eye(256, dtype=torch.float64, device=dev)
+            rhs = Rw.data_ptr() + 256 * 256 * 8
+            self._gemm(B, 256, 1, 256, Ry, 256, sY, Ry.data_ptr() + 256 * 256 * 8, 256, sY, rhs, 1, sY)
+            self._gemm(B, 256, 1, ldk, R, ldk, sG, grow, ldk, 0, rhs, 1, sY, beta=1.0)
+            infoW = self._factor_rows(W, 256, 256, rows=Rw)
+            # ycov = Y_W Y_W^T, ymu = Y_W (L_W^-1 rhs)
+            ycov = torch.empty(B, 256, 256, dtype=torch.float64, device=dev)
+            self._gemm(B, 256, 256, 256, Rw, 256, sY, Rw, 256, sY, ycov, 256, 65536)
+            ymu = torch.empty(B, 256, dtype=torch.float64, device=dev)
+            self._gemm(B, 256, 1, 256, Rw, 256, sY, rhs, 256, sY, ymu, 1, 256)
+            infoS = self._factor_rows(ycov, 256, 256)
+            _lib.check(lib.spb_tril(h, B, 256, _ptr(ycov), 256, 65536, _stream()))
+            out = self._draw(ymu, ycov, 256, 256, nsamples, unit_normals, generator)
+            bad = (((infoY | infoW | infoS) & 1) != 0) | ((infoC & 1) != 0)
+            out = torch.where(bad[:, None, None], torch.full_like(out, float("nan")), out)
+        return self._out(out)
