@@ -167,6 +167,13 @@ typedef struct {
                                 scalars / row-sum vector in the workspace: the affine map and the
                                 noise terms are applied by spb_cholesky_lnlike_affine.  Requires
                                 lower_only and no full-matrix data_cov / baseline_var.            */
+  /* (f-3) time-variable surfaces: the raw covariance is multiplied elementwise by the temporal
+   * kernel k(|t_i - t_j|; tau) before the normalisation (temporal.py:8-16, sp.py:697-698).
+   * Applied inside spb_assemble_marginal; the conditional branch scales K with
+   * spb_temporal_scale before spb_assemble_conditional.                                       */
+  int temporal_kind;         /* 0 none, 1 Matern-3/2, 2 squared exponential */
+  const double *tau;         /* one value, or one per batch element (tau_stride 0 | 1) */
+  long long tau_stride;
 } spb_noise_model;
 
 size_t spb_assemble_workspace_bytes(const spb_context *ctx, int B, int nt);
@@ -243,6 +250,13 @@ int spb_cholesky_solve_rows(spb_context *ctx, int nt, const double *L, int ldk, 
  *               nt..ld-1 are zeroed (ld even: the rows are right-hand sides of the solve); K_stride
  *               elements between batch entries.
  * ------------------------------------------------------------------------------------------- */
+/* (f-3) K[b][i][j] = K[b][i][j] * k(|t1_i - t2_j|; tau_b) + offset_b  -- temporal.py:8-16 applied to
+ * a (n1 x n2) block (sp.py:697-698 square, sp.py:893-895 rectangular K(ts, t) followed by the
+ * baseline variance).  kind: 1 Matern-3/2, 2 squared exponential; offset may be NULL.          */
+int spb_temporal_scale(spb_context *ctx, int B, int n1, int n2, const double *t1, const double *t2,
+                       int kind, const double *tau, long long tau_stride, const double *offset,
+                       long long offset_stride, double *K, int ld, long long K_stride, void *stream);
+
 int spb_gemm_nt(spb_context *ctx, int batch, int M, int N, int K, double alpha, const double *A,
                 int lda, long long strideA, const double *Bm, int ldb, long long strideB,
                 double beta, double *C, int ldc, long long strideC, void *stream);

@@ -626,6 +626,18 @@ def alpha_beta_series(z, order=20):
 # ----------------------------------------------------------------------------------------------
 # The process
 # ----------------------------------------------------------------------------------------------
+# temporal.py:8-16
+def ExpSquaredKernel(t1, t2, tau):
+    dt = np.abs(np.reshape(t1, (-1, 1)) - np.reshape(t2, (1, -1)))
+    return np.exp(-(dt ** 2) / (2 * tau))
+
+
+def Matern32Kernel(t1, t2, tau):
+    dt = np.abs(np.reshape(t1, (-1, 1)) - np.reshape(t2, (1, -1)))
+    x = np.sqrt(3) * dt / tau
+    return (1 + x) * np.exp(-x)
+
+
 class OracleProcess(object):
     """Eager NumPy restatement of ``StarryProcess`` (sp.py:38-284) for the lnlike hot path."""
 
@@ -633,8 +645,12 @@ class OracleProcess(object):
                  a=None, b=None, ydeg=15, udeg=2,
                  marginalize_over_inclination=DEFAULTS["marginalize_over_inclination"],
                  normalized=DEFAULTS["normalized"], covpts=DEFAULTS["covpts"], native="port",
-                 skip_longitude_eigh=False, q_ulp_noise_seed=None, **kwargs):
+                 skip_longitude_eigh=False, q_ulp_noise_seed=None, tau=None,
+                 temporal_kernel=Matern32Kernel, **kwargs):
         self.nat = get_native(native)
+        # sp.py:225-232
+        self.tau = None if tau is None else float(check_bounds("tau", tau, 0, np.inf))
+        self.temporal_kernel = temporal_kernel
         self.ydeg = int(ydeg)
         self.udeg = int(udeg)
         assert self.ydeg >= 5 or kwargs.pop("allow_low_ydeg", False)
@@ -829,6 +845,8 @@ class OracleProcess(object):
     # sp.py:674-727
     def cov(self, t, i=DEFAULTS["i"], p=DEFAULTS["p"], u=(0.0, 0.0)):
         mean, cov = self._flux_mean_cov(t, i, p, u)
+        if self.tau is not None:   # sp.py:697-698
+            cov = cov * self.temporal_kernel(t, t, self.tau)
         if self.normalized:
             return self._normalize(1.0 + mean, cov)
         return cov
@@ -922,6 +940,8 @@ class OracleProcess(object):
             A_ts = self.design_matrix(ts, i, p, u)
             A_t = self.design_matrix(t, i, p, u)
             K_ts_t = np.dot(np.dot(A_ts, self.cov_ylm), A_t.T)
+        if self.tau is not None:   # sp.py:893-894
+            K_ts_t = K_ts_t * self.temporal_kernel(ts, t, self.tau)
         K_ts_t = K_ts_t + baseline_var
         cho_K = cho_factor(K_t_t)
         mu = mean + np.dot(K_ts_t, cho_solve(cho_K, y - mean))
@@ -940,6 +960,8 @@ class OracleProcess(object):
                                p=DEFAULTS["p"], u=(0.0, 0.0), baseline_mean=0.0, baseline_var=0.0):
         if self.normalized:
             raise NotImplementedError("Method not implemented when the flux is normalized.")
+        if self.tau is not None:
+            raise NotImplementedError("Method not implemented for time-variable maps.")
         flux = np.asarray(flux, dtype=float)
         data_cov = np.asarray(data_cov, dtype=float)
         if data_cov.ndim == 0:
@@ -961,3 +983,11 @@ class OracleProcess(object):
         ycov = cho_solve(cho_W, np.eye(self.N))
         cho_ycov = cho_factor(ycov)
         return np.transpose(ymu[:, None] + np.dot(cho_ycov, unit_normals))
+
+    # sp.py:510-516 + ops/sample.py:24-33 (SampleYlmTemporalOp: y_i = L_t U_i L_y^T; the reference
+    # does NOT add mean_ylm on this branch), with U (nsamples, nt, N) given
+    def sample_ylm_temporal(self, t, unit_normals):
+        cov_t = self.temporal_kernel(t, t, self.tau)
+        cho_cov_t = cho_factor(cov_t)
+        Ly = self.cho_cov_ylm
+        return np.einsum("km,imj,nj->ikn", cho_cov_t, unit_normals, Ly)

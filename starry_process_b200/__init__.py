@@ -7,5 +7,6 @@ or a CUDA device is missing.
 """
 from .sp import StarryProcess, beta2gauss, defaults, gauss2beta, get_context  # noqa: F401
 from .distributed import gather_lnlike, shard_range  # noqa: F401
+from .temporal import ExpSquaredKernel, Matern32Kernel  # noqa: F401
 
 __version__ = "0.1.0"

@@ -23,6 +23,7 @@ class NoiseModel(_c.Structure):
         ("data_kind", _I), ("data_cov", _P), ("data_stride", _LL),
         ("base_kind", _I), ("baseline_var", _P), ("base_stride", _LL),
         ("lower_only", _I), ("defer", _I),
+        ("temporal_kind", _I), ("tau", _P), ("tau_stride", _LL),
     ]
 
 
@@ -66,6 +67,7 @@ PROTOTYPES = {
                                         _P, _P, _P, _P, _P]),
     "spb_assemble_workspace_layout": (None, [_I, _I, _P, _c.POINTER(_P), _c.POINTER(_P)]),
     "spb_cholesky_solve_rows": (_I, [_P, _I, _P, _I, _I, _P, _I, _P, _P]),
+    "spb_temporal_scale": (_I, [_P, _I, _I, _I, _P, _P, _I, _P, _LL, _P, _LL, _P, _I, _LL, _P]),
     "spb_gemm_nt": (_I, [_P, _I, _I, _I, _I, _D, _P, _I, _LL, _P, _I, _LL, _D, _P, _I, _LL, _P]),
     "spb_tril": (_I, [_P, _I, _I, _P, _I, _LL, _P]),
     "spb_cross_marginal": (_I, [_P, _I, _I, _I, _P, _P, _D, _I, _P, _P, _LL, _P, _I, _LL, _P]),

@@ -41,6 +41,17 @@ __device__ __forceinline__ double interp_cov(const double *cf, int nc, double in
   return cf[ind] + cf[nc + ind] * x0 + cf[2 * nc + ind] * x2 + cf[3 * nc + ind] * (x2 * x0);
 }
 
+// Temporal kernels of time-variable surfaces (temporal.py:8-16), Hadamard-multiplied into the flux
+// covariance BEFORE the normalisation (sp.py:697-698).  kind 1 = Matern-3/2, 2 = squared exponential.
+__device__ __forceinline__ double temporal_k(int kind, double ti, double tj, double tau) {
+  const double dt = fabs(ti - tj);
+  if (kind == 1) {
+    const double x = sqrt(3.0) * dt / tau;
+    return (1.0 + x) * exp(-x);
+  }
+  return exp(-(dt * dt) / (2.0 * tau));
+}
+
 // theta_i = 2 pi mod(t_i / p, 1)  (flux.py:261)
 __device__ __forceinline__ double phase_of(double t, double period) {
   const double x = t / period;
@@ -49,14 +60,18 @@ __device__ __forceinline__ double phase_of(double t, double period) {
 
 // ---- pass A (normalised only): row sums of the raw covariance -------------------------------
 __global__ void __launch_bounds__(256) rowsum_kernel(AsmParams p) {
-  extern __shared__ double sh[];  // coef (4*nc) | theta (nt)
+  extern __shared__ double sh[];  // coef (4*nc) | theta (nt) | t (nt, time-variable only)
   const int b = blockIdx.y;
   const int nc = p.covpts + 1;
-  double *cf = sh, *th = sh + 4 * nc;
+  double *cf = sh, *th = sh + 4 * nc, *tm = th + p.nt;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tkind = p.nm.temporal_kind;
+  const double tau = tkind ? p.nm.tau[(size_t)b * p.nm.tau_stride] : 1.0;
   if (p.marginal) {
     for (int k = tid; k < 4 * nc; k += 256) cf[k] = p.coef[(size_t)b * 4 * nc + k];
     for (int k = tid; k < p.nt; k += 256) th[k] = phase_of(p.t[k], p.period);
+    if (tkind)
+      for (int k = tid; k < p.nt; k += 256) tm[k] = p.t[k];
   }
   __syncthreads();
   const double dx = (double)p.covpts / (2.0 * 3.14159265358979323846);  // 1 / dx
@@ -67,7 +82,13 @@ __global__ void __launch_bounds__(256) rowsum_kernel(AsmParams p) {
         s = (lane == 0) ? p.var[b] : 0.0;
       } else {
         const double thi = th[i];
-        for (int j = lane; j < p.nt; j += 32) s += interp_cov(cf, nc, dx, thi, th[j]);
+        if (tkind) {
+          const double ti = tm[i];
+          for (int j = lane; j < p.nt; j += 32)
+            s += interp_cov(cf, nc, dx, thi, th[j]) * temporal_k(tkind, ti, tm[j], tau);
+        } else {
+          for (int j = lane; j < p.nt; j += 32) s += interp_cov(cf, nc, dx, thi, th[j]);
+        }
       }
     } else {
       const double *row = p.K + ((size_t)b * p.nt + i) * p.ldk;
@@ -88,13 +109,17 @@ constexpr int RS_G = 8;      // CTAs per sample
 constexpr int RS_CB = 1024;  // columns per register block (32 per lane)
 
 __global__ void __launch_bounds__(256) rowsum_sym_kernel(AsmParams p) {
-  extern __shared__ double sh[];  // coef (4*nc) | theta (nt) | part (8 x RS_CB)
+  extern __shared__ double sh[];  // coef (4*nc) | theta (nt) | part (8 x RS_CB) | t (nt, optional)
   const int b = blockIdx.y, c = blockIdx.x;
   const int nc = p.covpts + 1;
-  double *cf = sh, *th = sh + 4 * nc, *part = th + p.nt;
+  double *cf = sh, *th = sh + 4 * nc, *part = th + p.nt, *tm = part + 8 * RS_CB;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tkind = p.nm.temporal_kind;
+  const double tau = tkind ? p.nm.tau[(size_t)b * p.nm.tau_stride] : 1.0;
   for (int k = tid; k < 4 * nc; k += 256) cf[k] = p.coef[(size_t)b * 4 * nc + k];
   for (int k = tid; k < p.nt; k += 256) th[k] = phase_of(p.t[k], p.period);
+  if (tkind)
+    for (int k = tid; k < p.nt; k += 256) tm[k] = p.t[k];
   __syncthreads();
   const double dx = (double)p.covpts / (2.0 * 3.14159265358979323846);  // 1 / dx
   double *rowq = p.rowq + (size_t)b * p.nt;
@@ -106,6 +131,7 @@ __global__ void __launch_bounds__(256) rowsum_sym_kernel(AsmParams p) {
     for (int i = c * 8 + warp; i < p.nt; i += RS_G * 8) {
       if (i < cb0) continue;
       const double thi = th[i];
+      const double ti = tkind ? tm[i] : 0.0;
       double *Krow = p.K + ((size_t)b * p.nt + i) * p.ldk;
       double rs = 0.0;
 #pragma unroll
@@ -113,7 +139,8 @@ __global__ void __launch_bounds__(256) rowsum_sym_kernel(AsmParams p) {
         const int j = cb0 + 32 * k + lane;
         if (cb0 + 32 * k <= i) {        // warp-uniform
           if (j < i) {
-            const double v = interp_cov(cf, nc, dx, thi, th[j]);
+            double v = interp_cov(cf, nc, dx, thi, th[j]);
+            if (tkind) v *= temporal_k(tkind, ti, tm[j], tau);
             rs += v;
             cs[k] += v;
             if (p.nm.defer) Krow[j] = v;   // raw covariance, written once (coalesced along j)
@@ -207,10 +234,15 @@ __global__ void __launch_bounds__(256) write_kernel(AsmParams p) {
   const int b = blockIdx.y;
   const int nc = p.covpts + 1;
   double *cf = sh, *th = sh + (p.marginal ? 4 * nc : 0), *q = th + (p.marginal ? p.nt : 0);
+  double *tm = q + (p.nm.normalized ? p.nt : 0);
   const int tid = threadIdx.x;
+  const int tkind = p.marginal ? p.nm.temporal_kind : 0;
+  const double tau = tkind ? p.nm.tau[(size_t)b * p.nm.tau_stride] : 1.0;
   if (p.marginal) {
     for (int k = tid; k < 4 * nc; k += 256) cf[k] = p.coef[(size_t)b * 4 * nc + k];
     for (int k = tid; k < p.nt; k += 256) th[k] = phase_of(p.t[k], p.period);
+    if (tkind)
+      for (int k = tid; k < p.nt; k += 256) tm[k] = p.t[k];
   }
   double s1 = 1.0, s2 = 0.0, s3 = 0.0;
   if (p.nm.normalized) {
@@ -231,8 +263,12 @@ __global__ void __launch_bounds__(256) write_kernel(AsmParams p) {
     const int jend = (p.marginal && p.nm.lower_only) ? i + 1 : p.nt;
     for (int j = tid; j < jend; j += 256) {
       double v;
-      if (p.marginal) v = (p.nt == 1) ? p.var[b] : interp_cov(cf, nc, dx, thi, th[j]);
-      else v = row[j];
+      if (p.marginal) {
+        v = (p.nt == 1) ? p.var[b] : interp_cov(cf, nc, dx, thi, th[j]);
+        if (tkind) v *= temporal_k(tkind, tm[i], tm[j], tau);
+      } else {
+        v = row[j];
+      }
       if (p.nm.normalized) {
         const double qj = q[j];
         v = s1 * v + (s2 * ((1.0 - qi) * (1.0 - qj)) - s3 * (qi * qj));  // sp.py:721-726
@@ -254,8 +290,11 @@ int run_assemble(spb_context *ctx, AsmParams &p, void *workspace, size_t workspa
   p.scal = p.rowq + (size_t)p.B * p.nt;
   p.colpart = p.scal + (size_t)p.B * 4;
   const int nc = p.covpts + 1;
-  const size_t smA = (p.marginal ? (4 * nc + p.nt) : 0) * sizeof(double);
+  const size_t smT = (p.marginal && p.nm.temporal_kind) ? (size_t)p.nt * sizeof(double) : 0;
+  const size_t smA = (p.marginal ? (4 * nc + p.nt) : 0) * sizeof(double) + smT;
   const size_t smW = smA + (p.nm.normalized ? p.nt : 0) * sizeof(double);
+  SPB_REQUIRE(p.nm.temporal_kind >= 0 && p.nm.temporal_kind <= 2, "assemble: unknown temporal kernel");
+  SPB_REQUIRE(!p.nm.temporal_kind || p.nm.tau != nullptr, "assemble: temporal kernel without tau");
   SPB_REQUIRE(smW <= 200 * 1024, "assemble: nt too large for the shared-memory staging");
   static bool attr = false;
   if (!attr) {
@@ -334,6 +373,42 @@ __global__ void __launch_bounds__(256) cross_marginal_kernel(int nts, int nt, in
   }
 }
 }  // namespace
+
+namespace {
+__global__ void __launch_bounds__(256) temporal_scale_kernel(int n1, int n2, const double *t1,
+                                                             const double *t2, int kind,
+                                                             const double *tau, long long tau_stride,
+                                                             const double *offset,
+                                                             long long offset_stride, double *K,
+                                                             int ld, long long stride) {
+  const int b = blockIdx.y;
+  const double tb = tau[(size_t)b * tau_stride];
+  const double off = offset ? offset[(size_t)b * offset_stride] : 0.0;
+  for (int i = blockIdx.x; i < n1; i += gridDim.x) {
+    const double ti = t1[i];
+    double *row = K + (size_t)b * stride + (size_t)i * ld;
+    for (int j = threadIdx.x; j < n2; j += 256)
+      row[j] = fma(row[j], temporal_k(kind, ti, t2[j], tb), off);
+  }
+}
+}  // namespace
+
+extern "C" int spb_temporal_scale(spb_context *ctx, int B, int n1, int n2, const double *t1,
+                                  const double *t2, int kind, const double *tau,
+                                  long long tau_stride, const double *offset,
+                                  long long offset_stride, double *K, int ld, long long K_stride,
+                                  void *stream) {
+  SPB_REQUIRE(ctx != nullptr && B > 0 && n1 > 0 && n2 > 0 && ld >= n2 && K != nullptr && tau != nullptr,
+              "temporal_scale: bad arguments");
+  SPB_REQUIRE(kind == 1 || kind == 2, "temporal_scale: unknown kernel");
+  SPB_REQUIRE(B <= 65535, "temporal_scale: batch too large for one launch");
+  SPB_CHECK_CUDA(cudaSetDevice(ctx->device));
+  int gx = n1 < 8 * ctx->num_sms ? n1 : 8 * ctx->num_sms;
+  temporal_scale_kernel<<<dim3(gx, B), 256, 0, (cudaStream_t)stream>>>(
+      n1, n2, t1, t2, kind, tau, tau_stride, offset, offset_stride, K, ld, K_stride);
+  SPB_LAUNCH_CHECK(ctx);
+  return 0;
+}
 
 extern "C" int spb_cross_marginal(spb_context *ctx, int B, int nts, int nt, const double *ts,
                                   const double *t, double period, int covpts, const double *coef,

@@ -11,13 +11,14 @@ path; inputs/outputs are ``torch.float64`` CUDA tensors and evaluation is eager.
 behind ``include/spb200.h``) -- there is no CPU or PyTorch fallback: without the library (or without
 a CUDA device) construction raises.
 
-SURVEY.md section 8(f) rank 2 is covered as well: ``sample``, ``predict``, ``sample_conditional``
-and ``sample_ylm_conditional`` (sp.py:518-641, 729-765, 767-1002), composed from the same Cholesky
-/ GEMM / assembly kernels.
+SURVEY.md section 8(f) ranks 2 and 3 are covered as well: ``sample``, ``predict``,
+``sample_conditional`` and ``sample_ylm_conditional`` (sp.py:518-641, 729-765, 767-1002), composed
+from the same Cholesky / GEMM / assembly kernels, and time-variable surfaces (``tau``,
+``temporal_kernel``: temporal.py:8-16, sp.py:697-698, 893-894, 510-516).
 
 Out of scope in this drop-in (callers, listed under "next"): the uniform
-spot-size prior (``dr``), time-variable surfaces (``tau``), pixel-space moments and visualisation.
-They raise ``NotImplementedError``.
+spot-size prior (``dr``), gradients, pixel-space moments and visualisation.  They raise
+``NotImplementedError``.
 """
 import ctypes
 import math
@@ -25,7 +26,7 @@ import math
 import numpy as np
 import torch
 
-from . import _lib, _tables
+from . import _lib, _tables, temporal as _temporal
 
 __all__ = ["StarryProcess", "gauss2beta", "beta2gauss", "defaults"]
 
@@ -156,8 +157,24 @@ class StarryProcess(object):
             raise ValueError("Must provide either `a` and `b` *or* `mu` and `sigma`.")
         if dr is not None:
             raise NotImplementedError("uniform spot-size prior (dr) is outside the lnlike hot path")
-        if tau is not None:
-            raise NotImplementedError("time-variable surfaces (tau) are outside the lnlike hot path")
+        # sp.py:225-232; the reference accepts any callable f(t1, t2, tau): the CUDA assembly
+        # implements the two kernels the reference ships (temporal.py)
+        self._time_variable = tau is not None
+        self._tkind = 0
+        if self._time_variable:
+            tk = _temporal.Matern32Kernel if temporal_kernel is None else temporal_kernel
+            if isinstance(tk, str):
+                tk = {"matern32": _temporal.Matern32Kernel,
+                      "expsquared": _temporal.ExpSquaredKernel}.get(tk.lower())
+            kind = getattr(tk, "spb_kind", None)
+            if kind is None:
+                kind = {"Matern32Kernel": 1, "ExpSquaredKernel": 2}.get(
+                    getattr(tk, "__name__", ""), None)
+            if kind is None:
+                raise NotImplementedError("temporal_kernel must be Matern32Kernel or "
+                                          "ExpSquaredKernel (starry_process_b200.temporal)")
+            self._tkind = int(kind)
+            self._temporal_kernel = tk
         self._ydeg = int(kwargs.pop("ydeg", defaults["ydeg"]))
         self._udeg = int(kwargs.pop("udeg", defaults["udeg"]))
         if self._ydeg != 15:
@@ -184,6 +201,8 @@ class StarryProcess(object):
         self._lib = self._ctx.lib
 
         params = dict(r=r, c=c, n=n)
+        if self._time_variable:
+            params["tau"] = tau
         if a is None:
             params.update(mu=mu, sigma=sigma)
         else:
@@ -202,6 +221,8 @@ class StarryProcess(object):
             _check_bounds("b", hostvals["b"], 0, 1)
         if "n" in hostvals:
             _check_bounds("n", hostvals["n"], 0, np.inf)
+        if "tau" in hostvals:
+            _check_bounds("tau", hostvals["tau"], 0, np.inf)
         tens = {k: torch.as_tensor(v, dtype=torch.float64).to(self.device).reshape(-1)
                 for k, v in params.items()}
         B = max(t.numel() for t in tens.values())
@@ -212,6 +233,7 @@ class StarryProcess(object):
             tens[k] = t.expand(B).contiguous()
         self._B = B
         self._r, self._c, self._n = tens["r"], tens["c"], tens["n"]
+        self._tau = tens.get("tau", None)
         if a is None:
             self._a = torch.empty(B, dtype=torch.float64, device=self.device)
             self._b = torch.empty(B, dtype=torch.float64, device=self.device)
@@ -330,7 +352,7 @@ class StarryProcess(object):
         standard-normal draws, shape ``(nylm, nsamples)`` as in the reference's
         ``random_normal(self.random, (nylm, nsamples))`` or ``(B, nylm, nsamples)``."""
         if t is not None:
-            raise NotImplementedError("time-variable sampling (tau) is outside the lnlike hot path")
+            return self._sample_ylm_temporal(t, nsamples, u, generator)
         L = self.cho_cov_ylm
         L = L if self._batched else L[None]
         B = self._B
@@ -405,6 +427,9 @@ class StarryProcess(object):
         nm.baseline_var = None
         nm.data_stride = 0
         nm.base_stride = 0
+        nm.temporal_kind = self._tkind
+        nm.tau = self._tau[b0:].data_ptr() if self._tkind else None
+        nm.tau_stride = 1 if self._tkind else 0
         if data_cov is not None:
             d = torch.as_tensor(data_cov, dtype=torch.float64).to(self.device).contiguous()
             if d.ndim == 0:
@@ -491,6 +516,10 @@ class StarryProcess(object):
             _lib.check(lib.spb_flux_conditional(h, Bc, nt, _ptr(A), 0 if Ic == 1 else nt * 256,
                                                 _ptr(mean_ylm), _ptr(cov_ylm), _ptr(gp_mean),
                                                 _ptr(K), ldk, _ptr(ws), nb, _stream()))
+            if self._tkind:   # sp.py:697-698
+                _lib.check(lib.spb_temporal_scale(h, Bc, nt, nt, _ptr(t), _ptr(t), self._tkind,
+                                                  _ptr(self._tau[b0:b1].contiguous()), 1, None, 0,
+                                                  _ptr(K), ldk, nt * ldk, _stream()))
             _lib.check(lib.spb_assemble_conditional(h, Bc, nt, _ptr(gp_mean), ctypes.byref(nm),
                                                     _ptr(K), ldk, _ptr(z), _ptr(info), _ptr(ws_as),
                                                     nb_as, _stream()))
@@ -757,11 +786,14 @@ class StarryProcess(object):
             off = None
             if bvar is not None and scalar_bvar:
                 off = bvar.reshape(-1).contiguous()
+            off_s = 0 if off is None or off.numel() == 1 else 1
+            late_off = off if self._tkind else None   # K(ts,t) *= k_temporal BEFORE + baseline_var
+            if self._tkind:
+                off = None
             if marg:
                 _lib.check(lib.spb_cross_marginal(
                     h, B, nts, nt, _ptr(ts), _ptr(t), float(p), self._covpts,
-                    _ptr(self._last_coef), _ptr(off), 0 if off is None or off.numel() == 1 else 1,
-                    _ptr(R), ldk, rstride, _stream()))
+                    _ptr(self._last_coef), _ptr(off), off_s, _ptr(R), ldk, rstride, _stream()))
             else:
                 I = inc.numel()
                 per = torch.full((I,), float(p), dtype=torch.float64, device=dev)
@@ -783,6 +815,10 @@ class StarryProcess(object):
                     R[:, :nts, :nt] = off.reshape(-1, 1, 1)
                 self._gemm(B, nts, nt, 256, T, 256, nts * 256, A_t, 256, 0 if I == 1 else nt * 256,
                            R, ldk, rstride, alpha=1.0, beta=1.0)
+            if self._tkind:   # sp.py:893-895
+                _lib.check(lib.spb_temporal_scale(h, B, nts, nt, _ptr(ts), _ptr(t), self._tkind,
+                                                  _ptr(self._tau), 1, _ptr(late_off), off_s,
+                                                  _ptr(R), ldk, rstride, _stream()))
             if bvar is not None and not scalar_bvar:
                 R[:, :nts, :nt] += bvar
             R[:, nts, :nt] = (f - bm)[None, :] - gp_mean[:, None]
@@ -838,6 +874,8 @@ class StarryProcess(object):
         inverse a forward substitution on appended rows of the Cholesky kernel."""
         if self._normalized:
             raise NotImplementedError("Method not implemented when the flux is normalized.")
+        if self._time_variable:
+            raise NotImplementedError("Method not implemented for time-variable maps.")
         self._compute_moments()
         dev, B = self.device, self._B
         t = self._t(t)
@@ -901,4 +939,59 @@ class StarryProcess(object):
             out = self._draw(ymu, ycov, 256, 256, nsamples, unit_normals, generator)
             bad = (((infoY | infoW | infoS) & 1) != 0) | ((infoC & 1) != 0)
             out = torch.where(bad[:, None, None], torch.full_like(out, float("nan")), out)
+        return self._out(out)
+
+    # ------------------------------------------------------------------ SURVEY 8(f) rank 3
+    @property
+    def tau(self):
+        """sp.py:337-340."""
+        return None if self._tau is None else self._out(self._tau)
+
+    @property
+    def temporal_kernel(self):
+        """sp.py:342-345."""
+        return getattr(self, "_temporal_kernel", None)
+
+    def _sample_ylm_temporal(self, t, nsamples, u, generator):
+        """sp.py:510-516 + ops/sample.py:24-33 (a triple Python loop in the reference):
+        ``y_i = L_t U_i L_y^T`` with ``L_t = cho_factor(temporal_kernel(t, t, tau))`` -- two
+        tensor-core GEMMs per batch element.  As in the reference, ``mean_ylm`` is NOT added on
+        this branch.  ``u`` optionally supplies ``U`` of shape ``(nsamples, nt, nylm)``."""
+        if not self._time_variable:
+            raise ValueError("sample_ylm(t=...) needs a time-variable process (tau)")
+        t = self._t(t)
+        nt = t.numel()
+        ldt = nt + (nt & 1)
+        dev, B = self.device, self._B
+        Ly = self.cho_cov_ylm
+        Ly = (Ly if self._batched else Ly[None]).contiguous()
+        lib, h = self._lib, self._ctx.handle
+        with torch.cuda.device(dev):
+            Kt = torch.zeros(B, nt, ldt, dtype=torch.float64, device=dev)
+            Kt[:, :, :nt] = 1.0
+            _lib.check(lib.spb_temporal_scale(h, B, nt, nt, _ptr(t), _ptr(t), self._tkind,
+                                              _ptr(self._tau), 1, None, 0, _ptr(Kt), ldt, nt * ldt,
+                                              _stream()))
+            info = self._factor_rows(Kt, nt, ldt)
+            _lib.check(lib.spb_tril(h, B, nt, _ptr(Kt), ldt, nt * ldt, _stream()))
+            if u is None:
+                U = torch.randn(nsamples, nt, 256, dtype=torch.float64, device=dev,
+                                generator=generator)
+            else:
+                U = torch.as_tensor(u, dtype=torch.float64).to(dev)
+                if U.ndim != 3 or U.shape[1] != nt or U.shape[2] != 256:
+                    raise ValueError("u must have shape (nsamples, nt, 256)")
+                nsamples = U.shape[0]
+            # V[s] = L_t U_s  (NT form: Bm = U_s^T, k = time, zero-padded to an even length)
+            Ut = torch.zeros(nsamples, 256, ldt, dtype=torch.float64, device=dev)
+            Ut[:, :, :nt] = U.transpose(1, 2)
+            out = torch.empty(B, nsamples, nt, 256, dtype=torch.float64, device=dev)
+            V = torch.empty(nsamples, nt, 256, dtype=torch.float64, device=dev)
+            for b in range(B):
+                self._gemm(nsamples, nt, 256, ldt, Kt[b], ldt, 0, Ut, ldt, 256 * ldt, V, 256,
+                           nt * 256)
+                self._gemm(nsamples, nt, 256, 256, V, 256, nt * 256, Ly[b], 256, 0, out[b], 256,
+                           nt * 256)
+            out = torch.where(((info & 1) != 0)[:, None, None, None],
+                              torch.full_like(out, float("nan")), out)
         return self._out(out)
