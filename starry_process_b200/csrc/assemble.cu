@@ -108,17 +108,20 @@ __global__ void __launch_bounds__(256) rowsum_kernel(AsmParams p) {
 constexpr int RS_G = 8;      // CTAs per sample
 constexpr int RS_CB = 1024;  // columns per register block (32 per lane)
 
+// TEMPORAL is a compile-time switch: the time-variable branch must not cost the static path (the
+// bench workload) registers or predicated instructions in its inner loop.
+template <bool TEMPORAL>
 __global__ void __launch_bounds__(256) rowsum_sym_kernel(AsmParams p) {
   extern __shared__ double sh[];  // coef (4*nc) | theta (nt) | part (8 x RS_CB) | t (nt, optional)
   const int b = blockIdx.y, c = blockIdx.x;
   const int nc = p.covpts + 1;
   double *cf = sh, *th = sh + 4 * nc, *part = th + p.nt, *tm = part + 8 * RS_CB;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int tkind = p.nm.temporal_kind;
+  const int tkind = TEMPORAL ? p.nm.temporal_kind : 0;
   const double tau = tkind ? p.nm.tau[(size_t)b * p.nm.tau_stride] : 1.0;
   for (int k = tid; k < 4 * nc; k += 256) cf[k] = p.coef[(size_t)b * 4 * nc + k];
   for (int k = tid; k < p.nt; k += 256) th[k] = phase_of(p.t[k], p.period);
-  if (tkind)
+  if (TEMPORAL)
     for (int k = tid; k < p.nt; k += 256) tm[k] = p.t[k];
   __syncthreads();
   const double dx = (double)p.covpts / (2.0 * 3.14159265358979323846);  // 1 / dx
@@ -131,7 +134,7 @@ __global__ void __launch_bounds__(256) rowsum_sym_kernel(AsmParams p) {
     for (int i = c * 8 + warp; i < p.nt; i += RS_G * 8) {
       if (i < cb0) continue;
       const double thi = th[i];
-      const double ti = tkind ? tm[i] : 0.0;
+      const double ti = TEMPORAL ? tm[i] : 0.0;
       double *Krow = p.K + ((size_t)b * p.nt + i) * p.ldk;
       double rs = 0.0;
 #pragma unroll
@@ -140,7 +143,7 @@ __global__ void __launch_bounds__(256) rowsum_sym_kernel(AsmParams p) {
         if (cb0 + 32 * k <= i) {        // warp-uniform
           if (j < i) {
             double v = interp_cov(cf, nc, dx, thi, th[j]);
-            if (tkind) v *= temporal_k(tkind, ti, tm[j], tau);
+            if (TEMPORAL) v *= temporal_k(tkind, ti, tm[j], tau);
             rs += v;
             cs[k] += v;
             if (p.nm.defer) Krow[j] = v;   // raw covariance, written once (coalesced along j)
@@ -229,6 +232,7 @@ __device__ __forceinline__ double noise_term(const spb_noise_model &nm, int b, i
 }
 
 // ---- pass W: write K (marginal) or update it in place (conditional) ---------------------------
+template <bool TEMPORAL>
 __global__ void __launch_bounds__(256) write_kernel(AsmParams p) {
   extern __shared__ double sh[];
   const int b = blockIdx.y;
@@ -236,12 +240,12 @@ __global__ void __launch_bounds__(256) write_kernel(AsmParams p) {
   double *cf = sh, *th = sh + (p.marginal ? 4 * nc : 0), *q = th + (p.marginal ? p.nt : 0);
   double *tm = q + (p.nm.normalized ? p.nt : 0);
   const int tid = threadIdx.x;
-  const int tkind = p.marginal ? p.nm.temporal_kind : 0;
+  const int tkind = (TEMPORAL && p.marginal) ? p.nm.temporal_kind : 0;
   const double tau = tkind ? p.nm.tau[(size_t)b * p.nm.tau_stride] : 1.0;
   if (p.marginal) {
     for (int k = tid; k < 4 * nc; k += 256) cf[k] = p.coef[(size_t)b * 4 * nc + k];
     for (int k = tid; k < p.nt; k += 256) th[k] = phase_of(p.t[k], p.period);
-    if (tkind)
+    if (TEMPORAL && tkind)
       for (int k = tid; k < p.nt; k += 256) tm[k] = p.t[k];
   }
   double s1 = 1.0, s2 = 0.0, s3 = 0.0;
@@ -265,7 +269,7 @@ __global__ void __launch_bounds__(256) write_kernel(AsmParams p) {
       double v;
       if (p.marginal) {
         v = (p.nt == 1) ? p.var[b] : interp_cov(cf, nc, dx, thi, th[j]);
-        if (tkind) v *= temporal_k(tkind, tm[i], tm[j], tau);
+        if (TEMPORAL && tkind) v *= temporal_k(tkind, tm[i], tm[j], tau);
       } else {
         v = row[j];
       }
@@ -300,22 +304,27 @@ int run_assemble(spb_context *ctx, AsmParams &p, void *workspace, size_t workspa
   if (!attr) {
     SPB_CHECK_CUDA(cudaFuncSetAttribute(rowsum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         200 * 1024));
-    SPB_CHECK_CUDA(cudaFuncSetAttribute(write_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        200 * 1024));
+    SPB_CHECK_CUDA(cudaFuncSetAttribute(write_kernel<false>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    SPB_CHECK_CUDA(cudaFuncSetAttribute(write_kernel<true>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr = true;
   }
   if (p.nm.normalized) {
     if (p.marginal) {
       static bool attr2 = false;
       if (!attr2) {
-        SPB_CHECK_CUDA(cudaFuncSetAttribute(rowsum_sym_kernel,
+        SPB_CHECK_CUDA(cudaFuncSetAttribute(rowsum_sym_kernel<false>,
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        SPB_CHECK_CUDA(cudaFuncSetAttribute(rowsum_sym_kernel<true>,
                                             cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         attr2 = true;
       }
       const size_t smS = smA + (size_t)8 * RS_CB * sizeof(double);
       SPB_REQUIRE(smS <= 200 * 1024, "assemble: nt too large for the shared-memory staging");
       dim3 gridS(RS_G, p.B);
-      rowsum_sym_kernel<<<gridS, 256, smS, stream>>>(p);
+      if (p.nm.temporal_kind) rowsum_sym_kernel<true><<<gridS, 256, smS, stream>>>(p);
+      else rowsum_sym_kernel<false><<<gridS, 256, smS, stream>>>(p);
     } else {
       dim3 gridA(min((p.nt + 7) / 8, 16), p.B);
       rowsum_kernel<<<gridA, 256, smA, stream>>>(p);
@@ -334,12 +343,14 @@ int run_assemble(spb_context *ctx, AsmParams &p, void *workspace, size_t workspa
     raw.nm.data_cov = nullptr;
     raw.nm.baseline_var = nullptr;
     dim3 gridR(min(p.nt, 32), p.B);
-    write_kernel<<<gridR, 256, smW, stream>>>(raw);
+    if (p.marginal && p.nm.temporal_kind) write_kernel<true><<<gridR, 256, smW, stream>>>(raw);
+    else write_kernel<false><<<gridR, 256, smW, stream>>>(raw);
     SPB_LAUNCH_CHECK(ctx);
     return 0;
   }
   dim3 gridW(min(p.nt, 32), p.B);
-  write_kernel<<<gridW, 256, smW, stream>>>(p);
+  if (p.marginal && p.nm.temporal_kind) write_kernel<true><<<gridW, 256, smW, stream>>>(p);
+  else write_kernel<false><<<gridW, 256, smW, stream>>>(p);
   SPB_LAUNCH_CHECK(ctx);
   return 0;
 }

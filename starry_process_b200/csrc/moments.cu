@@ -41,22 +41,36 @@ struct K1Params {
   double *scale;     // (B)       (pi c)^2 n
   int *rkeep;        // (B)
   int32_t *info;     // (B)
+  double *Sred;      // (B,32,32) workspace: S = Z^T Q Z (K1a) -> V diag(sqrt w), compacted (K1b)
+  double *qs;        // (B,16)    workspace: spot-size coefficients q_l
 };
 
+// K1 is split in three so that the latency-bound eigen-solve (a chain of FP64 divisions and square
+// roots per Jacobi round, ~280 rounds) runs with ONE WARP per sample and a dozen samples in flight
+// per SM, instead of one 256-thread CTA per sample with 15 of its 16 warps idle:
+//   K1a (256 threads / sample)  profile, Beta moments, term table, S = Z^T Q Z, first moments
+//   K1b (1 warp / sample)       cyclic Jacobi on S, clip, X = V diag(sqrt w)
+//   K1c (256 threads / sample)  sqrtC_lat = q_l H X
 struct K1Smem {
+  double Zs[32][32];      // 32 rows of the range basis Z at a time (first: 16-byte aligned)
   double bprof[1000];
   double qs[16];
   double Bk[64];
   double tt[31][31];      // term(2a, 2b)
-  double Y[256][33];      // Q Z, later re-used
+  double Y[256][33];      // Q Z
+  double A[32][JS];       // S, symmetrised
+  double V[32][JS];       // staging
+  double m1lat[256];
+};
+
+constexpr int K1B_WARPS = 4;   // samples per CTA of the eigen-solve kernel
+struct K1bWarp {
   double A[32][JS];       // Jacobi iterate
   double V[32][JS];       // eigenvectors
-  double Xs[32][JS];      // V diag(sqrt w), kept modes compacted
   double cs[16][2];
-  double m1lat[256];
   int pp[16], qq[16];
-  int rotated;
   int order[32];
+  int rotated;
   int rk;
 };
 
@@ -67,10 +81,67 @@ __device__ __forceinline__ void lm_of(int n, int &l, int &m) {
   m = n - l * l - l;
 }
 
-__global__ void __launch_bounds__(NT1, 2) moments_k1(K1Params p) {
+// Ylm rows sorted by the parity of l - m (even first); see the Y = Q Z stage of K1a
+__constant__ int k1_perm[256];
+// term-table work list: k1_tt_sched[slot * 256 + tid] = a * 31 + b, or -1
+__constant__ int k1_tt_sched[3 * 256];
+
+int k1_upload_perm() {
+  static bool done = false;
+  if (!done) {
+    int perm[256], n = 0;
+    for (int par = 0; par < 2; ++par)
+      for (int l = 0; l <= SPB_LMAX; ++l)
+        for (int m = -l; m <= l; ++m)
+          if (((l - m) & 1) == par) perm[n++] = l * l + l + m;
+    if (cudaMemcpyToSymbol(k1_perm, perm, sizeof(perm)) != cudaSuccess) return 1;
+    // longest-processing-time-first assignment of the (a, b) pairs with a + b <= 30
+    int sched[3 * 256], cnt[256] = {0};
+    long load[256] = {0};
+    for (int i = 0; i < 3 * 256; ++i) sched[i] = -1;
+    bool used[961] = {false};
+    for (;;) {
+      int best = -1, bt = 0;
+      for (int idx = 0; idx < 961; ++idx) {
+        const int a2 = idx / 31, b2 = idx % 31;
+        if (used[idx] || a2 + b2 > 30) continue;
+        const int t = (a2 + 1) * (b2 + 1);
+        if (t > bt) {
+          bt = t;
+          best = idx;
+        }
+      }
+      if (best < 0) break;
+      used[best] = true;
+      int k = -1;
+      for (int t = 0; t < 256; ++t)
+        if (cnt[t] < 3 && (k < 0 || load[t] < load[k])) k = t;
+      if (k < 0) return 1;
+      sched[cnt[k] * 256 + k] = best;
+      ++cnt[k];
+      load[k] += bt;
+    }
+    if (cudaMemcpyToSymbol(k1_tt_sched, sched, sizeof(sched)) != cudaSuccess) return 1;
+    done = true;
+  }
+  return 0;
+}
+
+#ifdef SPB_POTRF_PROF
+__device__ unsigned long long g_k1a_prof[8];
+__device__ unsigned long long g_k1b_prof[8];
+#define K1PROF(k) do { __syncthreads(); if (threadIdx.x == 0) { unsigned long long _n = clock64(); atomicAdd(&g_k1a_prof[k], _n - _pt); _pt = _n; } } while (0)
+#else
+#define K1PROF(k)
+#endif
+
+__global__ void __launch_bounds__(NT1, 2) moments_k1a(K1Params p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   K1Smem &sm = *reinterpret_cast<K1Smem *>(smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+#ifdef SPB_POTRF_PROF
+  unsigned long long _pt = clock64();
+#endif
   const int b = blockIdx.x;
   const double *tab = p.tab;
 
@@ -100,6 +171,7 @@ __global__ void __launch_bounds__(NT1, 2) moments_k1(K1Params p) {
     if (lane == 0) sm.qs[row] = acc;
   }
 
+  K1PROF(0);
   // ---- Beta moments, latitude.py:197-200 and latitude.h:48-60
   if (tid == 0) {
     const double alpha0 = exp(aa * 10.0);
@@ -115,23 +187,53 @@ __global__ void __launch_bounds__(NT1, 2) moments_k1(K1Params p) {
   }
   __syncthreads();
 
+  K1PROF(1);
   // ---- term(2a, 2b) = sum_k1 sum_k2 C(a,k1) (-1)^k2 C(b,k2) B(k1+k2), latitude.h:112-143
   // The signed binomial products come from the LAT_FAC table (built on the host with the
   // reference's ratio recurrences, bit-identical to evaluating them here); the accumulation order
   // is the reference's.  The heavy (a, b) pairs are dealt out first so the tail is short.
   {
+    // Work list: the 496 non-zero (a, b) pairs are dealt to the 256 threads longest-first (LPT,
+    // k1_tt_sched): the longest chain is then the single heaviest pair (256 terms) instead of 374
+    // terms.  The factors live in L2 (371 KB table) and are streamed ahead of the (serial,
+    // reference-ordered) accumulation.
     const double *fac = p.tab + SPB_TAB_LAT_FAC;
     const double *facoff = p.tab + SPB_TAB_LAT_FACOFF;
     for (int idx = tid; idx < 31 * 31; idx += NT1) {
       const int a2 = idx / 31, b2 = idx % 31;
+      if (a2 + b2 > 30) sm.tt[a2][b2] = 0.0;
+    }
+#pragma unroll 1
+    for (int slot = 0; slot < 3; ++slot) {
+      const int idx = k1_tt_sched[slot * 256 + tid];
+      if (idx < 0) continue;
+      const int a2 = idx / 31, b2 = idx % 31;
       double acc = 0.0;
-      if (a2 + b2 <= 30) {
-        const double *f = fac + (int)facoff[idx];
-        for (int k1 = 0; k1 < a2 + 1; ++k1) {
-          const double *bk = sm.Bk + k1;
-#pragma unroll 4
-          for (int k2 = 0; k2 < b2 + 1; ++k2) acc += f[k2] * bk[k2];
-          f += b2 + 1;
+      const double *f = fac + (int)facoff[idx];
+      // the rows of the double sum are contiguous in the table: one flat, software-pipelined stream
+      // (16 factors in flight while the previous 16 are accumulated in the reference's order)
+      const int T = (a2 + 1) * (b2 + 1), w = b2 + 1;
+      double nxt[16];
+#pragma unroll
+      for (int u = 0; u < 16; ++u) nxt[u] = (u < T) ? __ldg(f + u) : 0.0;
+      int k1 = 0, k2 = 0;
+      for (int n0 = 0; n0 < T; n0 += 16) {
+        double cur[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) cur[u] = nxt[u];
+        if (n0 + 16 < T) {
+#pragma unroll
+          for (int u = 0; u < 16; ++u) nxt[u] = (n0 + 16 + u < T) ? __ldg(f + n0 + 16 + u) : 0.0;
+        }
+        // branch-free: slots past the end carry a zero factor (adding 0 is exact), and k1 + k2
+        // stays inside Bk[64]
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+          acc += cur[u] * sm.Bk[k1 + k2];
+          ++k2;
+          const bool wrap = (k2 == w);
+          k2 = wrap ? 0 : k2;
+          k1 += wrap ? 1 : 0;
         }
       }
       sm.tt[a2][b2] = acc;
@@ -139,50 +241,71 @@ __global__ void __launch_bounds__(NT1, 2) moments_k1(K1Params p) {
   }
   __syncthreads();
 
+  K1PROF(2);
   // ---- Y = Q Z with Q(n1,n2) = term(j1+j2, i1+i2) 2^-(l1+l2)   (latitude.h:146-172)
+  // Q(n1, n2) vanishes unless l - m has the same parity for both indices.  Rows are dealt to the
+  // threads sorted by that parity (136 even rows, then 120 odd: seven of the eight warps are
+  // parity-uniform and skip the other half of the n2 loop as a whole instead of idling half their
+  // lanes), and Z is staged through shared memory 32 rows at a time (the 64 KB table does not
+  // survive in the ~30 KB of L1 that two resident CTAs leave: every row used to be an L2 round
+  // trip).  Each y[a] still accumulates over n2 in ascending order: results are unchanged.
   int l1, m1;
   lm_of(tid, l1, m1);
-  const int j1 = m1 + l1, i1 = l1 - m1;
   {
+    int lp, mp;
+    const int n1 = k1_perm[tid];
+    lm_of(n1, lp, mp);
+    const int jp = mp + lp, ip = lp - mp;
     double y[32];   // column 31 of the padded basis is zero
 #pragma unroll
     for (int a = 0; a < 32; ++a) y[a] = 0.0;
     const double *Z = tab + SPB_TAB_LAT_Z;
     int l2 = 0, m2 = 0;
-    for (int n2 = 0; n2 < 256; ++n2) {
-      const int J = j1 + m2 + l2, I = i1 + l2 - m2;
-      // Q(n1, n2) vanishes unless l+m has the same parity for both indices (latitude.h:146-172):
-      // the warp-uniform row of Z is only fetched (as 16-byte loads) when this thread needs it
-      if (!(I & 1)) {
-        const double qv = ldexp(sm.tt[J >> 1][I >> 1], -(l1 + l2));
-        const double2 *zr = reinterpret_cast<const double2 *>(Z + n2 * 32);
+    for (int c0 = 0; c0 < 256; c0 += 32) {
+      __syncthreads();
+      for (int k = tid; k < 32 * 16; k += NT1)
+        reinterpret_cast<double2 *>(&sm.Zs[0][0])[k] =
+            __ldg(reinterpret_cast<const double2 *>(Z + c0 * 32) + k);
+      __syncthreads();
+      for (int r = 0; r < 32; ++r) {
+        const int J = jp + m2 + l2, I = ip + l2 - m2;
+        if (!(I & 1)) {
+          const double qv = ldexp(sm.tt[J >> 1][I >> 1], -(lp + l2));
+          const double2 *zr = reinterpret_cast<const double2 *>(&sm.Zs[r][0]);
 #pragma unroll
-        for (int a = 0; a < 16; ++a) {
-          const double2 z2 = __ldg(zr + a);
-          y[2 * a] = fma(qv, z2.x, y[2 * a]);
-          y[2 * a + 1] = fma(qv, z2.y, y[2 * a + 1]);
+          for (int a = 0; a < 16; ++a) {
+            const double2 z2 = zr[a];
+            y[2 * a] = fma(qv, z2.x, y[2 * a]);
+            y[2 * a + 1] = fma(qv, z2.y, y[2 * a + 1]);
+          }
+        }
+        if (++m2 > l2) {
+          ++l2;
+          m2 = -l2;
         }
       }
-      if (++m2 > l2) {
-        ++l2;
-        m2 = -l2;
+    }
+#pragma unroll
+    for (int a = 0; a < 31; ++a) sm.Y[n1][a] = y[a];
+  }
+  __syncthreads();
+  K1PROF(3);
+  // ---- S = Z^T Y (31 x 31), symmetrised, padded to 32.  Thread (warp, lane) owns the four entries
+  // S[warp + 8 j][lane]: four independent accumulation chains over n1 (ascending, as before)
+  // instead of four consecutive ones.
+  {
+    const double *Z = tab + SPB_TAB_LAT_Z;
+    double s4[4] = {0.0, 0.0, 0.0, 0.0};
+    if (lane < 31) {
+#pragma unroll 4
+      for (int n1 = 0; n1 < 256; ++n1) {
+        const double yv = sm.Y[n1][lane];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) s4[j] = fma(__ldg(Z + n1 * 32 + warp + 8 * j), yv, s4[j]);
       }
     }
 #pragma unroll
-    for (int a = 0; a < 31; ++a) sm.Y[tid][a] = y[a];
-  }
-  __syncthreads();
-  // ---- S = Z^T Y (31 x 31), symmetrised, padded to 32
-  {
-    const double *Z = tab + SPB_TAB_LAT_Z;
-    for (int idx = tid; idx < 32 * 32; idx += NT1) {
-      const int a = idx >> 5, c2 = idx & 31;
-      double s = 0.0;
-      if (a < 31 && c2 < 31) {
-        for (int n1 = 0; n1 < 256; ++n1) s = fma(Z[n1 * 32 + a], sm.Y[n1][c2], s);
-      }
-      sm.V[a][c2] = s;  // staging
-    }
+    for (int j = 0; j < 4; ++j) sm.V[warp + 8 * j][lane] = (warp + 8 * j < 31) ? s4[j] : 0.0;   // staging
   }
   __syncthreads();
   for (int idx = tid; idx < 32 * 32; idx += NT1) {
@@ -190,125 +313,11 @@ __global__ void __launch_bounds__(NT1, 2) moments_k1(K1Params p) {
     sm.A[a][c2] = 0.5 * (sm.V[a][c2] + sm.V[c2][a]);
   }
   __syncthreads();
-  for (int idx = tid; idx < 32 * 32; idx += NT1) {
-    const int a = idx >> 5, c2 = idx & 31;
-    sm.V[a][c2] = (a == c2) ? 1.0 : 0.0;
-  }
-  __syncthreads();
-
-  // ---- parallel cyclic Jacobi (round-robin ordering, 16 disjoint rotations per round)
-  double amax = 0.0;
-  for (int a = 0; a < 31; ++a) amax = fmax(amax, fabs(sm.A[a][a]));
-  const double rot_tol = 1e-20 * amax;
-  bool converged = false;
-  for (int sweep = 0; sweep < 16 && !converged; ++sweep) {
-    if (tid == 0) sm.rotated = 0;
-    __syncthreads();
-    for (int rnd = 0; rnd < 31; ++rnd) {
-      if (tid < 16) {
-        int pi, qi;
-        if (tid == 0) {
-          pi = rnd;
-          qi = 31;
-        } else {
-          pi = (rnd + tid) % 31;
-          qi = (rnd - tid + 31) % 31;
-        }
-        if (pi > qi) {
-          const int t = pi;
-          pi = qi;
-          qi = t;
-        }
-        const double apq = sm.A[pi][qi];
-        double cth = 1.0, sth = 0.0;
-        // rotate unless a_pq is negligible against sqrt(a_pp a_qq) (relative criterion for PSD
-        // matrices) or against the absolute floor 1e-20 max|a_ii|
-        const double thr = fmax(rot_tol, 4.0e-15 * sqrt(fabs(sm.A[pi][pi] * sm.A[qi][qi])));
-        if (fabs(apq) > thr && qi < 31) {
-          const double tau = (sm.A[qi][qi] - sm.A[pi][pi]) / (2.0 * apq);
-          const double t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
-          cth = 1.0 / sqrt(1.0 + t * t);
-          sth = t * cth;
-          sm.rotated = 1;
-        }
-        sm.pp[tid] = pi;
-        sm.qq[tid] = qi;
-        sm.cs[tid][0] = cth;
-        sm.cs[tid][1] = sth;
-      }
-      __syncthreads();
-      // rows: A <- J^T A
-      for (int idx = tid; idx < 16 * 32; idx += NT1) {
-        const int k = idx >> 5, j = idx & 31;
-        const int pi = sm.pp[k], qi = sm.qq[k];
-        const double cth = sm.cs[k][0], sth = sm.cs[k][1];
-        const double ap = sm.A[pi][j], aq = sm.A[qi][j];
-        sm.A[pi][j] = cth * ap - sth * aq;
-        sm.A[qi][j] = sth * ap + cth * aq;
-      }
-      __syncthreads();
-      // columns: A <- A J, V <- V J
-      for (int idx = tid; idx < 16 * 32; idx += NT1) {
-        const int k = idx >> 5, i = idx & 31;
-        const int pi = sm.pp[k], qi = sm.qq[k];
-        const double cth = sm.cs[k][0], sth = sm.cs[k][1];
-        const double ap = sm.A[i][pi], aq = sm.A[i][qi];
-        sm.A[i][pi] = cth * ap - sth * aq;
-        sm.A[i][qi] = sth * ap + cth * aq;
-        const double vp = sm.V[i][pi], vq = sm.V[i][qi];
-        sm.V[i][pi] = cth * vp - sth * vq;
-        sm.V[i][qi] = sth * vp + cth * vq;
-      }
-      __syncthreads();
-    }
-    converged = (sm.rotated == 0);
-    __syncthreads();
-  }
-  if (!converged) {
-    // rotations at the rounding floor can keep a sweep "busy"; the solve has failed only if a
-    // significant off-diagonal element survives
-    double offmax = 0.0;
-    for (int a = 0; a < 31; ++a)
-      for (int c2 = a + 1; c2 < 31; ++c2) offmax = fmax(offmax, fabs(sm.A[a][c2]));
-    converged = offmax <= 1e-13 * amax;
-  }
-
-  // ---- matrix_sqrt clip (math.py:133-136): keep w > 1e-15, compact kept modes to the front
-  if (tid == 0) {
-    int rk = 0;
-    for (int e = 0; e < 31; ++e)
-      if (sm.A[e][e] > 1e-15) sm.order[rk++] = e;
-    sm.rk = rk;
-  }
-  __syncthreads();
-  const int rk = sm.rk;
-  for (int idx = tid; idx < 32 * 32; idx += NT1) {
-    const int a = idx >> 5, e = idx & 31;
-    double v = 0.0;
-    if (e < rk && a < 31) {
-      const int src = sm.order[e];
-      v = sm.V[a][src] * sqrt(sm.A[src][src]);
-    }
-    sm.Xs[a][e] = v;
-  }
-  __syncthreads();
-
-  // ---- sqrtC_lat row (integrals.py:133-138 with eigE = q_size column, T = R_lat U)
+  K1PROF(4);
+  // S goes to the eigen-solve kernel
+  for (int idx = tid; idx < 32 * 32; idx += NT1) p.Sred[(size_t)b * 1024 + idx] = sm.A[idx >> 5][idx & 31];
+  if (tid < 16) p.qs[(size_t)b * 16 + tid] = sm.qs[tid];
   const double qsl = sm.qs[l1];
-  {
-    const double *H = tab + SPB_TAB_LAT_H + (size_t)tid * 32;
-    double out[32];
-#pragma unroll
-    for (int e = 0; e < 32; ++e) out[e] = 0.0;
-    for (int a = 0; a < 31; ++a) {
-      const double h = H[a];
-#pragma unroll
-      for (int e = 0; e < 32; ++e) out[e] = fma(h, sm.Xs[a][e], out[e]);
-    }
-    double *dst = p.S_lat + ((size_t)b * 256 + tid) * 32;
-#pragma unroll
-    for (int e = 0; e < 32; ++e) dst[e] = bad ? NAN : qsl * out[e];
-  }
 
   // ---- first moments (integrals.py:126-131): latitude then longitude
   {
@@ -338,12 +347,240 @@ __global__ void __launch_bounds__(NT1, 2) moments_k1(K1Params p) {
   if (tid == 0) {
     const double pi = 3.14159265358979323846;
     p.scale[b] = (pi * cc) * (pi * cc) * nn;  // contrast.py:23-25
-    p.rkeep[b] = rk;
-    int flag = 0;
-    if (bad) flag |= SPB_INFO_BOUNDS;
-    if (!converged) flag |= SPB_INFO_EIG_NOCONV;
-    p.info[b] = flag;
+    p.info[b] = bad ? SPB_INFO_BOUNDS : 0;
   }
+  K1PROF(5);
+}
+
+
+
+__device__ __forceinline__ double jrcp(double x) {
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  double e = fma(-x, y, 1.0);
+  y = fma(y, e, y);
+  e = fma(-x, y, 1.0);
+  return fma(y, e, y);
+}
+__device__ __forceinline__ double jrsqrt(double x) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  double e = fma(-x * y, y, 1.0);
+  y = fma(0.5 * y, e, y);
+  e = fma(-x * y, y, 1.0);
+  return fma(0.5 * y, e, y);
+}
+
+// ---- K1b: one warp per sample.  Same round-robin ordering, thresholds and clipping as the
+// CTA-wide version it replaces; the 16 disjoint rotations of
+// a round are computed by lanes 0-15, the row phase runs one column per lane and the column phase
+// one row per lane (both conflict-free with the 33-double stride), with __syncwarp in between.
+__global__ void __launch_bounds__(32 * K1B_WARPS) moments_k1b(K1Params p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.x * K1B_WARPS + warp;
+  if (b >= p.B) return;
+  K1bWarp &sm = reinterpret_cast<K1bWarp *>(smem_raw)[warp];
+  double *Sg = p.Sred + (size_t)b * 1024;
+  for (int a = 0; a < 32; ++a) {
+    sm.A[a][lane] = Sg[a * 32 + lane];
+    sm.V[a][lane] = (a == lane) ? 1.0 : 0.0;
+  }
+  __syncwarp();
+#ifdef SPB_POTRF_PROF
+  unsigned long long _pt = clock64(), _acc[4] = {0, 0, 0, 0};
+#define K1BPROF(k) do { unsigned long long _n = clock64(); _acc[k] += _n - _pt; _pt = _n; } while (0)
+#else
+#define K1BPROF(k)
+#endif
+  double amax = 0.0;
+  for (int a = 0; a < 31; ++a) amax = fmax(amax, fabs(sm.A[a][a]));
+  const double rot_tol = 1e-20 * amax;
+  bool converged = false;
+  for (int sweep = 0; sweep < 16 && !converged; ++sweep) {
+    if (lane == 0) sm.rotated = 0;
+    __syncwarp();
+    for (int rnd = 0; rnd < 31; ++rnd) {
+      K1BPROF(3);
+      if (lane < 16) {
+        int pi, qi;
+        if (lane == 0) {
+          pi = rnd;
+          qi = 31;
+        } else {
+          pi = (rnd + lane) % 31;
+          qi = (rnd - lane + 31) % 31;
+        }
+        if (pi > qi) {
+          const int t = pi;
+          pi = qi;
+          qi = t;
+        }
+        const double apq = sm.A[pi][qi];
+        const double app = sm.A[pi][pi], aqq = sm.A[qi][qi];
+        double cth = 1.0, sth = 0.0;
+        // rotate unless a_pq is negligible against sqrt(a_pp a_qq) (relative criterion for PSD
+        // matrices) or against the absolute floor 1e-20 max|a_ii| -- compared squared, no sqrt
+        const double thr2 = fmax(rot_tol * rot_tol, 1.6e-29 * fabs(app * aqq));
+        if (apq * apq > thr2 && qi < 31) {
+          // Jacobi rotation  t = sgn(tau) / (|tau| + sqrt(1 + tau^2)),  tau = (a_qq - a_pp) / (2 a_pq),
+          // written as t = sgn |o| / (|d| + sqrt(d^2 + o^2)) with d = a_qq - a_pp, o = 2 a_pq, and
+          // evaluated with MUFU-seeded reciprocal / reciprocal square root (two Newton steps each):
+          // the round's critical path is this chain, and IEEE division and square root cost ~15
+          // dependent FP64 instructions apiece where these cost five.
+          const double d = aqq - app, o = 2.0 * apq;
+          const double r2 = fma(d, d, o * o);
+          const double h = r2 * jrsqrt(r2);
+          const double sg = (((d >= 0.0) == (o >= 0.0)) || d == 0.0) ? 1.0 : -1.0;   // sgn(tau), tau = d / o
+          const double t = sg * fabs(o) * jrcp(fabs(d) + h);
+          cth = jrsqrt(fma(t, t, 1.0));
+          sth = t * cth;
+          sm.rotated = 1;
+        }
+        sm.pp[lane] = pi;
+        sm.qq[lane] = qi;
+        sm.cs[lane][0] = cth;
+        sm.cs[lane][1] = sth;
+      }
+      __syncwarp();
+      K1BPROF(0);
+      // The 16 rotations of a round touch disjoint row (column) pairs, so all operands are loaded
+      // first and all results stored last: the compiler cannot prove the shared-memory accesses of
+      // different rotations independent, and would otherwise serialise load -> FP64 -> store 16x.
+      // rows: A <- J^T A   (lane = column)
+      {
+        double ap[16], aq[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+          ap[k] = sm.A[sm.pp[k]][lane];
+          aq[k] = sm.A[sm.qq[k]][lane];
+        }
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+          const double cth = sm.cs[k][0], sth = sm.cs[k][1];
+          const double np_ = cth * ap[k] - sth * aq[k];
+          const double nq_ = sth * ap[k] + cth * aq[k];
+          ap[k] = np_;
+          aq[k] = nq_;
+        }
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+          sm.A[sm.pp[k]][lane] = ap[k];
+          sm.A[sm.qq[k]][lane] = aq[k];
+        }
+      }
+      __syncwarp();
+      K1BPROF(1);
+      // columns: A <- A J, V <- V J   (lane = row)
+      {
+        double ap[16], aq[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+          ap[k] = sm.A[lane][sm.pp[k]];
+          aq[k] = sm.A[lane][sm.qq[k]];
+        }
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+          const double cth = sm.cs[k][0], sth = sm.cs[k][1];
+          const double np_ = cth * ap[k] - sth * aq[k];
+          const double nq_ = sth * ap[k] + cth * aq[k];
+          ap[k] = np_;
+          aq[k] = nq_;
+        }
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+          sm.A[lane][sm.pp[k]] = ap[k];
+          sm.A[lane][sm.qq[k]] = aq[k];
+        }
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+          ap[k] = sm.V[lane][sm.pp[k]];
+          aq[k] = sm.V[lane][sm.qq[k]];
+        }
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+          const double cth = sm.cs[k][0], sth = sm.cs[k][1];
+          const double np_ = cth * ap[k] - sth * aq[k];
+          const double nq_ = sth * ap[k] + cth * aq[k];
+          ap[k] = np_;
+          aq[k] = nq_;
+        }
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+          sm.V[lane][sm.pp[k]] = ap[k];
+          sm.V[lane][sm.qq[k]] = aq[k];
+        }
+      }
+      __syncwarp();
+      K1BPROF(2);
+#ifdef SPB_POTRF_PROF
+      if (lane == 0) atomicAdd(&g_k1b_prof[6], 1ull);
+#endif
+    }
+    converged = (sm.rotated == 0);
+    __syncwarp();
+  }
+  if (!converged) {
+    // rotations at the rounding floor can keep a sweep "busy"; the solve has failed only if a
+    // significant off-diagonal element survives
+    double offmax = 0.0;
+    for (int a = 0; a < 31; ++a)
+      for (int c2 = a + 1; c2 < 31; ++c2) offmax = fmax(offmax, fabs(sm.A[a][c2]));
+    converged = offmax <= 1e-13 * amax;
+  }
+  // ---- matrix_sqrt clip (math.py:133-136): keep w > 1e-15, compact kept modes to the front
+  if (lane == 0) {
+    int rk = 0;
+    for (int e = 0; e < 31; ++e)
+      if (sm.A[e][e] > 1e-15) sm.order[rk++] = e;
+    sm.rk = rk;
+  }
+  __syncwarp();
+  const int rk = sm.rk;
+  for (int a = 0; a < 32; ++a) {   // lane = kept mode e
+    double v = 0.0;
+    if (lane < rk && a < 31) {
+      const int src = sm.order[lane];
+      v = sm.V[a][src] * sqrt(sm.A[src][src]);
+    }
+    Sg[a * 32 + lane] = v;
+  }
+#ifdef SPB_POTRF_PROF
+  if (lane == 0) {
+    atomicAdd(&g_k1b_prof[0], _acc[0]);
+    atomicAdd(&g_k1b_prof[1], _acc[1]);
+    atomicAdd(&g_k1b_prof[2], _acc[2]);
+    atomicAdd(&g_k1b_prof[3], _acc[3]);
+  }
+#endif
+  if (lane == 0) {
+    p.rkeep[b] = rk;
+    if (!converged) atomicOr(&p.info[b], SPB_INFO_EIG_NOCONV);
+  }
+}
+
+// ---- K1c: sqrtC_lat row (integrals.py:133-138 with eigE = q_size column, T = R_lat U)
+__global__ void __launch_bounds__(NT1) moments_k1c(K1Params p) {
+  __shared__ double Xs[32][JS];
+  const int tid = threadIdx.x, b = blockIdx.x;
+  for (int idx = tid; idx < 1024; idx += NT1) Xs[idx >> 5][idx & 31] = p.Sred[(size_t)b * 1024 + idx];
+  __syncthreads();
+  int l1, m1;
+  lm_of(tid, l1, m1);
+  const double qsl = p.qs[(size_t)b * 16 + l1];
+  const bool bad = (p.info[b] & SPB_INFO_BOUNDS) != 0;
+  const double *H = p.tab + SPB_TAB_LAT_H + (size_t)tid * 32;
+  double out[32];
+#pragma unroll
+  for (int e = 0; e < 32; ++e) out[e] = 0.0;
+  for (int a = 0; a < 31; ++a) {
+    const double h = H[a];
+#pragma unroll
+    for (int e = 0; e < 32; ++e) out[e] = fma(h, Xs[a][e], out[e]);
+  }
+  double *dst = p.S_lat + ((size_t)b * 256 + tid) * 32;
+#pragma unroll
+  for (int e = 0; e < 32; ++e) dst[e] = bad ? NAN : qsl * out[e];
 }
 
 // ------------------------------------------------------------------------------------------
@@ -454,7 +691,7 @@ int k2_upload_items(int *nitems_out) {
 constexpr int MOM_CHUNK = 1024;  // samples per pass (bounds the sqrtC_lon workspace to 2 GB)
 
 struct MomWs {
-  double *mom1, *S_lat, *scale, *X;
+  double *mom1, *S_lat, *scale, *X, *Sred, *qs;
   int *rkeep;
 };
 
@@ -471,7 +708,11 @@ size_t mom_ws_layout(int B, unsigned char *base, MomWs *ws) {
   size_t o_scale = take((size_t)B * 8);
   size_t o_rk = take((size_t)B * 4);
   size_t o_X = take((size_t)Bc * 256 * 992 * 8);
+  size_t o_Sred = take((size_t)B * 1024 * 8);
+  size_t o_qs = take((size_t)B * 16 * 8);
   if (ws) {
+    ws->Sred = reinterpret_cast<double *>(base + o_Sred);
+    ws->qs = reinterpret_cast<double *>(base + o_qs);
     ws->mom1 = reinterpret_cast<double *>(base + o_mom1);
     ws->S_lat = reinterpret_cast<double *>(base + o_S);
     ws->scale = reinterpret_cast<double *>(base + o_scale);
@@ -565,12 +806,15 @@ extern "C" int spb_ylm_moments(spb_context *ctx, int B, const double *r_deg, con
 
   static bool attr1 = false;
   if (!attr1) {
-    SPB_CHECK_CUDA(cudaFuncSetAttribute(moments_k1, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    SPB_CHECK_CUDA(cudaFuncSetAttribute(moments_k1a, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)sizeof(K1Smem)));
+    SPB_CHECK_CUDA(cudaFuncSetAttribute(moments_k1b, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)(K1B_WARPS * sizeof(K1bWarp))));
     SPB_CHECK_CUDA(cudaFuncSetAttribute(moments_k2, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)((K2_NRP * 31 + 2 * 31 * 32) * sizeof(double))));
     attr1 = true;
   }
+  SPB_REQUIRE(k1_upload_perm() == 0, "ylm_moments: constant upload failed");
   K1Params p1;
   p1.r_deg = r_deg;
   p1.a = a;
@@ -585,7 +829,13 @@ extern "C" int spb_ylm_moments(spb_context *ctx, int B, const double *r_deg, con
   p1.scale = ws.scale;
   p1.rkeep = ws.rkeep;
   p1.info = info;
-  moments_k1<<<B, NT1, sizeof(K1Smem), stream>>>(p1);
+  p1.Sred = ws.Sred;
+  p1.qs = ws.qs;
+  moments_k1a<<<B, NT1, sizeof(K1Smem), stream>>>(p1);
+  SPB_LAUNCH_CHECK(ctx);
+  moments_k1b<<<(B + K1B_WARPS - 1) / K1B_WARPS, 32 * K1B_WARPS, K1B_WARPS * sizeof(K1bWarp), stream>>>(p1);
+  SPB_LAUNCH_CHECK(ctx);
+  moments_k1c<<<B, NT1, 0, stream>>>(p1);
   SPB_LAUNCH_CHECK(ctx);
 
   int nitems = 0;
@@ -630,3 +880,15 @@ extern "C" int spb_ylm_moments(spb_context *ctx, int B, const double *r_deg, con
   }
   return 0;
 }
+
+#ifdef SPB_POTRF_PROF
+extern "C" int spb_k1a_prof(unsigned long long *out_host) {
+  if (cudaDeviceSynchronize() != cudaSuccess) return 1;
+  if (cudaMemcpyFromSymbol(out_host, g_k1a_prof, sizeof(unsigned long long) * 8) != cudaSuccess) return 1;
+  if (cudaMemcpyFromSymbol(out_host + 8, g_k1b_prof, sizeof(unsigned long long) * 8) != cudaSuccess) return 1;
+  unsigned long long z[8] = {0};
+  if (cudaMemcpyToSymbol(g_k1a_prof, z, sizeof(z)) != cudaSuccess) return 1;
+  if (cudaMemcpyToSymbol(g_k1b_prof, z, sizeof(z)) != cudaSuccess) return 1;
+  return 0;
+}
+#endif
