@@ -67,8 +67,6 @@ constexpr int K1B_WARPS = 4;   // samples per CTA of the eigen-solve kernel
 struct K1bWarp {
   double A[32][JS];       // Jacobi iterate
   double V[32][JS];       // eigenvectors
-  double cs[16][2];
-  int pp[16], qq[16];
   int order[32];
   int rotated;
   int rk;
@@ -402,6 +400,7 @@ __global__ void __launch_bounds__(32 * K1B_WARPS) moments_k1b(K1Params p) {
     __syncwarp();
     for (int rnd = 0; rnd < 31; ++rnd) {
       K1BPROF(3);
+      double cth_l = 1.0, sth_l = 0.0;
       if (lane < 16) {
         int pi, qi;
         if (lane == 0) {
@@ -418,7 +417,6 @@ __global__ void __launch_bounds__(32 * K1B_WARPS) moments_k1b(K1Params p) {
         }
         const double apq = sm.A[pi][qi];
         const double app = sm.A[pi][pi], aqq = sm.A[qi][qi];
-        double cth = 1.0, sth = 0.0;
         // rotate unless a_pq is negligible against sqrt(a_pp a_qq) (relative criterion for PSD
         // matrices) or against the absolute floor 1e-20 max|a_ii| -- compared squared, no sqrt
         const double thr2 = fmax(rot_tol * rot_tol, 1.6e-29 * fabs(app * aqq));
@@ -433,16 +431,33 @@ __global__ void __launch_bounds__(32 * K1B_WARPS) moments_k1b(K1Params p) {
           const double h = r2 * jrsqrt(r2);
           const double sg = (((d >= 0.0) == (o >= 0.0)) || d == 0.0) ? 1.0 : -1.0;   // sgn(tau), tau = d / o
           const double t = sg * fabs(o) * jrcp(fabs(d) + h);
-          cth = jrsqrt(fma(t, t, 1.0));
-          sth = t * cth;
+          cth_l = jrsqrt(fma(t, t, 1.0));
+          sth_l = t * cth_l;
           sm.rotated = 1;
         }
-        sm.pp[lane] = pi;
-        sm.qq[lane] = qi;
-        sm.cs[lane][0] = cth;
-        sm.cs[lane][1] = sth;
       }
-      __syncwarp();
+      // pair indices are lane-invariant functions of (rnd, k); (c, s) come from lane k by shuffle:
+      // no shared-memory broadcast loads in the update phases (they were half of the LSU traffic
+      // that bounds this kernel)
+      int P[16], Q[16];
+      double C[16], S[16];
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        int pk, qk;
+        if (k == 0) {
+          pk = rnd;
+          qk = 31;
+        } else {
+          pk = rnd + k;
+          pk -= (pk >= 31) ? 31 : 0;
+          qk = rnd - k + 31;
+          qk -= (qk >= 31) ? 31 : 0;
+        }
+        P[k] = min(pk, qk);
+        Q[k] = max(pk, qk);
+        C[k] = __shfl_sync(0xffffffffu, cth_l, k);
+        S[k] = __shfl_sync(0xffffffffu, sth_l, k);
+      }
       K1BPROF(0);
       // The 16 rotations of a round touch disjoint row (column) pairs, so all operands are loaded
       // first and all results stored last: the compiler cannot prove the shared-memory accesses of
@@ -452,12 +467,12 @@ __global__ void __launch_bounds__(32 * K1B_WARPS) moments_k1b(K1Params p) {
         double ap[16], aq[16];
 #pragma unroll
         for (int k = 0; k < 16; ++k) {
-          ap[k] = sm.A[sm.pp[k]][lane];
-          aq[k] = sm.A[sm.qq[k]][lane];
+          ap[k] = sm.A[P[k]][lane];
+          aq[k] = sm.A[Q[k]][lane];
         }
 #pragma unroll
         for (int k = 0; k < 16; ++k) {
-          const double cth = sm.cs[k][0], sth = sm.cs[k][1];
+          const double cth = C[k], sth = S[k];
           const double np_ = cth * ap[k] - sth * aq[k];
           const double nq_ = sth * ap[k] + cth * aq[k];
           ap[k] = np_;
@@ -465,8 +480,8 @@ __global__ void __launch_bounds__(32 * K1B_WARPS) moments_k1b(K1Params p) {
         }
 #pragma unroll
         for (int k = 0; k < 16; ++k) {
-          sm.A[sm.pp[k]][lane] = ap[k];
-          sm.A[sm.qq[k]][lane] = aq[k];
+          sm.A[P[k]][lane] = ap[k];
+          sm.A[Q[k]][lane] = aq[k];
         }
       }
       __syncwarp();
@@ -476,12 +491,12 @@ __global__ void __launch_bounds__(32 * K1B_WARPS) moments_k1b(K1Params p) {
         double ap[16], aq[16];
 #pragma unroll
         for (int k = 0; k < 16; ++k) {
-          ap[k] = sm.A[lane][sm.pp[k]];
-          aq[k] = sm.A[lane][sm.qq[k]];
+          ap[k] = sm.A[lane][P[k]];
+          aq[k] = sm.A[lane][Q[k]];
         }
 #pragma unroll
         for (int k = 0; k < 16; ++k) {
-          const double cth = sm.cs[k][0], sth = sm.cs[k][1];
+          const double cth = C[k], sth = S[k];
           const double np_ = cth * ap[k] - sth * aq[k];
           const double nq_ = sth * ap[k] + cth * aq[k];
           ap[k] = np_;
@@ -489,17 +504,17 @@ __global__ void __launch_bounds__(32 * K1B_WARPS) moments_k1b(K1Params p) {
         }
 #pragma unroll
         for (int k = 0; k < 16; ++k) {
-          sm.A[lane][sm.pp[k]] = ap[k];
-          sm.A[lane][sm.qq[k]] = aq[k];
+          sm.A[lane][P[k]] = ap[k];
+          sm.A[lane][Q[k]] = aq[k];
         }
 #pragma unroll
         for (int k = 0; k < 16; ++k) {
-          ap[k] = sm.V[lane][sm.pp[k]];
-          aq[k] = sm.V[lane][sm.qq[k]];
+          ap[k] = sm.V[lane][P[k]];
+          aq[k] = sm.V[lane][Q[k]];
         }
 #pragma unroll
         for (int k = 0; k < 16; ++k) {
-          const double cth = sm.cs[k][0], sth = sm.cs[k][1];
+          const double cth = C[k], sth = S[k];
           const double np_ = cth * ap[k] - sth * aq[k];
           const double nq_ = sth * ap[k] + cth * aq[k];
           ap[k] = np_;
@@ -507,8 +522,8 @@ __global__ void __launch_bounds__(32 * K1B_WARPS) moments_k1b(K1Params p) {
         }
 #pragma unroll
         for (int k = 0; k < 16; ++k) {
-          sm.V[lane][sm.pp[k]] = ap[k];
-          sm.V[lane][sm.qq[k]] = aq[k];
+          sm.V[lane][P[k]] = ap[k];
+          sm.V[lane][Q[k]] = aq[k];
         }
       }
       __syncwarp();
