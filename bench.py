@@ -424,7 +424,7 @@ def run_b200(args):
         "traffic": ncu_traffic("potrf_lnlike_kernel", flops_total / n_launch / (NT ** 3 / 3.0 + NT ** 2)
                                if args.workload == "sweep" else 1.0),
         "traffic_note": "DRAM read+write bytes per launch: per-matrix figure of the ncu capture "
-                        "profiles/r01_ncu_sweep_B592_final.txt (profiles/ncu_traffic.json) x matrices in the launch",
+                        "profiles/r01_ncu_sweep_B592_final2.txt (profiles/ncu_traffic.json) x matrices in the launch",
         "peak_source": "FP64 mma.sync peak measured in this run by spb_dmma_peak "
                        "(MEASURED_PEAKS.json has no fp64 entry; cuBLAS DGEMM 8192^3 on this pool: "
                        "35.5 TFLOP/s)",
