@@ -161,3 +161,41 @@ def test_gpu_predict_batched_and_errors(spb, golden):
         spb.StarryProcess(normalized=True, **FID).predict(g["t"], g["flux"], 1e-6)
     with pytest.raises(NotImplementedError):
         spb.StarryProcess(normalized=True, **FID).sample_ylm_conditional(g["t"], g["flux"], 1e-6)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("marg", [False, True])
+def test_gpu_predict_odd_sizes_vs_live_oracle(spb, oracle, golden, marg):
+    """Odd nt / nts (padded leading dimensions), vector data_cov, default t_sample, against the
+    oracle evaluated LIVE on this host.  The marginalised branch of the reference algorithm is
+    only reproducible to ~3e-6 between CPUs (LAPACK kernel selection moves its noise-level
+    eigenmodes; DESIGN.md "numerical fragility" -- the pinned 1e-8 check is the golden-fixture
+    test above), hence the looser bound there."""
+    g = golden("predict_nt200.npz")
+    nt, nts = 151, 77
+    t, f = g["t"][:nt], g["flux"][:nt]
+    ts = np.linspace(0.05, 0.7, nts)
+    dv = g["data_cov_vec"][:nt]
+    gp = spb.StarryProcess(marginalize_over_inclination=marg, normalized=False, **FID)
+    o = oracle.OracleProcess(marginalize_over_inclination=marg, normalized=False, **FID)
+    mu, K = gp.predict(t, f, dv, t_sample=ts, baseline_var=2e-6, **KW)
+    mo, Ko = o.predict(t, f, dv, t_sample=ts, baseline_var=2e-6, **KW)
+    scale = float(np.abs(o.cov(t, **KW)).max())
+    tol = 5e-6 if marg else 1e-7
+    assert tuple(mu.shape) == (nts,) and tuple(K.shape) == (nts, nts)
+    assert np.abs(mu.cpu().numpy() - mo).max() <= tol * np.abs(mo).max()
+    assert np.abs(K.cpu().numpy() - Ko).max() <= tol * scale
+    mu2, K2 = gp.predict(t, f, dv, **KW)          # t_sample = t
+    mo2, Ko2 = o.predict(t, f, dv, **KW)
+    assert np.abs(mu2.cpu().numpy() - mo2).max() <= tol * np.abs(mo2).max()
+    assert np.abs(K2.cpu().numpy() - Ko2).max() <= tol * scale
+    # draws: finite, right shape, reproducible for a fixed generator
+    import torch
+
+    s1 = gp.sample_conditional(t, f, dv, t_sample=ts, nsamples=4,
+                               generator=torch.Generator(device="cuda").manual_seed(1), **KW)
+    s2 = gp.sample_conditional(t, f, dv, t_sample=ts, nsamples=4,
+                               generator=torch.Generator(device="cuda").manual_seed(1), **KW)
+    assert tuple(s1.shape) == (4, nts) and bool(torch.isfinite(s1).all()) and torch.equal(s1, s2)
+    s3 = gp.sample(t, nsamples=2, generator=torch.Generator(device="cuda").manual_seed(2), **KW)
+    assert tuple(s3.shape) == (2, nt) and bool(torch.isfinite(s3).all())
