@@ -281,6 +281,47 @@ def design_phase(spb, _lib, ctx, dev, torch, I=64, nt=100000, reps=5):
             "traffic": ncu_traffic("design_rows_kernel", float(I) * nt)}
 
 
+def sample_ylm_phase(spb, _lib, ctx, dev, torch, dmma_peak, nsamples=1000000, reps=5):
+    """configs[4], second half: prior draws y = mean + L u (sp.py:505-509) for 1e6 samples.  One NT
+    GEMM on the FP64 tensor pipe; per draw 2 * 256^2 flop against 2048 B read (u) + 2048 B written
+    (y), i.e. 32 flop/B: on B200 (37 TFLOP/s FP64 tensor vs 6.5 TB/s) it sits on the tensor side
+    of the ridge (5.7 flop/B), so both fractions are reported."""
+    lib, h = ctx.lib, ctx.handle
+    P = lambda x: ctypes.c_void_p(x.data_ptr())  # noqa: E731
+    gp = spb.StarryProcess(r=10.0, mu=30.0, sigma=5.0, c=0.1, n=10.0)
+    L = gp.cho_cov_ylm.reshape(1, 256, 256).contiguous()
+    mean = gp.mean_ylm.reshape(1, 256).contiguous()
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(6)
+    un = torch.randn(1, nsamples, 256, dtype=torch.float64, device=dev, generator=gen)  # 2 GB >> L2
+    y = torch.empty(1, nsamples, 256, dtype=torch.float64, device=dev)
+    stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    times = []
+    for r in range(reps + 3):
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _lib.check(lib.spb_sample_ylm(h, 1, nsamples, P(mean), P(L), P(un), P(y), stream))
+        e1.record()
+        torch.cuda.synchronize()
+        if r >= 3:
+            times.append(e0.elapsed_time(e1))
+    ms = float(np.mean(times))
+    flops = 2.0 * 256 * 256 * nsamples
+    alg_bytes = nsamples * 4096.0
+    peak_bw, src = hbm_peak()
+    out = {"bound": "tensor", "kernel": "gnt::gemm_nt_kernel<EPI_ADD_ROWVEC> (DMMA)",
+           "workload": "configs[4]: sample_ylm, 1e6 prior draws of the 256 Ylm coefficients",
+           "achieved": flops / (ms * 1e-3) / 1e12, "peak": dmma_peak, "unit": "TFLOP/s",
+           "frac": flops / (ms * 1e-3) / 1e12 / dmma_peak, "ms_per_launch": ms,
+           "draws_per_s": nsamples / (ms * 1e-3), "algorithmic_flops_per_launch": flops,
+           "hbm": {"achieved": alg_bytes / (ms * 1e-3) / 1e9, "peak": peak_bw, "unit": "GB/s",
+                   "frac": alg_bytes / (ms * 1e-3) / 1e9 / peak_bw, "peak_source": src,
+                   "algorithmic_bytes_per_launch": alg_bytes}}
+    del un, y
+    return out
+
+
 # ------------------------------------------------------------------------------------------
 def run_b200(args):
     import torch
@@ -434,7 +475,8 @@ def run_b200(args):
     }
     # ---- design-matrix phase (BASELINE configs[4]: nt = 1e5 timestamps x 64 inclinations), timed in
     # the same process with CUDA events on the launching stream, against the measured HBM peak
-    phases = {"design_matrix": design_phase(spb, _lib, ctx, dev, torch)}
+    phases = {"design_matrix": design_phase(spb, _lib, ctx, dev, torch),
+              "sample_ylm": sample_ylm_phase(spb, _lib, ctx, dev, torch, dmma_peak)}
     # ---- CPU baseline: bounded sample of the same workload on the host cores
     cb_value, cb_kind, cb_out = cpu_evals(hp, t, flux, args.cpu_evals, args.workload, fens)
     parity = None

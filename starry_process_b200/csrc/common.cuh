@@ -10,6 +10,7 @@
 
 #define SPB_LMAX 15
 #define SPB_NUM_COUNTERS 256
+#define SPB_SCRATCH_PER_SLOT 256  // doubles per launch slot (cluster Cholesky: 8 per matrix)
 #define SPB_NSM_DEFAULT 148
 
 struct spb_context {
@@ -22,6 +23,7 @@ struct spb_context {
   // zeroed in-stream before the launch, so that concurrent streams never share one)
   unsigned int *d_counters;
   unsigned int counter_next;
+  double *d_scratch;      // SPB_NUM_COUNTERS x SPB_SCRATCH_PER_SLOT doubles, same ring
   // offsets (in doubles) into d_tables, see spb_tables.h
   const double *tab(size_t off) const { return d_tables + off; }
 };

@@ -33,6 +33,9 @@ extern "C" int spb_create(int device, const double *tables_host, size_t tables_c
   ctx->counter_next = 0;
   SPB_CHECK_CUDA(cudaMalloc(&ctx->d_counters, SPB_NUM_COUNTERS * sizeof(unsigned int)));
   SPB_CHECK_CUDA(cudaMemset(ctx->d_counters, 0, SPB_NUM_COUNTERS * sizeof(unsigned int)));
+  ctx->d_scratch = nullptr;
+  SPB_CHECK_CUDA(cudaMalloc(&ctx->d_scratch,
+                            (size_t)SPB_NUM_COUNTERS * SPB_SCRATCH_PER_SLOT * sizeof(double)));
   if (tables_count > 0) {
     SPB_REQUIRE(tables_host != nullptr, "spb_create: null table blob");
     SPB_CHECK_CUDA(cudaMalloc(&ctx->d_tables, tables_count * sizeof(double)));
@@ -52,6 +55,7 @@ extern "C" void spb_destroy(spb_context *ctx) {
   cudaSetDevice(ctx->device);
   if (ctx->d_tables) cudaFree(ctx->d_tables);
   if (ctx->d_counters) cudaFree(ctx->d_counters);
+  if (ctx->d_scratch) cudaFree(ctx->d_scratch);
   delete ctx;
 }
 

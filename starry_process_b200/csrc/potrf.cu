@@ -26,6 +26,8 @@
 //     column, column scaling deferred).
 //
 // Algorithmic flops per matrix: nt^3/3 (factor) + nt^2 M (forward solve); see DESIGN.md.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace {
@@ -54,6 +56,7 @@ struct PotrfParams {
   int mode;
   int rows_per_cta;  // MODE_SOLVE: RHS rows per work item
   unsigned int *counter;  // zeroed before the launch: work items beyond the first wave are claimed here
+  double *scratch;        // cluster kernel: (B, CLUSTER) per-CTA partial sums of |y|^2
   spb_affine aff;    // fused last assembly step (scal == q == diag == offset == NULL: none)
   int aff_on;
 };
@@ -847,6 +850,169 @@ __global__ void __launch_bounds__(NTHREADS, 2) potrf_lnlike_kernel(PotrfParams p
 }
 
 // ------------------------------------------------------------------------------------------
+// Small batches (B <= #SM / 8): ONE MATRIX PER THREAD-BLOCK CLUSTER of 8 CTAs (8 SMs).
+//
+// A lone CTA needs 2.3 ms for a 1000 x 1000 matrix (one SM's tensor pipe, every serial phase
+// exposed), which is the whole latency of a single log-likelihood evaluation -- the regime of a
+// single MCMC chain, of predict() and of the conditional samplers.  Here the 128-row tiles of a
+// panel are dealt round-robin to the CTAs of a cluster: all k-loops of a panel run concurrently on
+// different SMs, CTA 0 owns the diagonal tile (k-loop, in-register factorisation, L_jj written to
+// global memory), and two cluster barriers per panel (release / acquire: they order the global
+// writes) separate  "L_jj published"  and  "panel complete".  The other CTAs fetch L_jj through L2
+// (ld.global.cg), invert its 8x8 diagonal tiles locally and run the same in-register TRSM.  Same
+// device functions, same arithmetic per tile as the batch kernel: results are bit-identical to it.
+// ------------------------------------------------------------------------------------------
+constexpr int CLUSTER = 8;
+
+__device__ __forceinline__ unsigned cluster_rank() {
+  unsigned r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_barrier() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n"
+               "barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1) potrf_cluster_kernel(PotrfParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, tg = lane & 3;
+  const int rank = (int)cluster_rank();
+  const int item = blockIdx.x / CLUSTER;
+
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&sm.full[s], NTHREADS);
+      mbar_init(&sm.empty[s], NTHREADS / 32);
+    }
+    sm.bad = 0;
+  }
+  unsigned it = 0;
+
+  RowMap rm;
+  rm.n = p.n;
+  rm.ld = p.ld;
+  rm.ldr = p.ldr;
+  rm.mode = MODE_FACTOR;
+  rm.Kb = p.K + (size_t)item * p.strideK;
+  rm.Rb = p.R ? p.R + (size_t)item * p.strideR : nullptr;
+  rm.M = p.R ? p.M : 0;
+  rm.rb = 0;
+  rm.nrhs = rm.M;
+  double *quad_out = p.quad ? p.quad + (size_t)item * p.M : nullptr;
+  AffRow af;
+  af.q = nullptr;
+  af.dg = nullptr;
+  af.dg_vec = 0;
+  af.norm = false;
+  if (p.aff_on) {
+    af.norm = (p.aff.scal != nullptr) && (p.aff.q != nullptr);
+    if (af.norm) af.q = p.aff.q + (size_t)item * p.n;
+    if (p.aff.diag) {
+      af.dg = p.aff.diag + (size_t)item * p.aff.diag_stride;
+      af.dg_vec = (p.aff.diag_kind == 1);
+    }
+    if (tid == 0) {
+      sm.af[0] = af.norm ? p.aff.scal[4 * (size_t)item + 0] : 1.0;
+      sm.af[1] = af.norm ? p.aff.scal[4 * (size_t)item + 1] : 0.0;
+      sm.af[2] = af.norm ? p.aff.scal[4 * (size_t)item + 2] : 0.0;
+      sm.af[3] = p.aff.offset ? p.aff.offset[(size_t)item * p.aff.offset_stride] : 0.0;
+    }
+  }
+  // per-RHS accumulators are zeroed by CTA 0 before the first "L_jj published" barrier; every
+  // contribution is added after it
+  if (quad_out && rank == 0)
+    for (int m = tid; m < rm.M; m += NTHREADS) quad_out[m] = 0.0;
+  __syncthreads();
+
+  double logdet_part = 0.0, quad_part = 0.0;
+  double acc[2][8][2];
+
+  for (int c0 = 0; c0 < p.n; c0 += NB) {
+    rm.c0 = c0;
+    rm.nbelow = max(0, p.n - c0 - NB);
+    const int nvirt = NB + rm.nbelow + rm.M;
+    const int ntiles = (nvirt + TM - 1) / TM;
+    const bool full_panel = (c0 + NB <= p.n);
+    const bool have_tile = rank < ntiles;
+    // ---- first tile of this CTA: k-loop (needs nothing from this panel)
+    if (have_tile) {
+      const int v0 = rank * TM;
+      gemm_tile(sm, rm, v0, c0, nvirt, (rank == 0 && warp < 4) ? 2 * warp + 2 : 8, it, acc, [&]() {
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+          init_acc(sm, rm, af, p.aff_on != 0, v0 + warp * 16 + mt * 8 + g, c0, tg, full_panel, acc[mt]);
+      });
+    }
+    if (rank == 0) {
+      if (warp < 4) potf2_regs(sm, acc, warp, lane);
+      __syncthreads();
+      if (tid < min(NB, p.n - c0)) logdet_part += 0.5 * log(sm.dpiv[tid]);
+      for (int idx = tid; idx < NB * NB; idx += NTHREADS) {
+        const int i = idx >> 6, j = idx & 63;
+        if (j <= i && c0 + i < p.n) rm.Kb[(size_t)(c0 + i) * p.ld + c0 + j] = sm.Ld[i][j];
+      }
+      __threadfence();
+    }
+    cluster_barrier();   // L_jj published
+    if (rank != 0 && have_tile) {
+      for (int idx = tid; idx < NB * NB; idx += NTHREADS) {
+        const int i = idx >> 6, j = idx & 63;
+        double v = 0.0;
+        if (j <= i) {
+          if (c0 + i < p.n) v = __ldcg(rm.Kb + (size_t)(c0 + i) * p.ld + c0 + j);
+          else v = (i == j) ? 1.0 : 0.0;
+        }
+        sm.Ld[i][j] = v;
+      }
+      __syncthreads();
+      diag_inverses(sm);
+    }
+    // ---- finish the first tile, then any further tiles of this CTA
+    for (int ti = rank; ti < ntiles; ti += CLUSTER) {
+      const int v0 = ti * TM;
+      if (ti != rank) {
+        gemm_tile(sm, rm, v0, c0, nvirt, 8, it, acc, [&]() {
+#pragma unroll
+          for (int mt = 0; mt < 2; ++mt)
+            init_acc(sm, rm, af, p.aff_on != 0, v0 + warp * 16 + mt * 8 + g, c0, tg, full_panel, acc[mt]);
+        });
+      }
+      if (!(ti == 0 && warp < 4) && (v0 + warp * 16) < nvirt) {
+        trsm_warp(sm, acc, lane);
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+          store_rows(rm, v0 + warp * 16 + mt * 8 + g, c0, tg, acc[mt], quad_part, quad_out);
+      }
+    }
+    __threadfence();
+    cluster_barrier();   // panel complete: its columns are visible to every CTA of the cluster
+  }
+
+  const double quad = block_sum(sm, quad_part);
+  const double logdet = block_sum(sm, logdet_part);   // non-zero in CTA 0 only
+  // deterministic reduction: one partial per CTA, summed by CTA 0 in rank order
+  if (tid == 0) p.scratch[(size_t)item * CLUSTER + rank] = quad;
+  __threadfence();
+  cluster_barrier();
+  if (rank == 0 && tid == 0) {
+    double qtot = 0.0;
+#pragma unroll
+    for (int r = 0; r < CLUSTER; ++r) qtot += __ldcg(p.scratch + (size_t)item * CLUSTER + r);
+    const bool bad = sm.bad != 0;
+    double ll = -0.5 * qtot - (double)rm.M * logdet -
+                0.5 * (double)p.n * (double)rm.M * 1.8378770664093453;  // log(2 pi)
+    const int prev = p.info ? (p.info[item] & ~SPB_INFO_NOT_PD) : 0;
+    if (bad || (prev & (SPB_INFO_Z_RANGE | SPB_INFO_BOUNDS)) || ll != ll) ll = -INFINITY;
+    if (p.lnlike) p.lnlike[item] = ll;
+    if (p.logdet) p.logdet[item] = bad ? NAN : logdet;
+    if (p.info) p.info[item] = prev | (bad ? SPB_INFO_NOT_PD : 0);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // DMMA peak micro-benchmark: 8 warps x 16 independent accumulator tiles, operands in registers.
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256, 2) dmma_peak_kernel(int iters, double *sink) {
@@ -877,6 +1043,7 @@ static int potrf_launch(spb_context *ctx, PotrfParams &p, void *stream) {
                 "cholesky: resid must be 16-byte aligned with an even batch stride");
   }
   SPB_CHECK_CUDA(cudaSetDevice(ctx->device));
+  p.scratch = nullptr;
   const size_t smem = sizeof(Smem);
   static bool attr_set[64] = {false};
   if (!attr_set[ctx->device & 63]) {
@@ -885,6 +1052,36 @@ static int potrf_launch(spb_context *ctx, PotrfParams &p, void *stream) {
     attr_set[ctx->device & 63] = true;
   }
   int nitems = (p.mode == MODE_FACTOR) ? p.B : (p.M + p.rows_per_cta - 1) / p.rows_per_cta;
+  // few matrices: one 8-CTA cluster per matrix instead of one CTA (see potrf_cluster_kernel)
+  static const bool no_cluster = getenv("SPB_NO_CLUSTER") != nullptr;   // A/B switch for measurements
+  if (!no_cluster && p.mode == MODE_FACTOR && p.B * CLUSTER <= ctx->num_sms && p.n > 2 * TM &&
+      ctx->d_scratch) {
+    static bool cattr[64] = {false};
+    if (!cattr[ctx->device & 63]) {
+      SPB_CHECK_CUDA(cudaFuncSetAttribute(potrf_cluster_kernel,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      cattr[ctx->device & 63] = true;
+    }
+    const unsigned slot = __atomic_fetch_add(&ctx->counter_next, 1u, __ATOMIC_RELAXED) % SPB_NUM_COUNTERS;
+    p.scratch = ctx->d_scratch + (size_t)slot * SPB_SCRATCH_PER_SLOT;
+    SPB_REQUIRE(CLUSTER * p.B <= SPB_SCRATCH_PER_SLOT, "cholesky: cluster scratch too small");
+    p.counter = nullptr;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(p.B * CLUSTER));
+    cfg.blockDim = dim3(NTHREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CLUSTER;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    SPB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, potrf_cluster_kernel, p));
+    SPB_LAUNCH_CHECK(ctx);
+    return 0;
+  }
   int grid = nitems < 2 * ctx->num_sms ? nitems : 2 * ctx->num_sms;
   p.counter = ctx->d_counters +
       (__atomic_fetch_add(&ctx->counter_next, 1u, __ATOMIC_RELAXED) % SPB_NUM_COUNTERS);

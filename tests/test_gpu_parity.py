@@ -415,8 +415,10 @@ def test_bounds_and_flags(spb):
 
 def test_full_size_properties(spb, golden):
     """BASELINE sizes, size-independent properties: a batch of identical hyperparameters gives
-    identical lnlike in every slot; chunked and unchunked evaluation agree bit for bit; joint
-    lnlike of M curves == sum over curves + shared log-determinant bookkeeping."""
+    identical lnlike in every slot; chunked and unchunked evaluation agree bit for bit (same
+    kernel), and to rounding when the chunks are small enough to take the one-matrix-per-cluster
+    Cholesky (different summation order of |L^-1 r|^2); joint lnlike of M curves == sum over curves
+    + shared log-determinant bookkeeping."""
     g = golden("fiducial_nt1000.npz")
     t = g["t"]
     B = 296
@@ -426,9 +428,14 @@ def test_full_size_properties(spb, golden):
     assert float((ll - ll[0]).abs().max()) == 0.0
     assert rel(ll[0].item(), g["lnlike_m1_n1_uld"]) <= RTOL
     gp2 = spb.StarryProcess(r=np.full(B, 10.0), mu=np.full(B, 30.0), sigma=np.full(B, 5.0),
-                            c=np.full(B, 0.1), n=np.full(B, 10.0), max_chunk_bytes=100 << 20)
-    ll2 = gp2.log_likelihood(t, g["flux_norm"], 1e-6, u=U_LD)
+                            c=np.full(B, 0.1), n=np.full(B, 10.0), max_chunk_bytes=1 << 30)
+    ll2 = gp2.log_likelihood(t, g["flux_norm"], 1e-6, u=U_LD)     # chunks of ~120 matrices
     assert torch.equal(ll, ll2)
+    gp3 = spb.StarryProcess(r=np.full(B, 10.0), mu=np.full(B, 30.0), sigma=np.full(B, 5.0),
+                            c=np.full(B, 0.1), n=np.full(B, 10.0), max_chunk_bytes=100 << 20)
+    ll3 = gp3.log_likelihood(t, g["flux_norm"], 1e-6, u=U_LD)     # chunks of ~12: cluster kernel
+    assert float((ll3 - ll3[0]).abs().max()) == 0.0               # deterministic
+    assert float((ll3 - ll).abs().max()) <= 1e-13 * float(ll.abs().max())
     g1 = spb.StarryProcess(**FID)
     fe = g["flux_ens_norm"]
     joint = g1.log_likelihood(t, fe, 1e-6, u=U_LD).item()
