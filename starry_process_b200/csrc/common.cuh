@@ -10,7 +10,7 @@
 
 #define SPB_LMAX 15
 #define SPB_NUM_COUNTERS 256
-#define SPB_SCRATCH_PER_SLOT 256  // doubles per launch slot (cluster Cholesky: 8 per matrix)
+#define SPB_SCRATCH_PER_SLOT 256  // doubles per launch slot (cluster Cholesky: one per CTA)
 #define SPB_NSM_DEFAULT 148
 
 struct spb_context {

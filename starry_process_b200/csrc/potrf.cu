@@ -850,7 +850,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) potrf_lnlike_kernel(PotrfParams p
 }
 
 // ------------------------------------------------------------------------------------------
-// Small batches (B <= #SM / 8): ONE MATRIX PER THREAD-BLOCK CLUSTER of 8 CTAs (8 SMs).
+// Small batches (B <= #SM / 2): ONE MATRIX PER THREAD-BLOCK CLUSTER of 8, 4 or 2 CTAs (SMs).
 //
 // A lone CTA needs 2.3 ms for a 1000 x 1000 matrix (one SM's tensor pipe, every serial phase
 // exposed), which is the whole latency of a single log-likelihood evaluation -- the regime of a
@@ -862,7 +862,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) potrf_lnlike_kernel(PotrfParams p
 // (ld.global.cg), invert its 8x8 diagonal tiles locally and run the same in-register TRSM.  Same
 // device functions, same arithmetic per tile as the batch kernel: results are bit-identical to it.
 // ------------------------------------------------------------------------------------------
-constexpr int CLUSTER = 8;
+constexpr int CLUSTER_MAX = 8;   // portable cluster size; 4 and 2 serve mid-sized batches
 
 __device__ __forceinline__ unsigned cluster_rank() {
   unsigned r;
@@ -874,6 +874,7 @@ __device__ __forceinline__ void cluster_barrier() {
                "barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
 }
 
+template <int CLUSTER>
 __global__ void __launch_bounds__(NTHREADS, 1) potrf_cluster_kernel(PotrfParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
@@ -1054,31 +1055,66 @@ static int potrf_launch(spb_context *ctx, PotrfParams &p, void *stream) {
   int nitems = (p.mode == MODE_FACTOR) ? p.B : (p.M + p.rows_per_cta - 1) / p.rows_per_cta;
   // few matrices: one 8-CTA cluster per matrix instead of one CTA (see potrf_cluster_kernel)
   static const bool no_cluster = getenv("SPB_NO_CLUSTER") != nullptr;   // A/B switch for measurements
-  if (!no_cluster && p.mode == MODE_FACTOR && p.B * CLUSTER <= ctx->num_sms && p.n > 2 * TM &&
-      ctx->d_scratch) {
+  int cs = 0;
+  if (!no_cluster && p.mode == MODE_FACTOR && p.n > 2 * TM && ctx->d_scratch &&
+      p.B * 2 <= ctx->num_sms) {
+    // largest cluster size whose clusters are all co-resident (a second wave of clusters would
+    // cost more than a smaller cluster: GPCs host a whole number of clusters), asked of the driver
+    static int max_active[64][3];
     static bool cattr[64] = {false};
-    if (!cattr[ctx->device & 63]) {
-      SPB_CHECK_CUDA(cudaFuncSetAttribute(potrf_cluster_kernel,
+    const int dv = ctx->device & 63;
+    if (!cattr[dv]) {
+      SPB_CHECK_CUDA(cudaFuncSetAttribute(potrf_cluster_kernel<8>,
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      cattr[ctx->device & 63] = true;
+      SPB_CHECK_CUDA(cudaFuncSetAttribute(potrf_cluster_kernel<4>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      SPB_CHECK_CUDA(cudaFuncSetAttribute(potrf_cluster_kernel<2>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      for (int k = 0; k < 3; ++k) {
+        const int c = 8 >> k;
+        cudaLaunchConfig_t q = {};
+        q.gridDim = dim3((unsigned)(c * ctx->num_sms));
+        q.blockDim = dim3(NTHREADS);
+        q.dynamicSmemBytes = smem;
+        cudaLaunchAttribute a[1];
+        a[0].id = cudaLaunchAttributeClusterDimension;
+        a[0].val.clusterDim.x = (unsigned)c;
+        a[0].val.clusterDim.y = 1;
+        a[0].val.clusterDim.z = 1;
+        q.attrs = a;
+        q.numAttrs = 1;
+        int n = 0;
+        cudaError_t e = (c == 8)   ? cudaOccupancyMaxActiveClusters(&n, potrf_cluster_kernel<8>, &q)
+                        : (c == 4) ? cudaOccupancyMaxActiveClusters(&n, potrf_cluster_kernel<4>, &q)
+                                   : cudaOccupancyMaxActiveClusters(&n, potrf_cluster_kernel<2>, &q);
+        max_active[dv][k] = (e == cudaSuccess) ? n : 0;
+      }
+      (void)cudaGetLastError();
+      cattr[dv] = true;
     }
+    for (int k = 0; k < 3 && !cs; ++k)
+      if (p.B <= max_active[dv][k]) cs = 8 >> k;
+  }
+  if (cs) {
     const unsigned slot = __atomic_fetch_add(&ctx->counter_next, 1u, __ATOMIC_RELAXED) % SPB_NUM_COUNTERS;
     p.scratch = ctx->d_scratch + (size_t)slot * SPB_SCRATCH_PER_SLOT;
-    SPB_REQUIRE(CLUSTER * p.B <= SPB_SCRATCH_PER_SLOT, "cholesky: cluster scratch too small");
+    SPB_REQUIRE(cs * p.B <= SPB_SCRATCH_PER_SLOT, "cholesky: cluster scratch too small");
     p.counter = nullptr;
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)(p.B * CLUSTER));
+    cfg.gridDim = dim3((unsigned)(p.B * cs));
     cfg.blockDim = dim3(NTHREADS);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = (cudaStream_t)stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = CLUSTER;
+    attr[0].val.clusterDim.x = (unsigned)cs;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    SPB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, potrf_cluster_kernel, p));
+    if (cs == 8) SPB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, potrf_cluster_kernel<8>, p));
+    else if (cs == 4) SPB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, potrf_cluster_kernel<4>, p));
+    else SPB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, potrf_cluster_kernel<2>, p));
     SPB_LAUNCH_CHECK(ctx);
     return 0;
   }
