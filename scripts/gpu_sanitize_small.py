@@ -1,0 +1,24 @@
+"""Small end-to-end workload for compute-sanitizer (memcheck / racecheck): every kernel family once."""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np, torch
+import starry_process_b200 as spb
+t = np.linspace(0, 2, 301)
+rng = np.random.default_rng(0)
+f = 1e-3 * rng.standard_normal(301)
+for marg in (True, False):
+    gp = spb.StarryProcess(r=[12.0, 20.0, 15.0], mu=[30.0, 50.0, 10.0], sigma=[5.0, 10.0, 20.0], c=[0.1, 0.05, 0.2],
+                           n=[10.0, 3.0, 5.0], marginalize_over_inclination=marg)
+    print("lnlike", gp.log_likelihood(t, f, 1e-6, i=60.0, p=1.0, u=[0.4, 0.26]).cpu().numpy())
+gp = spb.StarryProcess(r=12.0, mu=30.0, sigma=5.0, c=0.1, n=10.0, normalized=False, tau=0.5)
+mu, K = gp.predict(t, f, 1e-6, t_sample=t[:77], i=60.0)
+print("predict", float(mu.sum()), float(K.trace()))
+print("sample", float(gp.sample(t[:100], nsamples=2).sum()))
+gp2 = spb.StarryProcess(r=12.0, mu=30.0, sigma=5.0, c=0.1, n=10.0, normalized=False,
+                        marginalize_over_inclination=False)
+print("ylm cond", float(gp2.sample_ylm_conditional(t, f, 1e-6, i=60.0).sum()))
+print("design", float(gp2.design_matrix(t, i=[10.0, 80.0]).sum()))
+print("sample_ylm", float(gp2.sample_ylm(nsamples=3).sum()))
+torch.cuda.synchronize()
+print("done")
