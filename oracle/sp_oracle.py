@@ -991,3 +991,37 @@ class OracleProcess(object):
         cho_cov_t = cho_factor(cov_t)
         Ly = self.cho_cov_ylm
         return np.einsum("km,imj,nj->ikn", cho_cov_t, unit_normals, Ly)
+
+    # sp.py:1237-1283
+    def flux(self, y, t, i=DEFAULTS["i"], p=DEFAULTS["p"], u=(0.0, 0.0)):
+        y = np.asarray(y, dtype=float)
+        A = self.design_matrix(t, i, p, u)
+        F = np.tensordot(A, y, axes=[[1], [y.ndim - 1]])
+        if self.tau is not None:
+            flux = np.diagonal(F, axis1=0, axis2=y.ndim - 1)
+        else:
+            flux = np.transpose(F)
+        if self.normalized:
+            flux = (1.0 + flux) / np.reshape(np.mean(1.0 + flux, axis=-1), (-1, 1)) - 1.0
+        return flux
+
+    # sp.py:1190-1198
+    def __add__(self, other):
+        return OracleProcessSum(self, other)
+
+
+class OracleProcessSum(OracleProcess):
+    """sp.py:1335-1400."""
+
+    def __init__(self, first, second):
+        assert first.normalized == second.normalized and first.marg == second.marg
+        assert first.covpts == second.covpts and first.tau is None and second.tau is None
+        self.__dict__.update(first.__dict__)
+        self.mean_ylm = first.mean_ylm + second.mean_ylm
+        self.cov_ylm = first.cov_ylm + second.cov_ylm
+        self._cho = None
+        # FluxIntegral.__init__ (flux.py:55-62) on the summed moments
+        self.ez = self._dotRx(self.mean_ylm.reshape(1, -1), self._rx90).T
+        mom2y = np.ascontiguousarray(self.cov_ylm + np.outer(self.mean_ylm, self.mean_ylm))
+        tmp = np.ascontiguousarray(self._dotRx(mom2y, self._rx90).T)
+        self.Ez = self._dotRx(tmp, self._rx90)

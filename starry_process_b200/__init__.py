@@ -5,7 +5,8 @@ Public surface mirrors the reference for this path: ``StarryProcess``, ``gauss2b
 loads ``libspb200.so`` (build it with ``python -m starry_process_b200.build``) and fails loudly if it
 or a CUDA device is missing.
 """
-from .sp import StarryProcess, beta2gauss, defaults, gauss2beta, get_context  # noqa: F401
+from .sp import (StarryProcess, StarryProcessSum, beta2gauss, defaults, gauss2beta,  # noqa: F401
+                 get_context)
 from .distributed import gather_lnlike, shard_range  # noqa: F401
 from .temporal import ExpSquaredKernel, Matern32Kernel  # noqa: F401
 

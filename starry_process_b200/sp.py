@@ -28,7 +28,7 @@ import torch
 
 from . import _lib, _tables, temporal as _temporal
 
-__all__ = ["StarryProcess", "gauss2beta", "beta2gauss", "defaults"]
+__all__ = ["StarryProcess", "StarryProcessSum", "gauss2beta", "beta2gauss", "defaults"]
 
 # starry_process/defaults.py:4-35
 defaults = dict(
@@ -995,3 +995,99 @@ class StarryProcess(object):
             out = torch.where(((info & 1) != 0)[:, None, None, None],
                               torch.full_like(out, float("nan")), out)
         return self._out(out)
+
+    # ------------------------------------------------------------------ flux of given surfaces, sums
+    def flux(self, y, t, i=defaults["i"], p=defaults["p"], u=None):
+        """sp.py:1237-1283: light curves ``(nsamples, nt)`` of spherical-harmonic vectors ``y``
+        (``(nsamples, nylm)``, or ``(nsamples, nt, nylm)`` for time-variable surfaces, e.g. the
+        output of ``sample_ylm``); mean-normalised when the process is ``normalized``."""
+        dev = self.device
+        yt = torch.as_tensor(y, dtype=torch.float64).to(dev)
+        squeeze = yt.ndim == 1
+        if squeeze:
+            yt = yt[None]
+        A = self.design_matrix(t, i, p, u)
+        if A.ndim != 2:
+            raise ValueError("flux() takes a scalar inclination")
+        nt = A.shape[0]
+        with torch.cuda.device(dev):
+            if self._time_variable:
+                if yt.ndim != 3 or yt.shape[1] != nt or yt.shape[2] != 256:
+                    raise ValueError("time-variable surfaces: y must have shape (nsamples, nt, 256)")
+                ns = yt.shape[0]
+                yt = yt.contiguous()
+                out = torch.empty(nt, ns, dtype=torch.float64, device=dev)
+                # F[k][s] = A[k] . y[s][k]  -- one (ns x 256)(256 x 1) product per time
+                self._gemm(nt, ns, 1, 256, yt, nt * 256, 256, A, 256, 256, out, 1, ns)
+                F = out.transpose(0, 1).contiguous()
+            else:
+                if yt.ndim != 2 or yt.shape[1] != 256:
+                    raise ValueError("y must have shape (nsamples, 256)")
+                ns = yt.shape[0]
+                F = torch.empty(ns, nt, dtype=torch.float64, device=dev)
+                self._gemm(1, ns, nt, 256, yt.contiguous(), 256, 0, A, 256, 0, F, nt, 0)
+            if self._normalized:   # sp.py:1279-1282
+                F = (1.0 + F) / (1.0 + F).mean(dim=-1, keepdim=True) - 1.0
+        return F[0] if squeeze else F
+
+    def __add__(self, other):
+        """sp.py:1190-1191."""
+        return StarryProcessSum(self, other)
+
+    def __radd__(self, other):
+        """sp.py:1193-1197 (so that ``sum([...])`` works)."""
+        if isinstance(other, (int, float)) and other == 0:
+            return self
+        return self.__add__(other)
+
+
+class StarryProcessSum(StarryProcess):
+    """sp.py:1335-1400: the sum of independent processes -- Ylm means and covariances add; every
+    flux-space method then runs on the summed moments through the same kernels."""
+
+    def __init__(self, first, second):
+        assert isinstance(second, StarryProcess), \
+            "Can only add instances of `StarryProcess` to each other."
+        assert first._ydeg == second._ydeg, "Mismatch in `ydeg`."
+        assert first._udeg == second._udeg, "Mismatch in `udeg`."
+        assert first._normalized == second._normalized, "Mismatch in `normalized`."
+        assert first._marginalize_over_inclination == second._marginalize_over_inclination, \
+            "Mismatch in `marginalize_over_inclination`."
+        assert first._covpts == second._covpts, "Mismatch in `covpts`."
+        assert first._time_variable is False and second._time_variable is False, \
+            "Sums of `StarryProcess` instances not implemented for time-variable surfaces."
+        assert first.device == second.device, "Mismatch in device."
+        for k in ("_ydeg", "_udeg", "_nylm", "_normalized", "_marginalize_over_inclination",
+                  "_covpts", "_normN", "_normzmax", "_max_chunk_bytes", "_sigma_max", "_ctx",
+                  "device", "_lib"):
+            setattr(self, k, getattr(first, k))
+        self._time_variable, self._tkind, self._tau = False, 0, None
+        self._children = []
+        for child in (first, second):
+            self._children += getattr(child, "_children", [child])
+        if first._B != second._B and 1 not in (first._B, second._B):
+            raise ValueError("batched summands must have the same batch size")
+        self._B = max(first._B, second._B)
+        self._batched = first._batched or second._batched
+        first._compute_moments()
+        second._compute_moments()
+        B = self._B
+        # Sum the random variables (sp.py:1383-1385)
+        self._mean_ylm = (first._mean_ylm + second._mean_ylm).expand(B, 256).contiguous()
+        self._cov_ylm = (first._cov_ylm + second._cov_ylm).expand(B, 256, 256).contiguous()
+        self._info = (first._info | second._info).expand(B).contiguous()
+        self._cho_cov_ylm = None
+        self._z = None
+        self._a = self._b = self._r = self._c = self._n = None
+
+    def _compute_moments(self):
+        return
+
+    def log_jac(self):
+        raise NotImplementedError("log_jac is defined for a single process (sp.py:1004-1050)")
+
+    @property
+    def a(self):
+        raise AttributeError("a sum of processes has no single latitude distribution")
+
+    b = a
