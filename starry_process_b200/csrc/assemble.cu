@@ -300,7 +300,8 @@ int run_assemble(spb_context *ctx, AsmParams &p, void *workspace, size_t workspa
   SPB_REQUIRE(p.nm.temporal_kind >= 0 && p.nm.temporal_kind <= 2, "assemble: unknown temporal kernel");
   SPB_REQUIRE(!p.nm.temporal_kind || p.nm.tau != nullptr, "assemble: temporal kernel without tau");
   SPB_REQUIRE(smW <= 200 * 1024, "assemble: nt too large for the shared-memory staging");
-  static bool attr = false;
+  static bool attr_dev[64] = {false};   // function attributes are per device
+  bool &attr = attr_dev[ctx->device & 63];
   if (!attr) {
     SPB_CHECK_CUDA(cudaFuncSetAttribute(rowsum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         200 * 1024));
@@ -312,7 +313,8 @@ int run_assemble(spb_context *ctx, AsmParams &p, void *workspace, size_t workspa
   }
   if (p.nm.normalized) {
     if (p.marginal) {
-      static bool attr2 = false;
+      static bool attr2_dev[64] = {false};
+      bool &attr2 = attr2_dev[ctx->device & 63];
       if (!attr2) {
         SPB_CHECK_CUDA(cudaFuncSetAttribute(rowsum_sym_kernel<false>,
                                             cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));

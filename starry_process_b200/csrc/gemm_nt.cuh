@@ -232,7 +232,8 @@ inline int launch(spb_context *ctx, const Desc &d, cudaStream_t stream) {
                   (d.strideA % 2) == 0 && (d.strideB % 2) == 0,
               "gemm_nt: operands must be 16-byte aligned");
   SPB_REQUIRE(d.batch <= 65535, "gemm_nt: batch too large for one launch");
-  static bool attr_set = false;
+  static bool attr_dev[64] = {false};   // function attributes are per device
+  bool &attr_set = attr_dev[ctx->device & 63];
   const size_t smem = sizeof(Smem);
   if (!attr_set) {
     SPB_CHECK_CUDA(cudaFuncSetAttribute(gemm_nt_kernel<EPI>,

@@ -84,8 +84,9 @@ __constant__ int k1_perm[256];
 // term-table work list: k1_tt_sched[slot * 256 + tid] = a * 31 + b, or -1
 __constant__ int k1_tt_sched[3 * 256];
 
-int k1_upload_perm() {
-  static bool done = false;
+int k1_upload_perm(int device) {
+  static bool done_dev[64] = {false};   // __constant__ banks are per device
+  bool &done = done_dev[device & 63];
   if (!done) {
     int perm[256], n = 0;
     for (int par = 0; par < 2; ++par)
@@ -679,9 +680,11 @@ __global__ void __launch_bounds__(256, 2) moments_k2(K2Params p) {
   }
 }
 
-int k2_upload_items(int *nitems_out) {
-  static bool done = false;
-  static int nitems = 0;
+int k2_upload_items(int device, int *nitems_out) {
+  static bool done_dev[64] = {false};
+  static int nitems_dev[64] = {0};
+  bool &done = done_dev[device & 63];
+  int &nitems = nitems_dev[device & 63];
   if (!done) {
     K2Item items[64];
     int toff = 0;
@@ -819,7 +822,8 @@ extern "C" int spb_ylm_moments(spb_context *ctx, int B, const double *r_deg, con
   MomWs ws;
   mom_ws_layout(B, reinterpret_cast<unsigned char *>(workspace), &ws);
 
-  static bool attr1 = false;
+  static bool attr1_dev[64] = {false};
+  bool &attr1 = attr1_dev[ctx->device & 63];
   if (!attr1) {
     SPB_CHECK_CUDA(cudaFuncSetAttribute(moments_k1a, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)sizeof(K1Smem)));
@@ -829,7 +833,7 @@ extern "C" int spb_ylm_moments(spb_context *ctx, int B, const double *r_deg, con
                                         (int)((K2_NRP * 31 + 2 * 31 * 32) * sizeof(double))));
     attr1 = true;
   }
-  SPB_REQUIRE(k1_upload_perm() == 0, "ylm_moments: constant upload failed");
+  SPB_REQUIRE(k1_upload_perm(ctx->device) == 0, "ylm_moments: constant upload failed");
   K1Params p1;
   p1.r_deg = r_deg;
   p1.a = a;
@@ -854,7 +858,7 @@ extern "C" int spb_ylm_moments(spb_context *ctx, int B, const double *r_deg, con
   SPB_LAUNCH_CHECK(ctx);
 
   int nitems = 0;
-  SPB_REQUIRE(k2_upload_items(&nitems) == 0, "ylm_moments: constant upload failed");
+  SPB_REQUIRE(k2_upload_items(ctx->device, &nitems) == 0, "ylm_moments: constant upload failed");
   for (int b0 = 0; b0 < B; b0 += MOM_CHUNK) {
     const int Bc = (B - b0 < MOM_CHUNK) ? B - b0 : MOM_CHUNK;
     K2Params p2;

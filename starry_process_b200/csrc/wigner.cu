@@ -422,7 +422,8 @@ extern "C" int spb_design_matrix(spb_context *ctx, int I, int nt, const double *
     int st = spb_encode_tmap_3d_f64(&tmap, A, 256, (unsigned long long)nt, (unsigned long long)I,
                                     256ull * 8, (unsigned long long)nt * 256 * 8, DM_CW, 32, 1);
     if (st) return st;
-    static bool attr = false;
+    static bool attr_dev[64] = {false};
+    bool &attr = attr_dev[ctx->device & 63];
     if (!attr) {
       SPB_CHECK_CUDA(cudaFuncSetAttribute(design_rows_kernel<true>,
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tma));
