@@ -26,9 +26,13 @@
 //     column, column scaling deferred).
 //
 // Algorithmic flops per matrix: nt^3/3 (factor) + nt^2 M (forward solve); see DESIGN.md.
+#include <cooperative_groups.h>
+#include <stddef.h>
 #include <stdlib.h>
 
 #include "common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace {
 
@@ -135,6 +139,9 @@ __device__ __forceinline__ unsigned long long gtimer() {
 #define PROF_DECL
 #define PROF_MARK(sm, k)
 #endif
+
+static_assert(offsetof(Smem, Dv) == offsetof(Smem, Ld) + sizeof(double) * NB * LS,
+              "Ld and Dv must be adjacent (copied as one block by the cluster kernel)");
 
 __device__ __forceinline__ int swz(int row, int k) {  // element index inside a stage row
   return (((k >> 1) ^ ((row & 3) << 1)) << 1) | (k & 1);
@@ -858,9 +865,10 @@ __global__ void __launch_bounds__(NTHREADS, 2) potrf_lnlike_kernel(PotrfParams p
 // panel are dealt round-robin to the CTAs of a cluster: all k-loops of a panel run concurrently on
 // different SMs, CTA 0 owns the diagonal tile (k-loop, in-register factorisation, L_jj written to
 // global memory), and two cluster barriers per panel (release / acquire: they order the global
-// writes) separate  "L_jj published"  and  "panel complete".  The other CTAs fetch L_jj through L2
-// (ld.global.cg), invert its 8x8 diagonal tiles locally and run the same in-register TRSM.  Same
-// device functions, same arithmetic per tile as the batch kernel: results are bit-identical to it.
+// writes) separate  "L_jj published"  and  "panel complete".  The other CTAs copy L_jj and the
+// inverses of its diagonal tiles out of CTA 0's shared memory (DSMEM) and run the same in-register
+// TRSM.  Same device functions, same operands per tile as the batch kernel: the factor and the
+// solved rows are bit-identical to it (lnlike to rounding: |y|^2 is summed per CTA).
 // ------------------------------------------------------------------------------------------
 constexpr int CLUSTER_MAX = 8;   // portable cluster size; 4 and 2 serve mid-sized batches
 
@@ -959,17 +967,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) potrf_cluster_kernel(PotrfParams 
     }
     cluster_barrier();   // L_jj published
     if (rank != 0 && have_tile) {
-      for (int idx = tid; idx < NB * NB; idx += NTHREADS) {
-        const int i = idx >> 6, j = idx & 63;
-        double v = 0.0;
-        if (j <= i) {
-          if (c0 + i < p.n) v = __ldcg(rm.Kb + (size_t)(c0 + i) * p.ld + c0 + j);
-          else v = (i == j) ? 1.0 : 0.0;
-        }
-        sm.Ld[i][j] = v;
-      }
+      // L_jj and the inverses of its 8x8 diagonal tiles straight from CTA 0's shared memory
+      // (distributed shared memory; Ld and Dv are adjacent in Smem): the same operands as CTA 0
+      // and the batch kernel use, hence bit-identical rows, and no second trip through L2
+      const double2 *src = reinterpret_cast<const double2 *>(
+          cg::this_cluster().map_shared_rank(&sm.Ld[0][0], 0));
+      double2 *dst = reinterpret_cast<double2 *>(&sm.Ld[0][0]);
+      for (int idx = tid; idx < (NB * LS + NB * DS) / 2; idx += NTHREADS) dst[idx] = src[idx];
       __syncthreads();
-      diag_inverses(sm);
     }
     // ---- finish the first tile, then any further tiles of this CTA
     for (int ti = rank; ti < ntiles; ti += CLUSTER) {

@@ -160,6 +160,36 @@ def test_cholesky_kernel_vs_lapack(spb):
     assert info.cpu().numpy().tolist() == [0, 1, 1]
 
 
+def test_cholesky_cluster_and_batch_kernels_agree(spb):
+    """The one-matrix-per-cluster kernel (small batches, cluster sizes 8 / 4 / 2) runs the same
+    arithmetic per tile as the one-CTA-per-matrix kernel: identical factors and solved rows, bit
+    for bit; lnlike to rounding (different summation order of |L^-1 r|^2); non-PD flagged alike."""
+    ctx = spb.get_context(0)
+    n, M, Bbig = 600, 3, 160   # 160 matrices: batch kernel; subsets of 3 / 20 / 60: clusters
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    A = torch.randn(Bbig, n, 32, dtype=torch.float64, device="cuda", generator=gen)
+    K0 = torch.bmm(A, A.transpose(1, 2)) / 32 + torch.eye(n, dtype=torch.float64, device="cuda")
+    K0[1, 300, 300] = -5.0     # one non-PD element
+    R0 = torch.randn(Bbig, M, n, dtype=torch.float64, device="cuda", generator=gen)
+
+    def run(B):
+        K, R = K0[:B].clone(), R0[:B].clone()
+        ll = torch.zeros(B, dtype=torch.float64, device="cuda")
+        info = torch.zeros(B, dtype=torch.int32, device="cuda")
+        assert ctx.lib.spb_cholesky_lnlike(ctx.handle, B, n, P(K), n, n * n, M, P(R), n, M * n,
+                                           P(ll), None, None, P(info), None) == 0
+        torch.cuda.synchronize()
+        return torch.tril(K), R, ll, info
+
+    Lb, Rb, llb, ib = run(Bbig)
+    for B in (3, 20, 60):
+        Lc, Rc, llc, ic = run(B)
+        ok = [b for b in range(B) if b != 1]
+        assert torch.equal(Lc[ok], Lb[:B][ok]) and torch.equal(Rc[ok], Rb[:B][ok])
+        assert float((llc[ok] - llb[:B][ok]).abs().max()) <= 1e-13 * float(llb[ok].abs().max())
+        assert torch.equal(ic, ib[:B]) and int(ic[1]) == 1 and bool(torch.isneginf(llc[1]))
+
+
 def test_solve_rows_many_rhs(spb):
     import scipy.linalg as sl
 
