@@ -188,7 +188,7 @@ class StarryProcess(object):
                 raise NotImplementedError("non-default `%s` is not supported" % key)
         self._normN = int(kwargs.pop("normalization_order", defaults["normalization_order"]))
         self._normzmax = float(kwargs.pop("normalization_zmax", defaults["normalization_zmax"]))
-        self._max_chunk_bytes = int(kwargs.pop("max_chunk_bytes", 48 << 30))
+        self._max_chunk_bytes = int(kwargs.pop("max_chunk_bytes", 96 << 30))
         self._sigma_max = float(kwargs.pop("sigma_max", defaults["sigma_max"]))
         kwargs.pop("seed", None)
         self._nylm = (self._ydeg + 1) ** 2
@@ -539,8 +539,13 @@ class StarryProcess(object):
         return gp_mean, K, z
 
     def _chunks(self, nt, ldk):
+        # as few chunks as the memory bound allows (96 GB of covariance matrices by default: the
+        # B200 has 180 GB), of equal size: the Cholesky kernel claims matrices dynamically, so one
+        # long launch has a shorter tail than several short ones
         per = nt * ldk * 8 + 4 * 256 * 256 * 8
         step = max(1, min(self._B, self._max_chunk_bytes // per))
+        nchunks = -(-self._B // step)
+        step = -(-self._B // nchunks)
         return [(b0, min(self._B, b0 + step)) for b0 in range(0, self._B, step)]
 
     def _prep(self, t, i, p, u, marginalize_over_inclination):
