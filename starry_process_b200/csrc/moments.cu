@@ -18,8 +18,8 @@
 //         Q (constant orthonormal basis Z): S = Z^T Q Z, parallel cyclic Jacobi in shared
 //         memory, eigenvalues <= 1e-15 clipped exactly as matrix_sqrt does
 //         -> sqrtC_lat (256 x r), first moments through the folded tensors R0, t_lon
-//   K2  sqrtC_lon = T_lon . sqrtC_lat  (integrals.py:133-138), T_lon slices staged in shared
-//       memory and re-used across 32 samples
+//   K2  sqrtC_lon = T_lon . sqrtC_lat  (integrals.py:133-138) as small DMMA GEMMs, the T_lon
+//       fragments register-resident and re-used across 32 samples
 //   K3  cov = (pi c)^2 n (sqrtC_lon sqrtC_lon^T - mom1 mom1^T) + diag(lambda) on the FP64 tensor
 //       pipe (gemm_nt.cuh, lower tiles mirrored); the longitude re-factorisation of
 //       integrals.py:144-150 only clips <=1e-15 modes of an explicitly PSD product and is skipped.
@@ -617,62 +617,70 @@ struct K2Params {
 };
 
 constexpr int K2_GROUP = 32;
-constexpr int K2_NRP = 256;  // row pitch of the transposed T tile
+constexpr int K2_SP = 36;   // shared-memory pitch of the S_lat slice: 36 = 4 (mod 16) makes the
+                            // (k = tg, n = g) fragment loads of m8n8k4 conflict-free
 
-// Thread tile: 4 rows x 4 kept eigen-columns (16 accumulators).  Per m the thread reads 4 T values
-// (one 32-byte run of the TRANSPOSED tile) and 4 S values and issues 16 FMAs, i.e. one shared-memory
-// wavefront per ~4 FMAs instead of one per FMA (the row-per-thread form was LSU-bound).  Only
-// the first rk4 = 4 ceil(rkeep / 4) columns are computed and written; the SYRK never reads the rest.
+// For each l this is a small GEMM  X_l (31 w x rk) = T_l (31 w x w) . S_l (w x rk),  w = 2l + 1, and it
+// runs on the FP64 tensor pipe: a warp owns 32 rows (4 m-tiles) of the constant tensor and keeps
+// their A fragments IN REGISTERS for all 32 samples of its group (the tensor never goes through
+// shared memory); per sample only the S_lat slice is staged (double-buffered, one barrier) and
+// read as B fragments.  k is padded to a multiple of 4 and the kept eigen-columns to n-tiles of 8;
+// only the first rk4 = 4 ceil(rkeep / 4) columns are written (the SYRK never reads the rest).
+// The scalar-FMA form of this kernel was shared-memory-LSU-bound (one wavefront per ~4 FMAs).
 __global__ void __launch_bounds__(256, 2) moments_k2(K2Params p) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  double *Tt = reinterpret_cast<double *>(smem_raw);    // [w][K2_NRP]  T_lon tile, transposed
+  __shared__ __align__(16) double Ssh[2][32][K2_SP];
   const K2Item it = k2_items[blockIdx.x];
   const int w = 2 * it.l + 1;
-  double *Ssh = Tt + 31 * K2_NRP;                        // [2][31][32]
-  const int tid = threadIdx.x;
+  const int nkk = (w + 3) >> 2;   // k-steps of 4
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, tg = lane & 3;
   const double *Tl = p.tab + SPB_TAB_LON_T + it.toff + (size_t)it.row0 * w;
-  const int nq = (it.nrows + 3) >> 2;
-  for (int idx = tid; idx < w * K2_NRP; idx += 256) {
-    const int m = idx >> 8, r = idx & (K2_NRP - 1);
-    Tt[idx] = (r < it.nrows) ? Tl[(size_t)r * w + m] : 0.0;
+  // A fragments: a[mt][kk] = T[row = 32 warp + 8 mt + g][k = 4 kk + tg]
+  double a[4][8];
+#pragma unroll
+  for (int mt = 0; mt < 4; ++mt) {
+    const int r = 32 * warp + 8 * mt + g;
+#pragma unroll
+    for (int kk = 0; kk < 8; ++kk) {
+      const int k = 4 * kk + tg;
+      a[mt][kk] = (r < it.nrows && k < w) ? __ldg(Tl + (size_t)r * w + k) : 0.0;
+    }
   }
+  const bool warp_live = 32 * warp < it.nrows;
   const int b0 = blockIdx.y * K2_GROUP;
   const int b1 = min(p.B, b0 + K2_GROUP);
   for (int b = b0; b < b1; ++b) {
-    double *Sb = Ssh + ((b - b0) & 1) * (31 * 32);
+    double(*Sb)[K2_SP] = Ssh[(b - b0) & 1];
     const double *src = p.S_lat + ((size_t)b * 256 + it.l * it.l) * 32;
-    for (int idx = tid; idx < w * 32; idx += 256) Sb[idx] = src[idx];
+    // rows k >= w of the padded slice are zero (4 nkk <= 32 rows)
+    for (int idx = tid; idx < 4 * nkk * 32; idx += 256) {
+      const int k = idx >> 5, e = idx & 31;
+      Sb[k][e] = (k < w) ? src[idx] : 0.0;
+    }
     __syncthreads();
-    const int ng = (p.rkeep[b] + 3) >> 2;   // groups of 4 kept columns
+    const int rk4 = (p.rkeep[b] + 3) & ~3;
+    const int nnt = (rk4 + 7) >> 3;
     double *Xb = p.X + (size_t)b * (256 * 992) + ((size_t)it.l * it.l * 31 + it.row0) * 32;
-    for (int tile = tid; tile < nq * ng; tile += 256) {
-      const int rq = tile / ng, eg = tile - rq * ng;
-      double acc[4][4];
+    if (warp_live) {
+      for (int nt = 0; nt < nnt; ++nt) {
+        double acc[4][2];
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+        for (int mt = 0; mt < 4; ++mt) acc[mt][0] = acc[mt][1] = 0.0;
 #pragma unroll
-        for (int e = 0; e < 4; ++e) acc[i][e] = 0.0;
-      const double *tp = Tt + 4 * rq;
-      const double *sp = Sb + 4 * eg;
-      for (int m = 0; m < w; ++m) {
-        const double2 t01 = *reinterpret_cast<const double2 *>(tp + m * K2_NRP);
-        const double2 t23 = *reinterpret_cast<const double2 *>(tp + m * K2_NRP + 2);
-        const double2 s01 = *reinterpret_cast<const double2 *>(sp + m * 32);
-        const double2 s23 = *reinterpret_cast<const double2 *>(sp + m * 32 + 2);
-        const double tv[4] = {t01.x, t01.y, t23.x, t23.y};
-        const double sv[4] = {s01.x, s01.y, s23.x, s23.y};
+        for (int kk = 0; kk < 8; ++kk) {
+          if (kk < nkk) {
+            const double bf = Sb[4 * kk + tg][8 * nt + g];
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
+            for (int mt = 0; mt < 4; ++mt) dmma_m8n8k4(acc[mt][0], acc[mt][1], a[mt][kk], bf);
+          }
+        }
+        const int col = 8 * nt + 2 * tg;
+        if (col < rk4) {
 #pragma unroll
-          for (int e = 0; e < 4; ++e) acc[i][e] = fma(tv[i], sv[e], acc[i][e]);
-      }
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int r = 4 * rq + i;
-        if (r < it.nrows) {
-          double2 *dst = reinterpret_cast<double2 *>(Xb + (size_t)r * 32 + 4 * eg);
-          dst[0] = make_double2(acc[i][0], acc[i][1]);
-          dst[1] = make_double2(acc[i][2], acc[i][3]);
+          for (int mt = 0; mt < 4; ++mt) {
+            const int r = 32 * warp + 8 * mt + g;
+            if (r < it.nrows)
+              *reinterpret_cast<double2 *>(Xb + (size_t)r * 32 + col) = make_double2(acc[mt][0], acc[mt][1]);
+          }
         }
       }
     }
@@ -829,8 +837,6 @@ extern "C" int spb_ylm_moments(spb_context *ctx, int B, const double *r_deg, con
                                         (int)sizeof(K1Smem)));
     SPB_CHECK_CUDA(cudaFuncSetAttribute(moments_k1b, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)(K1B_WARPS * sizeof(K1bWarp))));
-    SPB_CHECK_CUDA(cudaFuncSetAttribute(moments_k2, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)((K2_NRP * 31 + 2 * 31 * 32) * sizeof(double))));
     attr1 = true;
   }
   SPB_REQUIRE(k1_upload_perm(ctx->device) == 0, "ylm_moments: constant upload failed");
@@ -868,7 +874,7 @@ extern "C" int spb_ylm_moments(spb_context *ctx, int B, const double *r_deg, con
     p2.X = ws.X;
     p2.B = Bc;
     dim3 grid2(nitems, (Bc + K2_GROUP - 1) / K2_GROUP);
-    moments_k2<<<grid2, 256, (K2_NRP * 31 + 2 * 31 * 32) * sizeof(double), stream>>>(p2);
+    moments_k2<<<grid2, 256, 0, stream>>>(p2);
     SPB_LAUNCH_CHECK(ctx);
 
     gnt::Desc d = {};
