@@ -137,6 +137,12 @@ __global__ void __launch_bounds__(NTHREADS, 2) gemm_nt_kernel(Desc d) {
     nt_lim = (last_row - n0) / 8 + 1;       // may be <= 0: the whole warp tile is above the diagonal
     nt_lim = nt_lim < 0 ? 0 : (nt_lim > 8 ? 8 : nt_lim);
   }
+  // narrow outputs (N = 31 quadratic forms of the marginal kernel, N = 1 matrix-vector products of
+  // predict): 8-column groups beyond N are neither loaded nor multiplied
+  {
+    const int nt_n = (d.N - n0 + 7) / 8;
+    if (nt_n < nt_lim) nt_lim = nt_n;
+  }
   const int nch = ch_end - ch_begin;
   // prologue: STAGES-1 chunks in flight (empty commit groups keep the accounting uniform)
 #pragma unroll
