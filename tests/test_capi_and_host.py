@@ -185,3 +185,31 @@ def test_design_unrolled_body_in_sync():
     for (l, mp, j) in idx:
         dropped[T.nwig(l - 1) + mp * (2 * l + 1) + j] = 0.0
     assert dropped.max() < 1e-15 and np.abs(vals).min() > 1e-5
+
+
+def test_temporal_kernels_host_module(oracle):
+    """starry_process_b200.temporal mirrors temporal.py:8-16 (callable form, torch tensors) and
+    carries the kernel codes the CUDA assembly switches on."""
+    import torch
+
+    from starry_process_b200 import temporal
+
+    t1 = np.linspace(0, 3, 17)
+    t2 = np.linspace(0.5, 2, 9)
+    for fn, ofn, kind in ((temporal.Matern32Kernel, oracle.Matern32Kernel, 1),
+                          (temporal.ExpSquaredKernel, oracle.ExpSquaredKernel, 2)):
+        K = fn(torch.tensor(t1), torch.tensor(t2), 0.7).numpy()
+        assert K.shape == (17, 9)
+        assert np.abs(K - ofn(t1, t2, 0.7)).max() <= 1e-15
+        assert fn.spb_kind == kind
+
+
+def test_sass_uses_clusters_and_tma(built_lib):
+    """The small-batch Cholesky is a thread-block-cluster kernel (cluster barriers, distributed
+    shared memory) and the design-matrix kernel stores through TMA: both must be in the SASS."""
+    import subprocess
+
+    sass = subprocess.run(["cuobjdump", "-sass", built_lib], capture_output=True, text=True).stdout
+    assert "UCGABAR_ARV" in sass or "BAR.CLUSTER" in sass or "CGABAR" in sass  # barrier.cluster
+    assert "UTMASTG" in sass                                                  # cp.async.bulk.tensor store
+    assert "DMMA" in sass
