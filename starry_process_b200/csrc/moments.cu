@@ -52,7 +52,9 @@ struct K1Params {
 //   K1b (1 warp / sample)       cyclic Jacobi on S, clip, X = V diag(sqrt w)
 //   K1c (256 threads / sample)  sqrtC_lat = q_l H X
 struct K1Smem {
-  double Zs[32][32];      // 32 rows of the range basis Z at a time (first: 16-byte aligned)
+  double Zs[32][36];      // 32 (permuted) rows of the range basis Z at a time; first member:
+                          // 16-byte aligned; pitch 36 = 4 (mod 16): conflict-free B fragments
+  unsigned char kj[256], ki[256], kl[256];   // (m + l, l - m, l) of the permuted Ylm index
   double bprof[1000];
   double qs[16];
   double Bk[64];
@@ -242,69 +244,109 @@ __global__ void __launch_bounds__(NT1, 2) moments_k1a(K1Params p) {
 
   K1PROF(2);
   // ---- Y = Q Z with Q(n1,n2) = term(j1+j2, i1+i2) 2^-(l1+l2)   (latitude.h:146-172)
-  // Q(n1, n2) vanishes unless l - m has the same parity for both indices.  Rows are dealt to the
-  // threads sorted by that parity (136 even rows, then 120 odd: seven of the eight warps are
-  // parity-uniform and skip the other half of the n2 loop as a whole instead of idling half their
-  // lanes), and Z is staged through shared memory 32 rows at a time (the 64 KB table does not
-  // survive in the ~30 KB of L1 that two resident CTAs leave: every row used to be an L2 round
-  // trip).  Each y[a] still accumulates over n2 in ascending order: results are unchanged.
+  // A (256 x 256) x (256 x 31) product on the FP64 tensor pipe.  Q(n1, n2) vanishes unless l - m
+  // has the same parity for both indices, so rows AND the contraction index run in parity-sorted
+  // order (k1_perm: 136 even, then 120 odd; 8-row tiles and 4-wide k-steps never straddle the
+  // boundary) and every (m-tile, k-step) pair of opposite parity is skipped as a whole: half the
+  // DMMAs.  The Q entries are generated in the A-fragment layout from the term table (the 2^-(l1+l2)
+  // scaling is an exact exponent adjustment); Z is staged 32 permuted rows at a time, 36-double
+  // pitch (conflict-free B fragments).
   int l1, m1;
   lm_of(tid, l1, m1);
   {
-    int lp, mp;
-    const int n1 = k1_perm[tid];
-    lm_of(n1, lp, mp);
-    const int jp = mp + lp, ip = lp - mp;
-    double y[32];   // column 31 of the padded basis is zero
+    // (j, i, l) of the permuted index tid, for the k side
+    {
+      int lp, mp;
+      lm_of(k1_perm[tid], lp, mp);
+      sm.kj[tid] = (unsigned char)(mp + lp);
+      sm.ki[tid] = (unsigned char)(lp - mp);
+      sm.kl[tid] = (unsigned char)lp;
+    }
+    const int g = lane >> 2, tg = lane & 3;
+    int rj[4], ri[4], rl[4];
 #pragma unroll
-    for (int a = 0; a < 32; ++a) y[a] = 0.0;
+    for (int q = 0; q < 4; ++q) {
+      int lp, mp;
+      lm_of(k1_perm[32 * warp + 8 * q + g], lp, mp);
+      rj[q] = mp + lp;
+      ri[q] = lp - mp;
+      rl[q] = lp;
+    }
+    double acc[4][4][2];
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) acc[q][nt][0] = acc[q][nt][1] = 0.0;
     const double *Z = tab + SPB_TAB_LAT_Z;
-    int l2 = 0, m2 = 0;
     for (int c0 = 0; c0 < 256; c0 += 32) {
       __syncthreads();
-      for (int k = tid; k < 32 * 16; k += NT1)
-        reinterpret_cast<double2 *>(&sm.Zs[0][0])[k] =
-            __ldg(reinterpret_cast<const double2 *>(Z + c0 * 32) + k);
+      for (int k = tid; k < 32 * 16; k += NT1) {
+        const int r = k >> 4, c = k & 15;
+        const double2 z2 = __ldg(reinterpret_cast<const double2 *>(Z + k1_perm[c0 + r] * 32) + c);
+        *reinterpret_cast<double2 *>(&sm.Zs[r][2 * c]) = z2;
+      }
       __syncthreads();
-      for (int r = 0; r < 32; ++r) {
-        const int J = jp + m2 + l2, I = ip + l2 - m2;
-        if (!(I & 1)) {
-          const double qv = ldexp(sm.tt[J >> 1][I >> 1], -(lp + l2));
-          const double2 *zr = reinterpret_cast<const double2 *>(&sm.Zs[r][0]);
 #pragma unroll
-          for (int a = 0; a < 16; ++a) {
-            const double2 z2 = zr[a];
-            y[2 * a] = fma(qv, z2.x, y[2 * a]);
-            y[2 * a + 1] = fma(qv, z2.y, y[2 * a + 1]);
+      for (int ks = 0; ks < 8; ++ks) {
+        const int kp = c0 + 4 * ks;              // permuted contraction index of this k-step
+        const bool k_even = kp < 136;
+        const int kj = sm.kj[kp + tg], ki = sm.ki[kp + tg], kl = sm.kl[kp + tg];
+        double bf[4];
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) bf[nt] = sm.Zs[4 * ks + tg][8 * nt + g];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const bool m_even = 32 * warp + 8 * q < 136;   // warp-uniform
+          if (m_even == k_even) {
+            const double t = sm.tt[(rj[q] + kj) >> 1][(ri[q] + ki) >> 1];
+            // t * 2^-(l1 + l2): exact (ldexp in the scalar form)
+            const double av = t * __hiloint2double((1023 - (rl[q] + kl)) << 20, 0);
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) dmma_m8n8k4(acc[q][nt][0], acc[q][nt][1], av, bf[nt]);
           }
-        }
-        if (++m2 > l2) {
-          ++l2;
-          m2 = -l2;
         }
       }
     }
 #pragma unroll
-    for (int a = 0; a < 31; ++a) sm.Y[n1][a] = y[a];
+    for (int q = 0; q < 4; ++q) {
+      const int n1 = k1_perm[32 * warp + 8 * q + g];
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        const int col = 8 * nt + 2 * tg;
+        sm.Y[n1][col] = acc[q][nt][0];
+        if (col + 1 < 31) sm.Y[n1][col + 1] = acc[q][nt][1];
+      }
+    }
   }
   __syncthreads();
   K1PROF(3);
-  // ---- S = Z^T Y (31 x 31), symmetrised, padded to 32.  Thread (warp, lane) owns the four entries
-  // S[warp + 8 j][lane]: four independent accumulation chains over n1 (ascending, as before)
-  // instead of four consecutive ones.
+  // ---- S = Z^T Y (31 x 31), symmetrised, padded to 32: a (32 x 256) x (256 x 32) product on DMMA,
+  // warp w owns the 8 x 16 block  rows 8 (w / 2),  columns 16 (w % 2)
   {
     const double *Z = tab + SPB_TAB_LAT_Z;
-    double s4[4] = {0.0, 0.0, 0.0, 0.0};
-    if (lane < 31) {
-#pragma unroll 4
-      for (int n1 = 0; n1 < 256; ++n1) {
-        const double yv = sm.Y[n1][lane];
+    const int g = lane >> 2, tg = lane & 3;
+    const int a0 = 8 * (warp >> 1), c0 = 16 * (warp & 1);
+    double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+#pragma unroll 1
+    for (int k0 = 0; k0 < 256; k0 += 32) {
+      double av[8];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) s4[j] = fma(__ldg(Z + n1 * 32 + warp + 8 * j), yv, s4[j]);
+      for (int u = 0; u < 8; ++u) av[u] = __ldg(Z + (k0 + 4 * u + tg) * 32 + a0 + g);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int k = k0 + 4 * u + tg;
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt)
+          dmma_m8n8k4(acc[nt][0], acc[nt][1], av[u], sm.Y[k][c0 + 8 * nt + g]);
       }
     }
 #pragma unroll
-    for (int j = 0; j < 4; ++j) sm.V[warp + 8 * j][lane] = (warp + 8 * j < 31) ? s4[j] : 0.0;   // staging
+    for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int a = a0 + g, c = c0 + 8 * nt + 2 * tg + e;
+        sm.V[a][c] = (a < 31 && c < 31) ? acc[nt][e] : 0.0;   // staging
+      }
   }
   __syncthreads();
   for (int idx = tid; idx < 32 * 32; idx += NT1) {
