@@ -492,13 +492,16 @@ def run_b200(args):
         # figure: the live oracle on this host is only reproducible to ~1e-6 across CPUs
         # (DESIGN.md "numerical fragility"), the fixture is what every golden file was made with.
         gpath = os.path.join(ROOT, "tests", "golden", "bench_sweep_seed1234.npz")
-        if os.path.exists(gpath) and B >= 64:
+        if os.path.exists(gpath):
             gref = np.load(gpath)["lnlike_m1_n1"]
+            ng = min(len(gref), B)
+            gref = gref[:ng]
             gfin = np.isfinite(gref)
-            same_inf = bool(np.array_equal(np.isneginf(gref), np.isneginf(llall[:64])))
+            same_inf = bool(np.array_equal(np.isneginf(gref), np.isneginf(llall[:ng])))
+            gerr = np.abs(llall[:ng][gfin] - gref[gfin]) / np.abs(gref[gfin])
             parity_golden = {
-                "max_rel": float(np.max(np.abs(llall[:64][gfin] - gref[gfin]) / np.abs(gref[gfin]))),
-                "n": 64, "neg_inf_pattern_equal": same_inf, "tolerance": 1e-8}
+                "max_rel": float(np.max(gerr)), "median_rel": float(np.median(gerr)),
+                "n": int(ng), "neg_inf_pattern_equal": same_inf, "tolerance": 1e-8}
     cpu_baseline = {
         "value": cb_value, "unit": "evals/s", "cores": host_cores(), "kind": cb_kind,
         "sample": "%d evaluations of the same workload, reference C++ + NumPy/SciPy on the host, one "
