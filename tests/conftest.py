@@ -12,8 +12,26 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 REFERENCE = os.environ.get("SP_REFERENCE_ROOT", "/root/reference")
 
 
+# The golden fixtures were produced by the unmodified reference with the BLAS thread count of the
+# build container (8).  The reference's marginalised lnlike depends on that count at the 3e-6 level
+# (different LAPACK blocking -> different noise-level eigenmodes; DESIGN.md "numerical fragility"),
+# so the CPU comparisons of the oracle against the fixtures pin it -- whatever OMP_NUM_THREADS /
+# OPENBLAS_NUM_THREADS the caller's environment carries.
+GOLDEN_BLAS_THREADS = 8
+_BLAS_LIMIT = None
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (B200); run with -m gpu")
+    global _BLAS_LIMIT
+    try:
+        import numpy  # noqa: F401  (load every BLAS copy first: threadpoolctl only limits what is
+        import scipy.linalg  # noqa: F401   already loaded; NumPy and SciPy ship their own OpenBLAS)
+        from threadpoolctl import threadpool_limits
+
+        _BLAS_LIMIT = threadpool_limits(limits=GOLDEN_BLAS_THREADS, user_api="blas")
+    except Exception:  # threadpoolctl missing: the environment's default applies
+        _BLAS_LIMIT = None
 
 
 def _ensure_oracle_native():
