@@ -48,7 +48,9 @@ def synthetic_inputs(B, seed):
 
 
 class ClockSampler(object):
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clocks / throttle reasons during the timed region (B200_PROFILING.md recipe): NVML polled
+    every 10 ms from a thread (the same counters `nvidia-smi --query-gpu=clocks.sm,
+    clocks_event_reasons.*` prints), falling back to an `nvidia-smi -lms 100` subprocess."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -58,23 +60,71 @@ class ClockSampler(object):
         self.index = index
         self.rows = []
         self.proc = None
+        self.thread = None
+        self.nvml = None
+        self._stop = threading.Event()
+        self.sm, self.smax, self.reasons = [], [], set()
+
+    def _nvml_index(self):
+        # NVML enumerates physical devices: honour CUDA_VISIBLE_DEVICES when it lists indices
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+        try:
+            ids = [int(x) for x in vis.split(",") if x.strip() != ""]
+            return ids[self.index] if ids else self.index
+        except (ValueError, IndexError):
+            return self.index
 
     def start(self):
         try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(self._nvml_index())
+            self.smax.append(float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM)))
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
+        try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                 "--format=csv,noheader,nounits", "-lms", "25"],
+                 "--format=csv,noheader,nounits", "-lms", "100"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except OSError:
             self.proc = None
 
+    def _poll(self):
+        nv = self.nvml
+        bits = (("hw_slowdown", "nvmlClocksThrottleReasonHwSlowdown"),
+                ("hw_thermal_slowdown", "nvmlClocksThrottleReasonHwThermalSlowdown"),
+                ("sw_thermal_slowdown", "nvmlClocksThrottleReasonSwThermalSlowdown"),
+                ("sw_power_cap", "nvmlClocksThrottleReasonSwPowerCap"))
+        while not self._stop.is_set():
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM)))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+                for name, attr in bits:
+                    if r & getattr(nv, attr, 0):
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.01)
+
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append([x.strip() for x in line.split(",")])
 
     def stop(self):
+        if self.nvml is not None:
+            self._stop.set()
+            self.thread.join(timeout=2)
+            return {"sm_mhz": float(np.median(self.sm)) if self.sm else None,
+                    "sm_max_mhz": max(self.smax) if self.smax else None,
+                    "reasons": sorted(self.reasons), "samples": len(self.sm), "source": "nvml"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -93,7 +143,7 @@ class ClockSampler(object):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None,
                 "sm_max_mhz": max(smax) if smax else None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "source": "nvidia-smi"}
 
 
 # ------------------------------------------------------------------------------------------
