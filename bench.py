@@ -523,6 +523,11 @@ def run_b200(args):
         "algorithmic_flops_per_launch": flops_total / n_launch,
         "stage_ms_total": shares,
     }
+    if args.workload != "sweep":
+        roofline["note"] = ("configs[1] is ONE 1000 x 1000 factorisation (an 8-SM thread-block "
+                            "cluster, latency-bound by its 16 dependent panels) plus 1024 "
+                            "right-hand-side rows: a latency workload, not a throughput one -- the "
+                            "headline roofline is the sweep workload's")
     # ---- design-matrix phase (BASELINE configs[4]: nt = 1e5 timestamps x 64 inclinations), timed in
     # the same process with CUDA events on the launching stream, against the measured HBM peak
     phases = {"design_matrix": design_phase(spb, _lib, ctx, dev, torch),
