@@ -117,6 +117,23 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
       : "memory");
 }
 
+// ---- TMA tensor load global -> shared (3-D tensor map), completion on an mbarrier ---------------
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, unsigned bytes) {
+  unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n}\n" ::"r"(a),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void *sdst, const void *tmap, uint64_t *bar, int c0,
+                                            int c1, int c2) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(sdst);
+  unsigned b = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];\n" ::"r"(s),
+      "l"(tmap), "r"(b), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+
 // ---- TMA tensor store shared::cta -> global (cp.async.bulk.tensor, 3-D tensor map) ------------
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");

@@ -29,6 +29,7 @@
 #include <cooperative_groups.h>
 #include <stddef.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include "common.cuh"
 
@@ -61,6 +62,7 @@ struct PotrfParams {
   int rows_per_cta;  // MODE_SOLVE: RHS rows per work item
   unsigned int *counter;  // zeroed before the launch: work items beyond the first wave are claimed here
   double *scratch;        // cluster kernel: (B, CLUSTER) per-CTA partial sums of |y|^2
+  int use_tma;            // operand tiles that lie wholly inside K come through TMA (tensor map of K)
   spb_affine aff;    // fused last assembly step (scal == q == diag == offset == NULL: none)
   int aff_on;
 };
@@ -143,8 +145,10 @@ __device__ __forceinline__ unsigned long long gtimer() {
 static_assert(offsetof(Smem, Dv) == offsetof(Smem, Ld) + sizeof(double) * NB * LS,
               "Ld and Dv must be adjacent (copied as one block by the cluster kernel)");
 
-__device__ __forceinline__ int swz(int row, int k) {  // element index inside a stage row
-  return (((k >> 1) ^ ((row & 3) << 1)) << 1) | (k & 1);
+// element index inside a stage row: the TMA 128-byte swizzle (16-byte chunk index XOR row mod 8),
+// used by the cp.async path as well so that both fill the ring in the same layout
+__device__ __forceinline__ int swz(int row, int k) {
+  return (((k >> 1) ^ (row & 7)) << 1) | (k & 1);
 }
 
 __device__ __forceinline__ double negate(double x) {  // sign flip on the integer pipe
@@ -298,7 +302,8 @@ __device__ __forceinline__ void init_acc(const Smem &sm, const RowMap &rm, const
 template <class Init>
 __device__ __forceinline__ void gemm_tile(Smem &sm, const RowMap &rm, int v0, int c0, int nvirt,
                                           int nt_lim, unsigned &it, double (&acc)[2][8][2],
-                                          Init init) {
+                                          Init init, const CUtensorMap *tmK = nullptr,
+                                          int item = 0) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, tg = lane & 3;
   const int nchunks = c0 / KC;
   PROF_DECL;
@@ -312,7 +317,7 @@ __device__ __forceinline__ void gemm_tile(Smem &sm, const RowMap &rm, int v0, in
   // this thread's cp.async assignments: A: 4 x 16B, B: 2 x 16B per chunk
   const int seg = tid & 7;                 // 16-byte chunk of the 128-byte row segment
   const int r8 = tid >> 3;                 // 0..31
-  const int sseg = (seg ^ ((r8 & 3) << 1)) << 1;  // swizzled element offset (row & 3 == r8 & 3)
+  const int sseg = (seg ^ (r8 & 7)) << 1;  // swizzled element offset (row & 7 == r8 & 7)
   const double *arow[4];
   int abytes[4];
 #pragma unroll
@@ -330,12 +335,28 @@ __device__ __forceinline__ void gemm_tile(Smem &sm, const RowMap &rm, int v0, in
     brow[i] = (r < rm.n) ? rm.Kb + (size_t)r * rm.ld : rm.Kb;
     bbytes[i] = (r < rm.n) ? 16 : 0;
   }
+  // Tiles whose 128 rows are all rows of K (no appended right-hand-side or padding rows) are
+  // fetched by TMA: one thread requests the 128 x 16 and 64 x 16 operand boxes (three
+  // cp.async.bulk.tensor of 64 rows each; rows of the B box past the matrix are zero-filled by the
+  // tensor map), every other thread only arrives on the barrier.
+  const bool tma_tile = tmK != nullptr && rm.mode == MODE_FACTOR && (c0 + v0 + TM <= rm.n);
   // slot / phase of running chunk number x
   auto issue = [&](int ch, unsigned x, bool blocking) -> bool {
     const unsigned st = x % STAGES;
     // previous user of the slot fully read by every warp?
     if (blocking) mbar_wait(&sm.empty[st], ((x / STAGES) + 1u) & 1u);
     else if (!mbar_test(&sm.empty[st], ((x / STAGES) + 1u) & 1u)) return false;
+    if (tma_tile) {
+      if (tid == 0) {
+        mbar_arrive_expect_tx(&sm.full[st], (TM + NB) * KC * (unsigned)sizeof(double));
+        tma_load_3d(&sm.As[st][0][0], tmK, &sm.full[st], ch * KC, c0 + v0, item);
+        tma_load_3d(&sm.As[st][NB][0], tmK, &sm.full[st], ch * KC, c0 + v0 + NB, item);
+        tma_load_3d(&sm.Bs[st][0][0], tmK, &sm.full[st], ch * KC, c0, item);
+      } else {
+        mbar_arrive(&sm.full[st]);
+      }
+      return true;
+    }
     const int k0 = ch * KC + seg * 2;
 #pragma unroll
     for (int i = 0; i < 4; ++i) cp_async16(&sm.As[st][r8 + 32 * i][sseg], arow[i] + k0, abytes[i]);
@@ -680,8 +701,9 @@ __device__ __forceinline__ double block_sum(Smem &sm, double v) {
   return t;
 }
 
-__global__ void __launch_bounds__(NTHREADS, 2) potrf_lnlike_kernel(PotrfParams p) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+__global__ void __launch_bounds__(NTHREADS, 2)
+    potrf_lnlike_kernel(PotrfParams p, const __grid_constant__ CUtensorMap tmK) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];   // TMA 128-byte swizzle: 1 KB aligned
   Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, tg = lane & 3;
 
@@ -792,7 +814,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) potrf_lnlike_kernel(PotrfParams p
           for (int mt = 0; mt < 2; ++mt)
             init_acc(sm, rm, af, p.aff_on != 0, v0 + warp * 16 + mt * 8 + g, c0, tg, full_panel,
                      acc[mt]);
-        });   // acc = K - L L^T = P
+        }, p.use_tma ? &tmK : nullptr, item);   // acc = K - L L^T = P
 #ifdef SPB_POTRF_PROF
         _pt = clock64();
 #endif
@@ -1124,10 +1146,24 @@ static int potrf_launch(spb_context *ctx, PotrfParams &p, void *stream) {
     return 0;
   }
   int grid = nitems < 2 * ctx->num_sms ? nitems : 2 * ctx->num_sms;
+  // tensor map of the batch of matrices for the TMA-fed operand ring: (columns, rows, matrix),
+  // boxes of 16 columns x 64 rows, 128-byte swizzle
+  CUtensorMap tmK;
+  memset(&tmK, 0, sizeof(tmK));
+  static const bool no_tma = getenv("SPB_NO_TMA") != nullptr;   // A/B switch for measurements
+  p.use_tma = 0;
+  if (!no_tma && p.mode == MODE_FACTOR && p.n >= TM + NB) {
+    const unsigned long long sk = p.strideK > 0 ? (unsigned long long)p.strideK : (unsigned long long)p.n * p.ld;
+    int st = spb_encode_tmap_3d_f64(&tmK, p.K, (unsigned long long)p.ld, (unsigned long long)p.n,
+                                    (unsigned long long)p.B, (unsigned long long)p.ld * 8, sk * 8, KC,
+                                    NB, 1);
+    if (st) return st;
+    p.use_tma = 1;
+  }
   p.counter = ctx->d_counters +
       (__atomic_fetch_add(&ctx->counter_next, 1u, __ATOMIC_RELAXED) % SPB_NUM_COUNTERS);
   SPB_CHECK_CUDA(cudaMemsetAsync(p.counter, 0, sizeof(unsigned int), (cudaStream_t)stream));
-  potrf_lnlike_kernel<<<grid, NTHREADS, smem, (cudaStream_t)stream>>>(p);
+  potrf_lnlike_kernel<<<grid, NTHREADS, smem, (cudaStream_t)stream>>>(p, tmK);
   SPB_LAUNCH_CHECK(ctx);
   return 0;
 }
