@@ -212,4 +212,5 @@ def test_sass_uses_clusters_and_tma(built_lib):
     sass = subprocess.run(["cuobjdump", "-sass", built_lib], capture_output=True, text=True).stdout
     assert "UCGABAR_ARV" in sass or "BAR.CLUSTER" in sass or "CGABAR" in sass  # barrier.cluster
     assert "UTMASTG" in sass                                                  # cp.async.bulk.tensor store
+    assert "UTMALDG" in sass            # TMA-fed operand ring of the Cholesky kernel
     assert "DMMA" in sass
