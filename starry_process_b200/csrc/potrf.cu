@@ -1157,8 +1157,7 @@ static int potrf_launch(spb_context *ctx, PotrfParams &p, void *stream) {
     int st = spb_encode_tmap_3d_f64(&tmK, p.K, (unsigned long long)p.ld, (unsigned long long)p.n,
                                     (unsigned long long)p.B, (unsigned long long)p.ld * 8, sk * 8, KC,
                                     NB, 1);
-    if (st) return st;
-    p.use_tma = 1;
+    p.use_tma = (st == 0) ? 1 : 0;   // an unencodable layout simply keeps the cp.async path
   }
   p.counter = ctx->d_counters +
       (__atomic_fetch_add(&ctx->counter_next, 1u, __ATOMIC_RELAXED) % SPB_NUM_COUNTERS);
