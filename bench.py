@@ -2,14 +2,18 @@
 """bench.py -- lnlike evals/sec (ydeg=15, nt=1000, fp64) on N B200s of one node.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
-                    [--workload sweep|ensemble] [--batch B]
+                    [--workload sweep|ensemble] [--batch B] [--scaling strong|weak]
 
 Workload `sweep` (BASELINE.json configs[2], the configuration the metric is quoted on; it fits
-one GPU): an MCMC-style sweep of B hyperparameter samples x 1 synthetic light curve (nt=1000),
-marginalize_over_inclination=True, normalized=True (the reference defaults), limb darkened.
-One STEP = one pass of the hot path over the batch: Ylm moments -> marginal kernel -> covariance
-assembly -> batched Cholesky/solve/logdet -> B log-likelihoods.  Weak scaling: every rank owns B
-samples (no data-path collective; one all-gather of the B*N log-likelihoods per step).
+one GPU): an MCMC-style sweep of B = 4096 hyperparameter samples x 1 synthetic light curve
+(nt=1000), marginalize_over_inclination=True, normalized=True (the reference defaults), limb
+darkened.  One STEP = one pass of the hot path over the batch: Ylm moments -> marginal kernel ->
+covariance assembly -> batched Cholesky/solve/logdet -> B log-likelihoods.
+`--scaling strong` (default; what configs[2] names): ONE batch of B samples is sharded B/N per GPU
+through the product call starry_process_b200.log_likelihood_sharded (no data-path collective; one
+all-gather of the B log-likelihoods per step); value = B * steps / time.  `--scaling weak`: every
+rank owns B samples of its own; at N > 1 the default run also measures it and reports it under
+phases.weak_scaling.
 
 Workload `ensemble` (configs[1]): 1024 light curves sharing one hyperparameter set.
 
@@ -36,15 +40,41 @@ U_LD = [0.4, 0.26]
 METRIC = "lnlike evals/sec (ydeg=15, nt=1000, fp64)"
 
 
-def synthetic_inputs(B, seed):
-    """Hyperparameter draws from the reference's own stability prior with the contrast range
-    narrowed so that the normalised process stays inside its validity range (as in the golden
-    sweep, oracle/gen_golden.py), plus the fiducial synthetic light curve."""
+PRIORS = {
+    # the reference's own stability prior (joss/figures/stability.py:28-35)
+    "full": dict(r=(10, 45), c=(0, 1), n=(1, 50), mu=(0, 85), sigma=(5, 40)),
+    # the same prior with the spot size / contrast / number ranges narrowed so that the NORMALISED
+    # process stays inside its validity range z <= 0.023 (sp.py:1178-1183): under "full" ~95 % of
+    # the draws are rejected with -inf by that rule (same work per evaluation, no information)
+    "narrow": dict(r=(10, 30), c=(0.01, 0.15), n=(1, 12), mu=(0, 85), sigma=(5, 40)),
+}
+
+
+def synthetic_inputs(B, seed, prior="narrow"):
+    """Hyperparameter draws (uniform over PRIORS[prior], in the order r, c, n, mu, sigma of
+    stability.py) plus the fiducial synthetic light curve of tests/golden/fiducial_nt1000.npz."""
     rng = np.random.default_rng(seed)
-    hp = dict(r=rng.uniform(10, 30, B), c=rng.uniform(0.01, 0.15, B), n=rng.uniform(1, 12, B),
-              mu=rng.uniform(0, 85, B), sigma=rng.uniform(5, 40, B))
+    pr = PRIORS[prior]
+    hp = {k: rng.uniform(pr[k][0], pr[k][1], B) for k in ("r", "c", "n", "mu", "sigma")}
     g = np.load(os.path.join(ROOT, "tests", "golden", "fiducial_nt1000.npz"))
     return hp, g["t"].copy(), g["flux_norm"].copy(), g["flux_ens_norm"].copy()
+
+
+def ensemble_flux(M, nt=NT, seed=77, normalized=True):
+    """configs[1] inputs: M distinct synthetic light curves on t = linspace(0, 4, nt) -- a rotational
+    sinusoid of random harmonic / phase / amplitude plus 1e-3 white noise -- reproducible from the
+    seed alone (NumPy's PCG64 streams are platform independent), mean-normalised as sp.py:1067-1075
+    expects for a normalised process."""
+    rng = np.random.default_rng(seed)
+    t = np.linspace(0, 4, nt)
+    k = rng.integers(1, 6, M).astype(np.float64)
+    ph = rng.uniform(0, 2 * np.pi, M)
+    amp = rng.uniform(1e-3, 5e-3, M)
+    f = amp[:, None] * np.sin(2 * np.pi * k[:, None] * t[None, :] + ph[:, None])
+    f = f + 1e-3 * rng.standard_normal((M, nt))
+    if normalized:
+        f = (1 + f) / np.mean(1 + f, axis=1, keepdims=True) - 1
+    return t, f
 
 
 class ClockSampler(object):
@@ -224,6 +254,16 @@ def cpu_evals(hp, t, flux, n_eval, workload, flux_ens=None):
     return n_done / dt, kind, out
 
 
+def config_dict(args):
+    """The `config` object -- identical in both arms (b200 / reference) for the same command line."""
+    cfg = {"workload": workload_name(args), "nt": NT, "ydeg": 15, "scaling": args.scaling,
+           "prior": args.prior,
+           "l2": "per-step working set (one 8 MB covariance matrix per sample) is far larger than "
+                 "the 126 MB L2; no explicit flush needed"}
+    cfg["batch_total" if args.scaling == "strong" else "batch_per_gpu"] = args.batch
+    return cfg
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -231,10 +271,10 @@ def run_reference(args):
     from oracle import sp_oracle as so  # noqa: F401  (fails loudly if the oracle is missing)
 
     B = args.batch
-    hp, t, flux, fens = synthetic_inputs(max(B, 64), seed=1234)
+    hp, t, flux, fens = synthetic_inputs(max(B, 64), seed=1234, prior=args.prior)
     n_eval = args.ref_evals
     if args.workload == "ensemble":
-        fens = np.tile(fens, (128, 1))[:1024]
+        t, fens = ensemble_flux(1024)
     for _ in range(args.warmup):
         cpu_evals(hp, t, flux, 1, args.workload, fens[:8])
     rates = []
@@ -252,9 +292,9 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "evals/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / max(args.steps, 1),
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": workload_name(args), "nt": NT, "ydeg": 15, "batch_per_gpu": B},
+        "config": config_dict(args),
         "cpu_baseline": {"value": value, "unit": "evals/s", "cores": cores, "kind": kind,
                          "sample": sample},
         "e2e": {"value": value, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -266,9 +306,18 @@ def run_reference(args):
 
 def workload_name(args):
     if args.workload == "sweep":
-        return ("configs[2]: MCMC-style sweep of %d hyperparameter samples per GPU x 1 light curve "
-                "(nt=1000), marginalize_over_inclination=True, normalized=True, u=[0.4,0.26]"
-                % args.batch)
+        split = ("ONE batch sharded B/N per GPU (strong scaling)" if args.scaling == "strong"
+                 else "%d samples PER GPU (weak scaling)" % args.batch)
+        pr = PRIORS[args.prior]
+        return ("configs[2]: MCMC-style sweep of %d hyperparameter samples x 1 light curve (nt=1000), "
+                "marginalize_over_inclination=True, normalized=True, u=[0.4,0.26]; %s; "
+                "hyperparameters ~ U: r[%g,%g] c[%g,%g] n[%g,%g] mu[%g,%g] sigma[%g,%g] (%s)"
+                % (args.batch, split, pr["r"][0], pr["r"][1], pr["c"][0], pr["c"][1], pr["n"][0],
+                   pr["n"][1], pr["mu"][0], pr["mu"][1], pr["sigma"][0], pr["sigma"][1],
+                   "the reference's stability prior, joss/figures/stability.py:28-35"
+                   if args.prior == "full" else
+                   "the reference's stability prior with r, c, n narrowed so that the normalised "
+                   "process stays inside z <= 0.023; the full prior is phases.full_prior"))
     return ("configs[1]: ensemble of 1024 light curves (nt=1000) sharing one hyperparameter set: "
             "one K factorisation + 1024-RHS forward solve")
 
@@ -372,6 +421,143 @@ def sample_ylm_phase(spb, _lib, ctx, dev, torch, dmma_peak, nsamples=1000000, re
     return out
 
 
+def _event_ms(pairs):
+    return float(np.sum([a.elapsed_time(b) for a, b in pairs])) if pairs else float("nan")
+
+
+def ensemble_phase(spb, dev, torch, dmma_peak, reps=5):
+    """configs[1]: 1024 light curves sharing one hyperparameter set, through the public API: one
+    factorisation (8-CTA cluster kernel) + the 1024-row forward solve spread over the GPU."""
+    gpath = os.path.join(ROOT, "tests", "golden", "ensemble_nt1000.npz")
+    t, f = ensemble_flux(1024)
+    td, fd = torch.tensor(t, device=dev), torch.tensor(f, device=dev)
+    stage = {}
+    times = []
+    ll = None
+    for r in range(reps + 3):
+        gp = spb.StarryProcess(r=10.0, mu=30.0, sigma=5.0, c=0.1, n=10.0)
+        if r >= 3:
+            gp._stage_ms = stage
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        ll = gp.log_likelihood(td, fd, 1e-6, i=60.0, p=1.0, u=U_LD)
+        e1.record()
+        torch.cuda.synchronize()
+        if r >= 3:
+            times.append(e0.elapsed_time(e1))
+    ms = float(np.mean(times))
+    chol_ms = _event_ms(stage.get("cholesky", [])) / reps
+    flops = NT ** 3 / 3.0 + NT ** 2 * 1024.0
+    out = {"workload": "configs[1]: ensemble of 1024 synthetic light curves (nt=1000) sharing one "
+                       "hyperparameter set; one K factorisation + 1024-RHS forward solve, whole "
+                       "log_likelihood call (moments, kernel, assembly included)",
+           "value": 1024.0 / (ms * 1e-3), "unit": "curve-evals/s", "ms_per_call": ms,
+           "roofline": {"bound": "tensor", "kernel": "potrf_cluster_kernel<8> + potrf_lnlike_kernel "
+                        "(MODE_SOLVE)", "achieved": flops / (chol_ms * 1e-3) / 1e12, "peak": dmma_peak,
+                        "unit": "TFLOP/s", "frac": flops / (chol_ms * 1e-3) / 1e12 / dmma_peak,
+                        "ms_per_launch": chol_ms, "algorithmic_flops_per_launch": flops,
+                        "note": "nt^3/3 + nt^2 M (one forward solve: |L^-1 r|^2 needs no back "
+                                "substitution); ONE 1000x1000 factorisation is latency-bound (16 "
+                                "dependent panels on an 8-SM cluster), not a throughput workload"}}
+    if os.path.exists(gpath):
+        ref = float(np.load(gpath)["lnlike_m1_n1"])
+        out["parity_vs_reference_golden"] = {"rel": abs(ll.item() - ref) / abs(ref), "tolerance": 1e-8}
+    return out
+
+
+def long_baseline_phase(spb, dev, torch, dmma_peak, B=512, reps=2):
+    """configs[3]: 512 hyperparameter samples x one nt = 4096 limb-darkened light curve, conditional
+    on i = 60 deg: per sample A Sigma A^T (9.1 GF) + a 4096 x 4096 Cholesky (22.9 GF)."""
+    g1 = os.path.join(ROOT, "tests", "golden", "longbaseline_nt4096.npz")
+    g2 = os.path.join(ROOT, "tests", "golden", "longbaseline_nt4096_r2.npz")
+    if not (os.path.exists(g1) and os.path.exists(g2)):
+        return None
+    lb, r2 = np.load(g1), np.load(g2)
+    nt = 4096
+    ns = len(r2["r"])
+    rng = np.random.default_rng(41)
+    hp = {k: np.concatenate([r2[k], rng.uniform(PRIORS["narrow"][k][0], PRIORS["narrow"][k][1],
+                                                B - ns)]) for k in ("r", "c", "n", "mu", "sigma")}
+    hd = {k: torch.tensor(v, device=dev) for k, v in hp.items()}
+    td, fd = torch.tensor(lb["t"], device=dev), torch.tensor(lb["flux"], device=dev)
+    bvar = torch.zeros(B, dtype=torch.float64, device=dev)
+    bvar[:ns] = torch.tensor(r2["baseline_var"], device=dev)
+    stage = {}
+    times = []
+    ll = None
+    for r in range(reps + 1):
+        gp = spb.StarryProcess(marginalize_over_inclination=False, normalized=False, **hd)
+        if r >= 1:
+            gp._stage_ms = stage
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        ll = gp.log_likelihood(td, fd, 1e-6, i=60.0, p=1.0, u=U_LD, baseline_var=bvar)
+        e1.record()
+        torch.cuda.synchronize()
+        if r >= 1:
+            times.append(e0.elapsed_time(e1))
+        del gp
+    ms = float(np.mean(times))
+    chol_ms = _event_ms(stage.get("cholesky", [])) / reps
+    flops = B * (nt ** 3 / 3.0 + nt ** 2 * 1.0)
+    flops_all = flops + B * (2.0 * nt * 256 * 256 + 1.0 * nt * nt * 256)
+    got = ll[:ns].cpu().numpy()
+    ref = r2["lnlike_n0"]
+    fin = np.isfinite(ref)
+    return {"workload": "configs[3]: 512 hyperparameter samples x 1 light curve of nt = 4096, "
+                        "u=[0.4,0.26], conditional on i = 60 deg, unnormalised (one element non-PD by "
+                        "construction); K = 134 MB per sample (68.7 GB for the batch, one chunk)",
+            "value": B / (ms * 1e-3), "unit": "evals/s", "ms_per_call": ms,
+            "algorithmic_tflops_whole_call": flops_all / (ms * 1e-3) / 1e12,
+            "roofline": {"bound": "tensor", "kernel": "potrf_lnlike_kernel (nt = 4096)",
+                         "achieved": flops / (chol_ms * 1e-3) / 1e12, "peak": dmma_peak,
+                         "unit": "TFLOP/s", "frac": flops / (chol_ms * 1e-3) / 1e12 / dmma_peak,
+                         "ms_per_launch": chol_ms, "algorithmic_flops_per_launch": flops},
+            "parity_vs_reference_golden": {
+                "max_rel": float(np.max(np.abs(got[fin] - ref[fin]) / np.abs(ref[fin]))), "n": int(ns),
+                "neg_inf_pattern_equal": bool(np.array_equal(np.isneginf(got), np.isneginf(ref))),
+                "tolerance": 1e-8}}
+
+
+def full_prior_phase(spb, dev, torch, B=4096, reps=3):
+    """Second line item: the same sweep with the reference's FULL stability prior
+    (SURVEY.md section 8(d)): most draws leave the validity range of the normalised process and
+    return -inf by the z-rule (sp.py:1178-1183) -- the work per evaluation is the same."""
+    hp, t, flux, _ = synthetic_inputs(B, seed=4321, prior="full")
+    hd = {k: torch.tensor(v, device=dev) for k, v in hp.items()}
+    td, fd = torch.tensor(t, device=dev), torch.tensor(flux, device=dev)
+    times = []
+    ll = None
+    for r in range(reps + 2):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        ll = spb.StarryProcess(**hd).log_likelihood(td, fd, 1e-6, p=1.0, u=U_LD)
+        e1.record()
+        torch.cuda.synchronize()
+        if r >= 2:
+            times.append(e0.elapsed_time(e1))
+    ms = float(np.mean(times))
+    got = ll.cpu().numpy()
+    out = {"workload": "configs[2] with the reference's full stability prior: r[10,45] c[0,1] "
+                       "n[1,50] mu[0,85] sigma[5,40], %d draws, seed 4321" % B,
+           "value": B / (ms * 1e-3), "unit": "evals/s", "ms_per_step": ms,
+           "finite_fraction": float(np.isfinite(got).mean())}
+    gpath = os.path.join(ROOT, "tests", "golden", "bench_fullprior_seed4321.npz")
+    if os.path.exists(gpath):
+        ref = np.load(gpath)["lnlike_m1_n1"]
+        n = len(ref)
+        fin = np.isfinite(ref)
+        out["parity_vs_reference_golden"] = {
+            "n": int(n), "neg_inf_pattern_equal": bool(np.array_equal(np.isneginf(got[:n]),
+                                                                     np.isneginf(ref))),
+            "max_rel": float(np.max(np.abs(got[:n][fin] - ref[fin]) / np.abs(ref[fin])))
+            if fin.any() else None,
+            "tolerance": 5e-7,
+            "note": "broad prior, marginalised branch: the reference's own eigensolver noise floor "
+                    "(DESIGN.md, numerical fragility)"}
+    return out
+
+
 # ------------------------------------------------------------------------------------------
 def run_b200(args):
     import torch
@@ -390,7 +576,7 @@ def run_b200(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     B = args.batch
-    hp, t, flux, fens = synthetic_inputs(B, seed=1234 + rank)
+    strong = args.scaling == "strong"
     ctx = spb.get_context(local)
     lib, h = ctx.lib, ctx.handle
 
@@ -400,47 +586,59 @@ def run_b200(args):
     _lib.check(lib.spb_dmma_peak(h, 40000, ctypes.byref(tf), ctypes.byref(ms)))
     dmma_peak = tf.value
 
+    def make_inputs(seed):
+        hp_, t_, flux_, _ = synthetic_inputs(B, seed=seed, prior=args.prior)
+        return hp_, t_, flux_
+
+    # strong: the SAME full batch on every rank (each evaluates its shard_range slice);
+    # weak: every rank draws its own batch
+    hp, t, flux = make_inputs(1234 if strong else 1234 + rank)
     t_d = torch.tensor(t, device=dev)
     f_d = torch.tensor(flux, device=dev)
     hp_d = {k: torch.tensor(v, device=dev) for k, v in hp.items()}
     if args.workload == "ensemble":
-        fens = np.tile(fens, (128, 1))[:1024]
+        t_e, fens = ensemble_flux(1024)
+        t_d = torch.tensor(t_e, device=dev)
         fe_d = torch.tensor(fens, device=dev)
+        fe_h = torch.tensor(fens).pin_memory()
+        t = t_e
     # pinned host copies for the end-to-end arm
     hp_h = {k: torch.tensor(v).pin_memory() for k, v in hp.items()}
     t_h = torch.tensor(t).pin_memory()
     f_h = torch.tensor(flux).pin_memory()
-    out_h = torch.empty(B, dtype=torch.float64).pin_memory()
-    if args.workload == "ensemble":
-        fe_h = torch.tensor(fens).pin_memory()
+    out_h = torch.empty(B * (1 if strong else world), dtype=torch.float64).pin_memory()
+    fid = dict(r=10.0, mu=30.0, sigma=5.0, c=0.1, n=10.0)
 
     stage_ms = {}
 
+    def sweep_step(hyper, tt, ff, strong_):
+        if strong_:
+            # the product call: shard_range slice -> StarryProcess -> all-gather of B doubles
+            return spb.log_likelihood_sharded(hyper, tt, ff, 1e-6, p=1.0, u=U_LD)
+        ll_ = spb.StarryProcess(**hyper).log_likelihood(tt, ff, 1e-6, p=1.0, u=U_LD)
+        return spb.gather_lnlike(ll_, equal_shards=True) if world > 1 else ll_
+
     def step_device():
         if args.workload == "sweep":
-            gp = spb.StarryProcess(**hp_d)
-            gp._stage_ms = stage_ms
-            ll = gp.log_likelihood(t_d, f_d, 1e-6, p=1.0, u=U_LD)
-        else:
-            gp = spb.StarryProcess(r=10.0, mu=30.0, sigma=5.0, c=0.1, n=10.0)
-            gp._stage_ms = stage_ms
-            ll = gp.log_likelihood(t_d, fe_d, 1e-6, p=1.0, u=U_LD).reshape(1)
+            return sweep_step(hp_d, t_d, f_d, strong)
         if world > 1:
-            ll = spb.gather_lnlike(ll, equal_shards=True)
-        return ll
+            return spb.ensemble_log_likelihood_sharded(fid, t_d, fe_d, 1e-6, p=1.0, u=U_LD).reshape(1)
+        return spb.StarryProcess(**fid).log_likelihood(t_d, fe_d, 1e-6, p=1.0, u=U_LD).reshape(1)
 
     def step_e2e():
         if args.workload == "sweep":
-            hd = {k: v.to(dev, non_blocking=True) for k, v in hp_h.items()}
-            gp = spb.StarryProcess(**hd)
-            ll = gp.log_likelihood(t_h.to(dev, non_blocking=True), f_h.to(dev, non_blocking=True),
-                                   1e-6, p=1.0, u=U_LD)
-            out_h.copy_(ll, non_blocking=True)
+            # host buffers in: the shard's hyperparameters, t and the light curve are copied H2D
+            # inside the call; the gathered log-likelihood vector is read back D2H
+            ll_ = sweep_step(hp_h, t_h, f_h, strong)
+            out_h[: ll_.numel()].copy_(ll_, non_blocking=True)
         else:
-            gp = spb.StarryProcess(r=10.0, mu=30.0, sigma=5.0, c=0.1, n=10.0)
-            ll = gp.log_likelihood(t_h.to(dev, non_blocking=True), fe_h.to(dev, non_blocking=True),
-                                   1e-6, p=1.0, u=U_LD).reshape(1)
-            out_h[:1].copy_(ll, non_blocking=True)
+            if world > 1:
+                ll_ = spb.ensemble_log_likelihood_sharded(fid, t_h, fe_h, 1e-6, p=1.0,
+                                                          u=U_LD).reshape(1)
+            else:
+                ll_ = spb.StarryProcess(**fid).log_likelihood(t_h, fe_h, 1e-6, p=1.0,
+                                                              u=U_LD).reshape(1)
+            out_h[:1].copy_(ll_, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         return out_h
 
@@ -463,30 +661,50 @@ def run_b200(args):
             dist.all_reduce(ms_, op=dist.ReduceOp.MAX)
         return ms_.item(), out
 
-    for _ in range(max(args.warmup, 3)):
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
         step_device()
-    stage_ms.clear()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    spb.StarryProcess._stage_ms = stage_ms      # per-stage CUDA events on the launching stream
     l0 = ctx.launches()
     total_ms, ll = timed(step_device, args.steps)
     launches = ctx.launches() - l0
+    spb.StarryProcess._stage_ms = None
     clocks = sampler.stop() if rank == 0 else None
     stage_snapshot = {k: list(v) for k, v in stage_ms.items()}
     for _ in range(2):
         step_e2e()
     e2e_ms, _ = timed(step_e2e, args.steps)
 
-    units = (B if args.workload == "sweep" else 1024) * world
+    if args.workload == "sweep":
+        units = B if strong else B * world
+        nloc = -(-B // world) if strong else B
+        h2d = world * (5 * nloc + 2 * NT) * 8          # job total: every rank copies its shard
+        d2h = world * 8 * units                        # every rank reads the gathered vector
+    else:
+        units = 1024
+        h2d = world * (-(-1024 // world) * NT + NT) * 8
+        d2h = world * 8
     value = units * args.steps / (total_ms * 1e-3)
     e2e_value = units * args.steps / (e2e_ms * 1e-3)
-    if args.workload == "sweep":
-        h2d = (5 * B + 2 * NT) * 8
-        d2h = 8 * B
-    else:
-        h2d = (1024 * NT + NT) * 8
-        d2h = 8
+
+    # ---- the other scaling mode, for the record (sweep workload, N > 1 only)
+    other = None
+    if args.workload == "sweep" and world > 1 and not args.no_phases:
+        o_strong = not strong
+        hp_o, t_o, f_o = synthetic_inputs(B, seed=1234 if o_strong else 1234 + rank,
+                                          prior=args.prior)[:3]
+        hp_od = {k: torch.tensor(v, device=dev) for k, v in hp_o.items()}
+        ksteps = max(2, min(args.steps, 5))
+        for _ in range(2):
+            sweep_step(hp_od, t_d, f_d, o_strong)
+        o_ms, _ = timed(lambda: sweep_step(hp_od, t_d, f_d, o_strong), ksteps)
+        o_units = B if o_strong else B * world
+        other = {"scaling": "strong" if o_strong else "weak", "value": o_units * ksteps / (o_ms * 1e-3),
+                 "unit": "evals/s", "ms_per_step": o_ms / ksteps, "steps": ksteps,
+                 ("batch_total" if o_strong else "batch_per_gpu"): B}
 
     if rank != 0:
         if world > 1:
@@ -494,19 +712,19 @@ def run_b200(args):
         return 0
 
     # ---- roofline of the dominant kernel (batched Cholesky): events recorded on the launching
-    # stream around every launch inside the timed region
+    # stream around every launch inside the timed region (rank 0's shard)
     torch.cuda.synchronize()
     chol = stage_snapshot.get("cholesky", [])
-    chol_ms = float(np.sum([a.elapsed_time(b) for a, b in chol])) if chol else float("nan")
+    chol_ms = _event_ms(chol)
     n_launch = max(len(chol), 1)
+    b0, b1 = spb.shard_range(B, 0, world) if strong else (0, B)
+    n_mat = b1 - b0                                    # matrices per step on this GPU
     if args.workload == "sweep":
-        flops_total = args.steps * B * (NT ** 3 / 3.0 + NT ** 2 * 1.0)
+        flops_total = args.steps * n_mat * (NT ** 3 / 3.0 + NT ** 2 * 1.0)
     else:
-        flops_total = args.steps * (NT ** 3 / 3.0 + NT ** 2 * 1024.0)
+        flops_total = args.steps * (NT ** 3 / 3.0 + NT ** 2 * 1024.0 / world)
     achieved = flops_total / (chol_ms * 1e-3) / 1e12 if chol else None
-    shares = {}
-    for k, v in stage_snapshot.items():
-        shares[k] = float(np.sum([a.elapsed_time(b) for a, b in v]))
+    shares = {k: _event_ms(v) for k, v in stage_snapshot.items()}
     roofline = {
         "bound": "tensor", "kernel": "potrf_lnlike_kernel (DMMA m8n8k4.f64 left-looking Cholesky + "
                                      "augmented forward solve)",
@@ -514,12 +732,13 @@ def run_b200(args):
         "frac": (achieved / dmma_peak) if achieved else None,
         "traffic": ncu_traffic("potrf_lnlike_kernel", flops_total / n_launch / (NT ** 3 / 3.0 + NT ** 2)
                                if args.workload == "sweep" else 1.0),
-        "traffic_note": "DRAM read+write bytes per launch: per-matrix figure of the ncu capture "
-                        "profiles/r01_ncu_sweep_B592_final2.txt (profiles/ncu_traffic.json) x matrices in the launch",
+        "traffic_note": "DRAM read+write bytes per launch: per-matrix figure of the committed ncu "
+                        "capture (profiles/ncu_traffic.json) x matrices in the launch",
         "peak_source": "FP64 mma.sync peak measured in this run by spb_dmma_peak "
                        "(MEASURED_PEAKS.json has no fp64 entry; cuBLAS DGEMM 8192^3 on this pool: "
                        "35.5 TFLOP/s)",
         "launches_timed": n_launch, "ms_per_launch": chol_ms / n_launch if chol else None,
+        "matrices_per_launch": n_mat if args.workload == "sweep" else 1,
         "algorithmic_flops_per_launch": flops_total / n_launch,
         "stage_ms_total": shares,
     }
@@ -528,26 +747,37 @@ def run_b200(args):
                             "cluster, latency-bound by its 16 dependent panels) plus 1024 "
                             "right-hand-side rows: a latency workload, not a throughput one -- the "
                             "headline roofline is the sweep workload's")
-    # ---- design-matrix phase (BASELINE configs[4]: nt = 1e5 timestamps x 64 inclinations), timed in
-    # the same process with CUDA events on the launching stream, against the measured HBM peak
-    phases = {"design_matrix": design_phase(spb, _lib, ctx, dev, torch),
-              "sample_ylm": sample_ylm_phase(spb, _lib, ctx, dev, torch, dmma_peak)}
-    # ---- CPU baseline: bounded sample of the same workload on the host cores
-    cb_value, cb_kind, cb_out = cpu_evals(hp, t, flux, args.cpu_evals, args.workload, fens)
-    parity = None
+    phases = {}
+    cpu_baseline = None
     parity_golden = None
+    if other is not None:
+        phases[other["scaling"] + "_scaling"] = other
+    if world == 1 and not args.no_phases:
+        # ---- the other configs of BASELINE.json, timed in the same process with CUDA events on the
+        # launching stream (each carries its own roofline / parity entry)
+        def guarded(name, fn):
+            # a failing secondary config must not take the headline line down with it
+            try:
+                torch.cuda.empty_cache()
+                res = fn()
+                if res is not None:
+                    phases[name] = res
+            except Exception as exc:  # noqa: BLE001
+                phases[name] = {"error": "%s: %s" % (type(exc).__name__, exc)}
+                torch.cuda.synchronize()
+
+        guarded("design_matrix", lambda: design_phase(spb, _lib, ctx, dev, torch))
+        guarded("sample_ylm", lambda: sample_ylm_phase(spb, _lib, ctx, dev, torch, dmma_peak))
+        if args.workload == "sweep":
+            guarded("ensemble_1024", lambda: ensemble_phase(spb, dev, torch, dmma_peak))
+            guarded("full_prior", lambda: full_prior_phase(spb, dev, torch))
+            guarded("long_baseline_nt4096", lambda: long_baseline_phase(spb, dev, torch, dmma_peak))
     if args.workload == "sweep":
         llall = ll.cpu().numpy()
-        llh = llall[: args.cpu_evals]
-        ref = np.array(cb_out)
-        fin = np.isfinite(ref)
-        parity = float(np.max(np.abs(llh[fin] - ref[fin]) / np.abs(ref[fin]))) if fin.any() else None
-        # the same first samples evaluated by the UNMODIFIED reference in the build container
-        # (tests/golden/bench_sweep_seed1234.npz, oracle/gen_golden_bench.py).  This is the parity
-        # figure: the live oracle on this host is only reproducible to ~1e-6 across CPUs
-        # (DESIGN.md "numerical fragility"), the fixture is what every golden file was made with.
+        # the first samples evaluated by the UNMODIFIED reference in the build container
+        # (tests/golden/bench_sweep_seed1234.npz, oracle/gen_golden_bench.py): the pinned parity figure
         gpath = os.path.join(ROOT, "tests", "golden", "bench_sweep_seed1234.npz")
-        if os.path.exists(gpath):
+        if os.path.exists(gpath) and args.prior == "narrow" and (strong or world == 1):
             gref = np.load(gpath)["lnlike_m1_n1"]
             ng = min(len(gref), B)
             gref = gref[:ng]
@@ -556,23 +786,50 @@ def run_b200(args):
             gerr = np.abs(llall[:ng][gfin] - gref[gfin]) / np.abs(gref[gfin])
             parity_golden = {
                 "max_rel": float(np.max(gerr)), "median_rel": float(np.median(gerr)),
-                "n": int(ng), "neg_inf_pattern_equal": same_inf, "tolerance": 1e-8}
-    cpu_baseline = {
-        "value": cb_value, "unit": "evals/s", "cores": host_cores(), "kind": cb_kind,
-        "sample": "%d evaluations of the same workload, reference C++ + NumPy/SciPy on the host, one "
-                  "worker process per core" % (args.cpu_evals if args.workload == "sweep" else 1024),
-        "max_rel_lnlike_diff_vs_gpu_on_sample": parity,
-        "note": "live oracle on THIS host; the reference algorithm moves by up to ~3e-6 between "
-                "CPUs (LAPACK kernel selection), see parity_vs_reference_golden for the pinned check",
-    }
+                "n": int(ng), "neg_inf_pattern_equal": same_inf, "tolerance": 1e-8,
+                "longitude_basis": "pinned"}
+    if world == 1:
+        # ---- CPU baseline: bounded sample of the same workload on the host cores (rank 0, N = 1)
+        cb_value, cb_kind, cb_out = cpu_evals(hp, t, flux, args.cpu_evals, args.workload,
+                                              fens if args.workload == "ensemble" else None)
+        parity = parity_host = None
+        if args.workload == "sweep":
+            llh = llall[: args.cpu_evals]
+            ref = np.array(cb_out)
+            fin = np.isfinite(ref)
+            parity = float(np.max(np.abs(llh[fin] - ref[fin]) / np.abs(ref[fin]))) if fin.any() else None
+            # parity on THIS host: the CUDA path with this host's own longitude eigenvector table
+            # against the oracle evaluated in THIS process (same NumPy eigh call, same BLAS threads)
+            from oracle import sp_oracle as so
+
+            nh = min(16, args.cpu_evals)
+            gph = spb.StarryProcess(longitude_basis="host", **{k: hp_d[k][:nh] for k in hp_d})
+            ll_host = gph.log_likelihood(t_d, f_d, 1e-6, p=1.0, u=U_LD).cpu().numpy()
+            native = "ref" if so.ref_available(15, 2) else "port"
+            ref_h = np.array([so.OracleProcess(native=native, **{k: hp[k][s] for k in hp})
+                              .log_likelihood(t, flux, 1e-6, p=1.0, u=U_LD) for s in range(nh)])
+            finh = np.isfinite(ref_h)
+            parity_host = float(np.max(np.abs(ll_host[finh] - ref_h[finh]) / np.abs(ref_h[finh]))) \
+                if finh.any() else None
+        cpu_baseline = {
+            "value": cb_value, "unit": "evals/s", "cores": host_cores(), "kind": cb_kind,
+            "sample": "%d evaluations of the same workload, reference C++ + NumPy/SciPy on the host, "
+                      "one worker process per core"
+                      % (args.cpu_evals if args.workload == "sweep" else 1024),
+            "max_rel_lnlike_diff_vs_gpu_on_sample": parity,
+            "max_rel_lnlike_diff_vs_gpu_host_basis": parity_host,
+            "note": "first figure: GPU with the PINNED longitude table vs the oracle on this host's "
+                    "worker processes (the reference algorithm moves by up to ~3e-6 between hosts / "
+                    "BLAS thread counts through that table; parity_vs_reference_golden is the pinned "
+                    "check).  second figure: GPU with longitude_basis='host' vs the oracle in this "
+                    "process, 16 samples -- tolerance 1e-8",
+        }
     line = {
         "metric": METRIC, "value": value, "unit": "evals/s", "n_gpus": world, "steps": args.steps,
-        "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "warmup": warm, "ms_per_step": total_ms / args.steps,
+        "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": workload_name(args), "nt": NT, "ydeg": 15, "batch_per_gpu": B,
-                   "l2": "per-step working set (B x 8 MB covariance matrices) is far larger than "
-                         "the 126 MB L2; no explicit flush needed"},
+        "config": config_dict(args),
         "e2e": {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps},
         "gpu_launches": int(launches),
@@ -614,7 +871,15 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="sweep", choices=["sweep", "ensemble"])
-    ap.add_argument("--batch", type=int, default=4096, help="hyperparameter samples per GPU")
+    ap.add_argument("--batch", type=int, default=4096,
+                    help="hyperparameter samples: in total (strong) or per GPU (weak)")
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
+                    help="strong: ONE batch sharded across the GPUs (configs[2]); weak: one batch per GPU")
+    ap.add_argument("--prior", default="narrow", choices=sorted(PRIORS),
+                    help="hyperparameter prior of the sweep (see PRIORS)")
+    ap.add_argument("--no-phases", action="store_true",
+                    help="skip the secondary configs (design matrix, sample_ylm, ensemble, nt=4096, "
+                         "full prior, the other scaling mode)")
     ap.add_argument("--cpu-evals", type=int, default=64, help="CPU-baseline sample size")
     ap.add_argument("--ref-evals", type=int, default=96, help="reference arm: evaluations per step")
     args = ap.parse_args()

@@ -123,8 +123,9 @@ int spb_design_matrix(spb_context *ctx, int I, int nt, const double *t, const do
  * ops/wigner/special_tensordotRz.cc:10-65 (wigner.h:410-459):
  *   mean_ylm (B,256), cov_ylm (B,256,256), rTA1 (256) [shared], t (nt), period p, covpts
  *   -> gp_mean (B) (the scalar flux mean), kernel coefficient table coef (B, 4, covpts+1),
- *      var (B) (the nt == 1 variance).  The dense (nt,nt) covariance is then either materialised
- *      by spb_kernel_matrix or generated on the fly inside spb_lnlike_marginal.
+ *      var (B) (the nt == 1 variance).  The dense (nt,nt) covariance is then materialised from the
+ *      table by spb_assemble_marginal (and the rectangular K(ts, t) of predict by
+ *      spb_cross_marginal).
  *
  * Conditional on inclination -- flux.py:335-343:
  *   K[b] = A cov_ylm[b] A^T, gp_mean[b] = (A mean_ylm[b])[0];  A: (nt,256) shared by the batch
@@ -271,6 +272,11 @@ int spb_cross_marginal(spb_context *ctx, int B, int nts, int nt, const double *t
  * micro-benchmark used as the roofline denominator; returns achieved TFLOP/s via *tflops_host.
  * ------------------------------------------------------------------------------------------- */
 int spb_dmma_peak(spb_context *ctx, int iters, double *tflops_host, double *ms_host);
+/* Run-time switches for A/B measurements and the bit-for-bit stress tests (defaults: everything on;
+ * the environment variables SPB_NO_TMA / SPB_NO_CLUSTER set the defaults at spb_create):
+ *   "cholesky_tma"     1 | 0   operand ring of the batched Cholesky fed by TMA | by cp.async
+ *   "cholesky_cluster" 1 | 0   few matrices: one matrix per thread-block cluster | per CTA       */
+int spb_set_option(spb_context *ctx, const char *name, int value);
 int spb_launch_count(const spb_context *ctx, long long *count_host);
 
 #ifdef __cplusplus

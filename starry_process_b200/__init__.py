@@ -7,7 +7,8 @@ or a CUDA device is missing.
 """
 from .sp import (StarryProcess, StarryProcessSum, beta2gauss, defaults, gauss2beta,  # noqa: F401
                  get_context)
-from .distributed import gather_lnlike, shard_range  # noqa: F401
+from .distributed import (design_matrix_sharded, ensemble_log_likelihood_sharded,  # noqa: F401
+                          gather_lnlike, log_likelihood_sharded, shard_range)
 from .temporal import ExpSquaredKernel, Matern32Kernel  # noqa: F401
 
 __version__ = "0.1.0"

@@ -73,6 +73,7 @@ PROTOTYPES = {
     "spb_cross_marginal": (_I, [_P, _I, _I, _I, _P, _P, _D, _I, _P, _P, _LL, _P, _I, _LL, _P]),
     "spb_dmma_peak": (_I, [_P, _I, _c.POINTER(_D), _c.POINTER(_D)]),
     "spb_launch_count": (_I, [_P, _c.POINTER(_LL)]),
+    "spb_set_option": (_I, [_P, _c.c_char_p, _I]),
 }
 
 _lib = None

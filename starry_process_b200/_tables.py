@@ -327,13 +327,36 @@ def _matrix_sqrt(Q, neig):
 
 
 _CACHE = {}
+LONGITUDE_BASES = ("pinned", "host")
 
 
-def build_tables(use_pinned_longitude=True):
-    """Returns (blob float64[_TOTAL], offsets dict)."""
-    if "blob" in _CACHE:
-        return _CACHE["blob"], offsets()
+def build_tables(longitude_basis="pinned", use_pinned_longitude=None):
+    """Returns (blob float64[_TOTAL], offsets dict).
+
+    ``longitude_basis`` selects the hyperparameter-independent longitude eigenvector table
+    ``U_lon = matrix_sqrt(Q_lon)`` (longitude.py:9-49 -> integrals.py:116-124 -> math.py:121-139):
+
+    * ``"pinned"`` (default): the table shipped in ``data/longitude_U_ydeg15.npy`` (regenerate it
+      with ``scripts/gen_longitude_U.py``; provenance in the ``.json`` next to it).  ``Q_lon`` has
+      eigenvalues at the 1e-15 clip whose eigenvectors depend on the LAPACK build / thread count, and
+      the reference's lnlike moves by up to 3e-6 with them; the pinned table makes every host
+      reproduce the values of the build container that generated the golden fixtures.
+    * ``"host"``: ``numpy.linalg.eigh`` on THIS host, exactly what the reference (and the CPU
+      oracle) computes in this process -- the basis to use when comparing against a reference run on
+      the same machine.
+    """
+    if use_pinned_longitude is not None:   # round-1 spelling
+        longitude_basis = "pinned" if use_pinned_longitude else "host"
+    if longitude_basis not in LONGITUDE_BASES:
+        raise ValueError("longitude_basis must be one of %r" % (LONGITUDE_BASES,))
+    if ("blob", longitude_basis) in _CACHE:
+        return _CACHE[("blob", longitude_basis)], offsets()
     off = offsets()
+    if "common" in _CACHE:
+        blob = _CACHE["common"].copy()
+        _put_longitude(blob, off, longitude_basis)
+        _CACHE[("blob", longitude_basis)] = blob
+        return blob, off
     blob = np.zeros(off["_TOTAL"])
 
     def put(name, arr):
@@ -397,40 +420,8 @@ def build_tables(use_pinned_longitude=True):
     put("LAT_H", H)
     put("LAT_R0", R0)
 
-    # ---- longitude (longitude.py:9-49, integrals.py:116-124)
-    R_lon = wigner_poly(YDEG, 1, 0, 1, 0)
+    # ---- longitude (longitude.py:9-49, integrals.py:116-124): filled per basis by _put_longitude
     n4 = 4 * YDEG + 1
-    term = np.zeros((n4, n4))
-    for i in range(n4):
-        for j in range(0, n4, 2):
-            term[i, j] = _gamma(0.5 * (i + 1)) * _gamma(0.5 * (j + 1)) / _gamma(0.5 * (2 + i + j))
-    term /= np.pi
-    jj = m_of + l_of
-    ii = l_of - m_of
-    q_lon = term[jj, ii]
-    Q_lon = term[jj[:, None] + jj[None, :], ii[:, None] + ii[None, :]]
-    pinned = os.path.join(HERE, "data", "longitude_U_ydeg15.npy")
-    U_lon = _matrix_sqrt(Q_lon, NEIG)
-    if use_pinned_longitude and os.path.exists(pinned):
-        # U_lon contains eigenvectors of eigenvalues ~1e-15 whose values depend on the LAPACK
-        # build's rounding; the table generated in the build container is shipped so that every
-        # host reproduces the same constants ("numerical fragility").
-        U_pin = np.load(pinned)
-        if U_pin.shape == U_lon.shape:
-            U_lon = U_pin
-    T1 = np.zeros(NWIG)
-    TL = np.zeros(NEIG * NWIG)
-    pos = 0
-    for l in range(YDEG + 1):
-        w = 2 * l + 1
-        T1[nwig(l - 1):nwig(l)] = np.dot(R_lon[l], q_lon[l * l:(l + 1) ** 2]).reshape(-1)
-        # T[l][m', e2, m] = sum_k R[l][m', m, k] U[l^2 + k, e2]
-        Tl = np.swapaxes(np.dot(R_lon[l], U_lon[l * l:(l + 1) ** 2]), 1, 2)
-        TL[pos:pos + w * NEIG * w] = Tl.reshape(-1)
-        pos += w * NEIG * w
-    put("LON_T1", T1)
-    put("LON_T", TL)
-    _CACHE["U_lon"] = U_lon
 
     # ---- flux integrals (flux.py:107-179)
     def _G(j, i):
@@ -493,5 +484,60 @@ def build_tables(use_pinned_longitude=True):
     lam[15 ** 2:] = 1e-9
     put("LAMBDA", lam)
 
-    _CACHE["blob"] = blob
+    _CACHE["common"] = blob.copy()
+    _put_longitude(blob, off, longitude_basis)
+    _CACHE[("blob", longitude_basis)] = blob
     return blob, off
+
+
+def longitude_qQ():
+    """longitude.py:22-49: first / second moment integrals of the (uniform) longitude prior."""
+    l_of, m_of = _lm()
+    n4 = 4 * YDEG + 1
+    term = np.zeros((n4, n4))
+    for i in range(n4):
+        for j in range(0, n4, 2):
+            term[i, j] = _gamma(0.5 * (i + 1)) * _gamma(0.5 * (j + 1)) / _gamma(0.5 * (2 + i + j))
+    term /= np.pi
+    jj = m_of + l_of
+    ii = l_of - m_of
+    q_lon = term[jj, ii]
+    Q_lon = term[jj[:, None] + jj[None, :], ii[:, None] + ii[None, :]]
+    return q_lon, Q_lon
+
+
+PINNED_LONGITUDE = os.path.join(HERE, "data", "longitude_U_ydeg15.npy")
+
+
+def longitude_U(basis):
+    """``U_lon (256, 31)`` for the requested basis (see build_tables)."""
+    if basis == "pinned":
+        if not os.path.exists(PINNED_LONGITUDE):
+            raise RuntimeError("%s is missing: regenerate it with scripts/gen_longitude_U.py"
+                               % PINNED_LONGITUDE)
+        U = np.load(PINNED_LONGITUDE)
+        if U.shape != (N, NEIG):
+            raise RuntimeError("pinned longitude table has the wrong shape %r" % (U.shape,))
+        return U
+    return _matrix_sqrt(longitude_qQ()[1], NEIG)
+
+
+def _put_longitude(blob, off, basis):
+    if "R_lon" not in _CACHE:
+        _CACHE["R_lon"] = wigner_poly(YDEG, 1, 0, 1, 0)
+    R_lon = _CACHE["R_lon"]
+    q_lon, _ = longitude_qQ()
+    U_lon = longitude_U(basis)
+    T1 = np.zeros(NWIG)
+    TL = np.zeros(NEIG * NWIG)
+    pos = 0
+    for l in range(YDEG + 1):
+        w = 2 * l + 1
+        T1[nwig(l - 1):nwig(l)] = np.dot(R_lon[l], q_lon[l * l:(l + 1) ** 2]).reshape(-1)
+        # T[l][m', e2, m] = sum_k R[l][m', m, k] U[l^2 + k, e2]
+        Tl = np.swapaxes(np.dot(R_lon[l], U_lon[l * l:(l + 1) ** 2]), 1, 2)
+        TL[pos:pos + w * NEIG * w] = Tl.reshape(-1)
+        pos += w * NEIG * w
+    blob[off["LON_T1"]:off["LON_T1"] + NWIG] = T1
+    blob[off["LON_T"]:off["LON_T"] + NEIG * NWIG] = TL
+    _CACHE[("U_lon", basis)] = U_lon

@@ -205,7 +205,10 @@ __global__ void __launch_bounds__(256) norm_scalars_kernel(AsmParams p) {
     p.scal[4 * b + 2] = z * alpha;
     p.scal[4 * b + 3] = m;
     if (p.z_out) p.z_out[b] = z;
-    if (p.info && (z > p.nm.normalization_zmax)) atomicOr(&p.info[b], SPB_INFO_Z_RANGE);
+    // re-evaluated on every call, as the reference does (sp.py:1178-1183): z depends on t, i, p, u,
+    // so the bit is WRITTEN, not OR-ed into the process' persistent flags (one writer per element)
+    if (p.info)
+      p.info[b] = (p.info[b] & ~SPB_INFO_Z_RANGE) | ((z > p.nm.normalization_zmax) ? SPB_INFO_Z_RANGE : 0);
     mshare = m;
   }
   __syncthreads();
@@ -300,28 +303,25 @@ int run_assemble(spb_context *ctx, AsmParams &p, void *workspace, size_t workspa
   SPB_REQUIRE(p.nm.temporal_kind >= 0 && p.nm.temporal_kind <= 2, "assemble: unknown temporal kernel");
   SPB_REQUIRE(!p.nm.temporal_kind || p.nm.tau != nullptr, "assemble: temporal kernel without tau");
   SPB_REQUIRE(smW <= 200 * 1024, "assemble: nt too large for the shared-memory staging");
-  static bool attr_dev[64] = {false};   // function attributes are per device
-  bool &attr = attr_dev[ctx->device & 63];
-  if (!attr) {
-    SPB_CHECK_CUDA(cudaFuncSetAttribute(rowsum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        200 * 1024));
-    SPB_CHECK_CUDA(cudaFuncSetAttribute(write_kernel<false>,
-                                        cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    SPB_CHECK_CUDA(cudaFuncSetAttribute(write_kernel<true>,
-                                        cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr = true;
+  static spb_once_flag attr_once;   // function attributes are per device
+  {
+    const int st = spb_once_per_device(attr_once, ctx->device, [&]() -> int {
+      SPB_CHECK_CUDA(cudaFuncSetAttribute(rowsum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          200 * 1024));
+      SPB_CHECK_CUDA(cudaFuncSetAttribute(write_kernel<false>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      SPB_CHECK_CUDA(cudaFuncSetAttribute(write_kernel<true>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      SPB_CHECK_CUDA(cudaFuncSetAttribute(rowsum_sym_kernel<false>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      SPB_CHECK_CUDA(cudaFuncSetAttribute(rowsum_sym_kernel<true>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      return 0;
+    });
+    if (st) return st;
   }
   if (p.nm.normalized) {
     if (p.marginal) {
-      static bool attr2_dev[64] = {false};
-      bool &attr2 = attr2_dev[ctx->device & 63];
-      if (!attr2) {
-        SPB_CHECK_CUDA(cudaFuncSetAttribute(rowsum_sym_kernel<false>,
-                                            cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        SPB_CHECK_CUDA(cudaFuncSetAttribute(rowsum_sym_kernel<true>,
-                                            cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr2 = true;
-      }
       const size_t smS = smA + (size_t)8 * RS_CB * sizeof(double);
       SPB_REQUIRE(smS <= 200 * 1024, "assemble: nt too large for the shared-memory staging");
       dim3 gridS(RS_G, p.B);

@@ -4,12 +4,17 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <atomic>
+#include <mutex>
 #include <string>
 
 #include "../../include/spb200.h"
 
 #define SPB_LMAX 15
-#define SPB_NUM_COUNTERS 256
+// Ring of per-launch work counters / scratch slots.  A slot is reused after SPB_NUM_COUNTERS further
+// launches through the same context; a CUDA device cannot hold that many launches in flight (the
+// launch queues block the host long before), so two running kernels never share a slot.
+#define SPB_NUM_COUNTERS 4096
 #define SPB_SCRATCH_PER_SLOT 256  // doubles per launch slot (cluster Cholesky: one per CTA)
 #define SPB_NSM_DEFAULT 148
 
@@ -18,7 +23,11 @@ struct spb_context {
   int num_sms;
   double *d_tables;       // device copy of the packed constant blob
   size_t tables_count;
-  long long launches;     // number of kernels launched through this context
+  std::atomic<long long> launches;   // number of kernels launched through this context
+  // run-time switches (spb_set_option): A/B measurements and the bit-for-bit stress tests
+  int opt_no_tma;         // Cholesky operand ring: cp.async instead of TMA
+  int opt_no_cluster;     // Cholesky: never use the one-matrix-per-cluster kernel
+  int max_active_clusters[3];   // cudaOccupancyMaxActiveClusters for cluster sizes 8, 4, 2 (-1: unknown)
   // ring of work counters for kernels that claim their work items dynamically (one per launch,
   // zeroed in-stream before the launch, so that concurrent streams never share one)
   unsigned int *d_counters;
@@ -29,6 +38,21 @@ struct spb_context {
 };
 
 void spb_set_error(const std::string &msg);
+
+// One-time per-device initialisation (function attributes, __constant__ uploads) that is safe
+// against concurrent callers: the header promises re-entrancy across streams and devices.
+struct spb_once_flag {
+  std::mutex mu;
+  bool done[64] = {};
+};
+template <class F>
+inline int spb_once_per_device(spb_once_flag &f, int device, F &&fn) {
+  std::lock_guard<std::mutex> lock(f.mu);
+  if (f.done[device & 63]) return 0;
+  const int st = fn();
+  if (st == 0) f.done[device & 63] = true;
+  return st;
+}
 int spb_encode_tmap_3d_f64(CUtensorMap *out, void *base, unsigned long long d0,
                            unsigned long long d1, unsigned long long d2, unsigned long long s1,
                            unsigned long long s2, unsigned b0, unsigned b1, unsigned b2);
@@ -132,6 +156,12 @@ __device__ __forceinline__ void tma_load_3d(void *sdst, const void *tmap, uint64
       "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];\n" ::"r"(s),
       "l"(tmap), "r"(b), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
+}
+
+// Orders this thread's earlier generic-proxy writes to GLOBAL memory (st.global) before later
+// async-proxy accesses (TMA loads of the same addresses) -- a __threadfence() does not.
+__device__ __forceinline__ void fence_proxy_async_global() {
+  asm volatile("fence.proxy.async.global;\n" ::: "memory");
 }
 
 // ---- TMA tensor store shared::cta -> global (cp.async.bulk.tensor, 3-D tensor map) ------------

@@ -1,4 +1,6 @@
 // Context management, error reporting, launch accounting for libspb200.
+#include <stdlib.h>
+
 #include <mutex>
 
 #include "common.cuh"
@@ -13,6 +15,29 @@ void spb_set_error(const std::string &msg) { g_last_error = msg; }
 extern "C" const char *spb_last_error(void) { return g_last_error.c_str(); }
 extern "C" int spb_version(void) { return 100; }
 
+// Everything spb_create allocates; released by spb_destroy AND by every early return of spb_create
+// (the guard below), so a failed construction leaks nothing.
+static void spb_release(spb_context *ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  if (ctx->d_tables) cudaFree(ctx->d_tables);
+  if (ctx->d_counters) cudaFree(ctx->d_counters);
+  if (ctx->d_scratch) cudaFree(ctx->d_scratch);
+  delete ctx;
+}
+
+namespace {
+struct CtxGuard {
+  spb_context *ctx;
+  ~CtxGuard() { spb_release(ctx); }
+  spb_context *release() {
+    spb_context *c = ctx;
+    ctx = nullptr;
+    return c;
+  }
+};
+}  // namespace
+
 extern "C" int spb_create(int device, const double *tables_host, size_t tables_count,
                           spb_context **out) {
   SPB_REQUIRE(out != nullptr, "spb_create: null output pointer");
@@ -23,7 +48,8 @@ extern "C" int spb_create(int device, const double *tables_host, size_t tables_c
   cudaDeviceProp prop;
   SPB_CHECK_CUDA(cudaGetDeviceProperties(&prop, device));
   SPB_REQUIRE(prop.major >= 10, "spb_create: libspb200 is built for sm_100a (B200) only");
-  spb_context *ctx = new spb_context();
+  CtxGuard guard{new spb_context()};
+  spb_context *ctx = guard.ctx;
   ctx->device = device;
   ctx->num_sms = prop.multiProcessorCount;
   ctx->d_tables = nullptr;
@@ -31,9 +57,12 @@ extern "C" int spb_create(int device, const double *tables_host, size_t tables_c
   ctx->launches = 0;
   ctx->d_counters = nullptr;
   ctx->counter_next = 0;
+  ctx->d_scratch = nullptr;
+  ctx->opt_no_tma = getenv("SPB_NO_TMA") != nullptr;          // defaults of the A/B switches
+  ctx->opt_no_cluster = getenv("SPB_NO_CLUSTER") != nullptr;
+  for (int k = 0; k < 3; ++k) ctx->max_active_clusters[k] = -1;
   SPB_CHECK_CUDA(cudaMalloc(&ctx->d_counters, SPB_NUM_COUNTERS * sizeof(unsigned int)));
   SPB_CHECK_CUDA(cudaMemset(ctx->d_counters, 0, SPB_NUM_COUNTERS * sizeof(unsigned int)));
-  ctx->d_scratch = nullptr;
   SPB_CHECK_CUDA(cudaMalloc(&ctx->d_scratch,
                             (size_t)SPB_NUM_COUNTERS * SPB_SCRATCH_PER_SLOT * sizeof(double)));
   if (tables_count > 0) {
@@ -46,17 +75,19 @@ extern "C" int spb_create(int device, const double *tables_host, size_t tables_c
       if (st) return st;
     }
   }
-  *out = ctx;
+  *out = guard.release();
   return 0;
 }
 
-extern "C" void spb_destroy(spb_context *ctx) {
-  if (!ctx) return;
-  cudaSetDevice(ctx->device);
-  if (ctx->d_tables) cudaFree(ctx->d_tables);
-  if (ctx->d_counters) cudaFree(ctx->d_counters);
-  if (ctx->d_scratch) cudaFree(ctx->d_scratch);
-  delete ctx;
+extern "C" void spb_destroy(spb_context *ctx) { spb_release(ctx); }
+
+extern "C" int spb_set_option(spb_context *ctx, const char *name, int value) {
+  SPB_REQUIRE(ctx != nullptr && name != nullptr, "spb_set_option: null argument");
+  const std::string key(name);
+  if (key == "cholesky_tma") ctx->opt_no_tma = value ? 0 : 1;
+  else if (key == "cholesky_cluster") ctx->opt_no_cluster = value ? 0 : 1;
+  else SPB_REQUIRE(false, "spb_set_option: unknown option");
+  return 0;
 }
 
 extern "C" int spb_device(const spb_context *ctx) { return ctx ? ctx->device : -1; }

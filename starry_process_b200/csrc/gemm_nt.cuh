@@ -238,13 +238,15 @@ inline int launch(spb_context *ctx, const Desc &d, cudaStream_t stream) {
                   (d.strideA % 2) == 0 && (d.strideB % 2) == 0,
               "gemm_nt: operands must be 16-byte aligned");
   SPB_REQUIRE(d.batch <= 65535, "gemm_nt: batch too large for one launch");
-  static bool attr_dev[64] = {false};   // function attributes are per device
-  bool &attr_set = attr_dev[ctx->device & 63];
+  static spb_once_flag attr_once;   // function attributes are per device (one flag per EPI)
   const size_t smem = sizeof(Smem);
-  if (!attr_set) {
-    SPB_CHECK_CUDA(cudaFuncSetAttribute(gemm_nt_kernel<EPI>,
-                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
+  {
+    const int st = spb_once_per_device(attr_once, ctx->device, [&]() -> int {
+      SPB_CHECK_CUDA(cudaFuncSetAttribute(gemm_nt_kernel<EPI>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      return 0;
+    });
+    if (st) return st;
   }
   const int tilesM = (d.M + TM - 1) / TM, tilesN = (d.N + TN - 1) / TN;
   dim3 grid(tilesM * tilesN * d.ksplit, d.batch);

@@ -87,6 +87,8 @@ __constant__ int k1_perm[256];
 __constant__ int k1_tt_sched[3 * 256];
 
 int k1_upload_perm(int device) {
+  static std::mutex mu;                 // concurrent first calls from several host threads
+  std::lock_guard<std::mutex> lock(mu);
   static bool done_dev[64] = {false};   // __constant__ banks are per device
   bool &done = done_dev[device & 63];
   if (!done) {
@@ -731,6 +733,8 @@ __global__ void __launch_bounds__(256, 2) moments_k2(K2Params p) {
 }
 
 int k2_upload_items(int device, int *nitems_out) {
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lock(mu);
   static bool done_dev[64] = {false};
   static int nitems_dev[64] = {0};
   bool &done = done_dev[device & 63];
@@ -872,14 +876,16 @@ extern "C" int spb_ylm_moments(spb_context *ctx, int B, const double *r_deg, con
   MomWs ws;
   mom_ws_layout(B, reinterpret_cast<unsigned char *>(workspace), &ws);
 
-  static bool attr1_dev[64] = {false};
-  bool &attr1 = attr1_dev[ctx->device & 63];
-  if (!attr1) {
-    SPB_CHECK_CUDA(cudaFuncSetAttribute(moments_k1a, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)sizeof(K1Smem)));
-    SPB_CHECK_CUDA(cudaFuncSetAttribute(moments_k1b, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)(K1B_WARPS * sizeof(K1bWarp))));
-    attr1 = true;
+  static spb_once_flag attr1_once;
+  {
+    const int st = spb_once_per_device(attr1_once, ctx->device, [&]() -> int {
+      SPB_CHECK_CUDA(cudaFuncSetAttribute(moments_k1a, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)sizeof(K1Smem)));
+      SPB_CHECK_CUDA(cudaFuncSetAttribute(moments_k1b, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)(K1B_WARPS * sizeof(K1bWarp))));
+      return 0;
+    });
+    if (st) return st;
   }
   SPB_REQUIRE(k1_upload_perm(ctx->device) == 0, "ylm_moments: constant upload failed");
   K1Params p1;

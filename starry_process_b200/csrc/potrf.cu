@@ -14,16 +14,24 @@
 //     traffic is ~n^3/(6 NB) reads + one write of L (a right-looking update would re-write the
 //     trailing matrix once per panel);
 //   * the panel update  P = K[:, j] - L[:, :j] L[j, :j]^T  runs on mma.sync.m8n8k4.f64 (DMMA) from
-//     a cp.async double-buffered shared-memory pipeline; each warp owns 16 full rows x 64 columns
-//     of the panel in registers;
+//     a 3-slot shared-memory ring handed off through mbarriers (no CTA-wide rendezvous in the
+//     k-loop); tiles that lie wholly inside K are fetched by TMA (cp.async.bulk.tensor through a
+//     tensor map of the batch, hardware 128-byte swizzle), tiles that mix matrix rows with appended
+//     right-hand-side rows by per-thread cp.async writing the same swizzle; each warp owns 16 full
+//     rows x 64 columns of the panel in registers;
 //   * the triangular solve  X = P L_jj^-T  is done IN REGISTERS on the tensor pipe as an 8x8-blocked
 //     forward substitution (accumulator fragments are re-shaped into A fragments with warp
 //     shuffles), so the panel never round-trips through shared memory;
 //   * the residual light curves r are appended as extra ROWS of the matrix ("augmented" Cholesky):
 //     the same panel loop then produces y = L^-1 r, so lnlike needs no back substitution:
 //         r^T K^-1 r = |y|^2;
-//   * only the 64x64 diagonal block is factorised with scalar FP64 (shared memory, one barrier per
-//     column, column scaling deferred).
+//   * the 64x64 diagonal block is factorised IN THE ACCUMULATOR REGISTERS of warps 0-3
+//     (potf2_regs): 8x8 diagonal tiles by their owner warp with shuffles only (potf2_tile8), the
+//     tiles below solved and the trailing tiles updated with DMMA, two 128-thread named barriers per
+//     8-column sub-panel.
+//   * memory-model note: the factor is written with ordinary st.global (generic proxy) and re-read
+//     by TMA (async proxy) in later panels, so every thread executes fence.proxy.async.global after
+//     its stores of a panel and before the barrier that ends the panel.
 //
 // Algorithmic flops per matrix: nt^3/3 (factor) + nt^2 M (forward solve); see DESIGN.md.
 #include <cooperative_groups.h>
@@ -841,6 +849,9 @@ __global__ void __launch_bounds__(NTHREADS, 2)
           PROF_MARK(sm, 6);
         }
       }
+      // this thread's st.global of the panel (store_rows, the L_jj write-back) must be visible to the
+      // async proxy before any thread requests them through TMA in a later panel
+      fence_proxy_async_global();
       __syncthreads();  // Ld/Dv are rewritten by the next panel; global writes of this panel done
       __threadfence_block();
       PROF_MARK(sm, 7);
@@ -1073,59 +1084,62 @@ static int potrf_launch(spb_context *ctx, PotrfParams &p, void *stream) {
   SPB_CHECK_CUDA(cudaSetDevice(ctx->device));
   p.scratch = nullptr;
   const size_t smem = sizeof(Smem);
-  static bool attr_set[64] = {false};
-  if (!attr_set[ctx->device & 63]) {
-    SPB_CHECK_CUDA(cudaFuncSetAttribute(potrf_lnlike_kernel,
-                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set[ctx->device & 63] = true;
-  }
-  int nitems = (p.mode == MODE_FACTOR) ? p.B : (p.M + p.rows_per_cta - 1) / p.rows_per_cta;
-  // few matrices: one 8-CTA cluster per matrix instead of one CTA (see potrf_cluster_kernel)
-  static const bool no_cluster = getenv("SPB_NO_CLUSTER") != nullptr;   // A/B switch for measurements
-  int cs = 0;
-  if (!no_cluster && p.mode == MODE_FACTOR && p.n > 2 * TM && ctx->d_scratch &&
-      p.B * 2 <= ctx->num_sms) {
-    // largest cluster size whose clusters are all co-resident (a second wave of clusters would
-    // cost more than a smaller cluster: GPCs host a whole number of clusters), asked of the driver
-    static int max_active[64][3];
-    static bool cattr[64] = {false};
-    const int dv = ctx->device & 63;
-    if (!cattr[dv]) {
+  static spb_once_flag attr_once;
+  {
+    const int st = spb_once_per_device(attr_once, ctx->device, [&]() -> int {
+      SPB_CHECK_CUDA(cudaFuncSetAttribute(potrf_lnlike_kernel,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       SPB_CHECK_CUDA(cudaFuncSetAttribute(potrf_cluster_kernel<8>,
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       SPB_CHECK_CUDA(cudaFuncSetAttribute(potrf_cluster_kernel<4>,
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       SPB_CHECK_CUDA(cudaFuncSetAttribute(potrf_cluster_kernel<2>,
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      for (int k = 0; k < 3; ++k) {
-        const int c = 8 >> k;
-        cudaLaunchConfig_t q = {};
-        q.gridDim = dim3((unsigned)(c * ctx->num_sms));
-        q.blockDim = dim3(NTHREADS);
-        q.dynamicSmemBytes = smem;
-        cudaLaunchAttribute a[1];
-        a[0].id = cudaLaunchAttributeClusterDimension;
-        a[0].val.clusterDim.x = (unsigned)c;
-        a[0].val.clusterDim.y = 1;
-        a[0].val.clusterDim.z = 1;
-        q.attrs = a;
-        q.numAttrs = 1;
-        int n = 0;
-        cudaError_t e = (c == 8)   ? cudaOccupancyMaxActiveClusters(&n, potrf_cluster_kernel<8>, &q)
-                        : (c == 4) ? cudaOccupancyMaxActiveClusters(&n, potrf_cluster_kernel<4>, &q)
-                                   : cudaOccupancyMaxActiveClusters(&n, potrf_cluster_kernel<2>, &q);
-        max_active[dv][k] = (e == cudaSuccess) ? n : 0;
+      return 0;
+    });
+    if (st) return st;
+  }
+  int nitems = (p.mode == MODE_FACTOR) ? p.B : (p.M + p.rows_per_cta - 1) / p.rows_per_cta;
+  // few matrices: one 8-CTA cluster per matrix instead of one CTA (see potrf_cluster_kernel)
+  int cs = 0;
+  if (!ctx->opt_no_cluster && p.mode == MODE_FACTOR && p.n > 2 * TM && ctx->d_scratch &&
+      p.B * 2 <= ctx->num_sms) {
+    // largest cluster size whose clusters are all co-resident (a second wave of clusters would
+    // cost more than a smaller cluster: GPCs host a whole number of clusters), asked of the driver
+    static std::mutex occ_mu;
+    {
+      std::lock_guard<std::mutex> lock(occ_mu);
+      if (ctx->max_active_clusters[0] < 0) {
+        for (int k = 0; k < 3; ++k) {
+          const int c = 8 >> k;
+          cudaLaunchConfig_t q = {};
+          q.gridDim = dim3((unsigned)(c * ctx->num_sms));
+          q.blockDim = dim3(NTHREADS);
+          q.dynamicSmemBytes = smem;
+          cudaLaunchAttribute a[1];
+          a[0].id = cudaLaunchAttributeClusterDimension;
+          a[0].val.clusterDim.x = (unsigned)c;
+          a[0].val.clusterDim.y = 1;
+          a[0].val.clusterDim.z = 1;
+          q.attrs = a;
+          q.numAttrs = 1;
+          int n = 0;
+          cudaError_t e = (c == 8)   ? cudaOccupancyMaxActiveClusters(&n, potrf_cluster_kernel<8>, &q)
+                          : (c == 4) ? cudaOccupancyMaxActiveClusters(&n, potrf_cluster_kernel<4>, &q)
+                                     : cudaOccupancyMaxActiveClusters(&n, potrf_cluster_kernel<2>, &q);
+          ctx->max_active_clusters[k] = (e == cudaSuccess) ? n : 0;
+        }
+        (void)cudaGetLastError();
       }
-      (void)cudaGetLastError();
-      cattr[dv] = true;
     }
+    // a cluster size is eligible only if its per-CTA partial sums fit the launch's scratch slot;
+    // otherwise fall through to the next size and finally to the one-CTA-per-matrix kernel
     for (int k = 0; k < 3 && !cs; ++k)
-      if (p.B <= max_active[dv][k]) cs = 8 >> k;
+      if (p.B <= ctx->max_active_clusters[k] && (8 >> k) * p.B <= SPB_SCRATCH_PER_SLOT) cs = 8 >> k;
   }
   if (cs) {
     const unsigned slot = __atomic_fetch_add(&ctx->counter_next, 1u, __ATOMIC_RELAXED) % SPB_NUM_COUNTERS;
     p.scratch = ctx->d_scratch + (size_t)slot * SPB_SCRATCH_PER_SLOT;
-    SPB_REQUIRE(cs * p.B <= SPB_SCRATCH_PER_SLOT, "cholesky: cluster scratch too small");
     p.counter = nullptr;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(p.B * cs));
@@ -1150,9 +1164,8 @@ static int potrf_launch(spb_context *ctx, PotrfParams &p, void *stream) {
   // boxes of 16 columns x 64 rows, 128-byte swizzle
   CUtensorMap tmK;
   memset(&tmK, 0, sizeof(tmK));
-  static const bool no_tma = getenv("SPB_NO_TMA") != nullptr;   // A/B switch for measurements
   p.use_tma = 0;
-  if (!no_tma && p.mode == MODE_FACTOR && p.n >= TM + NB) {
+  if (!ctx->opt_no_tma && p.mode == MODE_FACTOR && p.n >= TM + NB) {
     const unsigned long long sk = p.strideK > 0 ? (unsigned long long)p.strideK : (unsigned long long)p.n * p.ld;
     int st = spb_encode_tmap_3d_f64(&tmK, p.K, (unsigned long long)p.ld, (unsigned long long)p.n,
                                     (unsigned long long)p.B, (unsigned long long)p.ld * 8, sk * 8, KC,

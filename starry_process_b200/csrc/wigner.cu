@@ -422,13 +422,13 @@ extern "C" int spb_design_matrix(spb_context *ctx, int I, int nt, const double *
     int st = spb_encode_tmap_3d_f64(&tmap, A, 256, (unsigned long long)nt, (unsigned long long)I,
                                     256ull * 8, (unsigned long long)nt * 256 * 8, DM_CW, 32, 1);
     if (st) return st;
-    static bool attr_dev[64] = {false};
-    bool &attr = attr_dev[ctx->device & 63];
-    if (!attr) {
+    static spb_once_flag attr_once;
+    st = spb_once_per_device(attr_once, ctx->device, [&]() -> int {
       SPB_CHECK_CUDA(cudaFuncSetAttribute(design_rows_kernel<true>,
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tma));
-      attr = true;
-    }
+      return 0;
+    });
+    if (st) return st;
     design_rows_kernel<true><<<grid, DM_THREADS, smem_tma, stream>>>(p, tmap);
   } else {
     design_rows_kernel<false><<<grid, DM_THREADS, smem_base, stream>>>(p, tmap);

@@ -22,6 +22,7 @@ spot-size prior (``dr``), gradients, pixel-space moments and visualisation.  The
 """
 import ctypes
 import math
+import os
 
 import numpy as np
 import torch
@@ -40,6 +41,8 @@ defaults = dict(
 )
 
 _CTX = {}
+# module-wide default of the `longitude_basis` keyword (environment: SPB200_LONGITUDE_BASIS)
+DEFAULT_LONGITUDE_BASIS = os.environ.get("SPB200_LONGITUDE_BASIS", "pinned")
 
 
 def _ptr(t):
@@ -49,12 +52,13 @@ def _ptr(t):
 class _Context(object):
     """One libspb200 context (constant tables resident in HBM) per CUDA device."""
 
-    def __init__(self, device):
+    def __init__(self, device, longitude_basis="pinned"):
         if not torch.cuda.is_available():
             raise RuntimeError("starry_process_b200 needs a CUDA device (sm_100a); no CPU fallback")
         self.lib = _lib.load()
         self.device = torch.device("cuda", device)
-        blob, _ = _tables.build_tables()
+        self.longitude_basis = longitude_basis
+        blob, _ = _tables.build_tables(longitude_basis)
         h = ctypes.c_void_p()
         with torch.cuda.device(self.device):
             torch.cuda.current_stream().synchronize()
@@ -62,20 +66,30 @@ class _Context(object):
                                            ctypes.byref(h)))
         self.handle = h
 
+    def set_option(self, name, value):
+        """Run-time switches of the library (include/spb200.h: spb_set_option)."""
+        _lib.check(self.lib.spb_set_option(self.handle, name.encode(), int(value)))
+
     def launches(self):
         n = ctypes.c_longlong()
         _lib.check(self.lib.spb_launch_count(self.handle, ctypes.byref(n)))
         return n.value
 
 
-def get_context(device=None):
+def get_context(device=None, longitude_basis=None):
+    """The libspb200 context of ``device`` (created on first use).  ``longitude_basis``:
+    ``"pinned"`` (default; the shipped longitude eigenvector table, identical on every host) or
+    ``"host"`` (this host's own ``numpy.linalg.eigh``, what a reference run in this process uses) --
+    see ``_tables.build_tables``.  The two bases are separate contexts."""
     if device is None:
         device = torch.cuda.current_device() if torch.cuda.is_available() else 0
     if isinstance(device, torch.device):
         device = device.index if device.index is not None else torch.cuda.current_device()
-    if device not in _CTX:
-        _CTX[device] = _Context(int(device))
-    return _CTX[device]
+    basis = DEFAULT_LONGITUDE_BASIS if longitude_basis is None else longitude_basis
+    key = (int(device), basis)
+    if key not in _CTX:
+        _CTX[key] = _Context(int(device), basis)
+    return _CTX[key]
 
 
 def _stream():
@@ -196,7 +210,7 @@ class StarryProcess(object):
         self._normalized = bool(normalized)
         self._marginalize_over_inclination = bool(marginalize_over_inclination)
 
-        self._ctx = get_context(device)
+        self._ctx = get_context(device, kwargs.pop("longitude_basis", None))
         self.device = self._ctx.device
         self._lib = self._ctx.lib
 
@@ -280,8 +294,12 @@ class StarryProcess(object):
     _stage_ms = None
 
     def _mark(self, name):
+        """Opens an NVTX range for one phase of the path (moments, flux_marginal /
+        design, assemble, cholesky; visible in nsys / ncu --nvtx) and, when ``_stage_ms`` is set,
+        brackets it with CUDA events on the launching stream."""
+        torch.cuda.nvtx.range_push("spb200:" + name)
         if self._stage_ms is None:
-            return None
+            return False
         e0 = torch.cuda.Event(enable_timing=True)
         e1 = torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -290,8 +308,9 @@ class StarryProcess(object):
 
     @staticmethod
     def _mark_end(ev):
-        if ev is not None:
+        if ev is not False:
             ev.record()
+        torch.cuda.nvtx.range_pop()
 
     def log_jac(self):
         """sp.py:1004-1050 -> LatitudeIntegral._log_jac (latitude.py:281-316): log-Jacobian of the
@@ -382,11 +401,23 @@ class StarryProcess(object):
         return u[: self._udeg].to(self.device).contiguous()
 
     def _rTA1(self, u):
+        """Flux operator row vector for limb darkening ``u`` (a13), cached per process object for
+        host-resident ``u`` (it only depends on ``u``; keyed by value, so no device sync)."""
+        key = None
+        if not (isinstance(u, torch.Tensor) and u.is_cuda):
+            uh = np.asarray(defaults["u"] if u is None else
+                            (u.detach().cpu().numpy() if isinstance(u, torch.Tensor) else u),
+                            dtype=np.float64).reshape(-1)
+            key = tuple(uh.tolist())
+            if key in self._rTA1_cache:
+                return self._rTA1_cache[key]
         ud = self._u(u)
         out = torch.empty(256, dtype=torch.float64, device=self.device)
         with torch.cuda.device(self.device):
             _lib.check(self._lib.spb_flux_operator(self._ctx.handle, 1, _ptr(ud), _ptr(out),
                                                    _stream()))
+        if key is not None:
+            self._rTA1_cache[key] = out
         return out
 
     def _t(self, t):
@@ -543,7 +574,8 @@ class StarryProcess(object):
         # B200 has 180 GB), of equal size: the Cholesky kernel claims matrices dynamically, so one
         # long launch has a shorter tail than several short ones
         per = nt * ldk * 8 + 4 * 256 * 256 * 8
-        step = max(1, min(self._B, self._max_chunk_bytes // per))
+        # (the assembly / GEMM kernels carry the batch in grid.y: at most 65535 elements a launch)
+        step = max(1, min(self._B, self._max_chunk_bytes // per, 65535))
         nchunks = -(-self._B // step)
         step = -(-self._B // nchunks)
         return [(b0, min(self._B, b0 + step)) for b0 in range(0, self._B, step)]
@@ -987,16 +1019,20 @@ class StarryProcess(object):
                 if U.ndim != 3 or U.shape[1] != nt or U.shape[2] != 256:
                     raise ValueError("u must have shape (nsamples, nt, 256)")
                 nsamples = U.shape[0]
-            # V[s] = L_t U_s  (NT form: Bm = U_s^T, k = time, zero-padded to an even length)
-            Ut = torch.zeros(nsamples, 256, ldt, dtype=torch.float64, device=dev)
-            Ut[:, :, :nt] = U.transpose(1, 2)
-            out = torch.empty(B, nsamples, nt, 256, dtype=torch.float64, device=dev)
-            V = torch.empty(nsamples, nt, 256, dtype=torch.float64, device=dev)
-            for b in range(B):
-                self._gemm(nsamples, nt, 256, ldt, Kt[b], ldt, 0, Ut, ldt, 256 * ldt, V, 256,
-                           nt * 256)
-                self._gemm(nsamples, nt, 256, 256, V, 256, nt * 256, Ly[b], 256, 0, out[b], 256,
-                           nt * 256)
+            # Two batched tensor-core GEMMs for the whole (B x nsamples) set, no Python loop:
+            #   V[b] (nt, ns*256) = L_t[b] (nt, nt) . [U_0 | U_1 | ...]   (NT form: Bm = the stacked
+            #   U_s^T, (ns*256, ldt), shared by every b; k = time, zero-padded to an even length)
+            #   W[b] (nt*ns, 256) = V[b] viewed as (nt*ns, 256) . L_y[b]^T
+            # and one permutation (t, s) -> (s, t) of the result.
+            Ut = torch.zeros(nsamples * 256, ldt, dtype=torch.float64, device=dev)
+            Ut[:, :nt] = U.transpose(1, 2).reshape(nsamples * 256, nt)
+            V = torch.empty(B, nt, nsamples * 256, dtype=torch.float64, device=dev)
+            self._gemm(B, nt, nsamples * 256, ldt, Kt, ldt, nt * ldt, Ut, ldt, 0, V, nsamples * 256,
+                       nt * nsamples * 256)
+            W = torch.empty(B, nt * nsamples, 256, dtype=torch.float64, device=dev)
+            self._gemm(B, nt * nsamples, 256, 256, V, 256, nt * nsamples * 256, Ly, 256, 65536, W,
+                       256, nt * nsamples * 256)
+            out = W.view(B, nt, nsamples, 256).transpose(1, 2).contiguous()
             out = torch.where(((info & 1) != 0)[:, None, None, None],
                               torch.full_like(out, float("nan")), out)
         return self._out(out)
@@ -1083,6 +1119,7 @@ class StarryProcessSum(StarryProcess):
         self._info = (first._info | second._info).expand(B).contiguous()
         self._cho_cov_ylm = None
         self._z = None
+        self._rTA1_cache = {}
         self._a = self._b = self._r = self._c = self._n = None
 
     def _compute_moments(self):

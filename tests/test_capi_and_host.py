@@ -214,3 +214,39 @@ def test_sass_uses_clusters_and_tma(built_lib):
     assert "UTMASTG" in sass                                                  # cp.async.bulk.tensor store
     assert "UTMALDG" in sass            # TMA-fed operand ring of the Cholesky kernel
     assert "DMMA" in sass
+
+
+def test_sass_cholesky_orders_generic_writes_before_tma_reads(built_lib):
+    """the batched Cholesky writes its factor with st.global (generic proxy) and
+    re-reads it through TMA (async proxy) in later panels: the kernel must carry the
+    fence.proxy.async.global that orders the two (SASS: FENCE.VIEW.ASYNC.G)."""
+    import subprocess
+
+    sass = subprocess.run(["cuobjdump", "-sass", built_lib], capture_output=True, text=True).stdout
+    beg = sass.index("potrf_lnlike_kernel")
+    end = sass.find("Function :", beg)
+    body = sass[beg:end if end > 0 else None]
+    assert "UTMALDG" in body and "FENCE.VIEW.ASYNC.G" in body
+
+
+def test_longitude_basis_tables():
+    """The pinned longitude eigenvector table is what scripts/gen_longitude_U.py regenerates in the
+    build container (SHA-256 recorded next to it), the "host" basis is this host's own eigh, both span
+    the same 31-dimensional space, and only the LON_T block of the constant blob depends on it."""
+    import hashlib
+    import json
+
+    from starry_process_b200 import _tables as T
+
+    Up, Uh = T.longitude_U("pinned"), T.longitude_U("host")
+    meta = json.load(open(T.PINNED_LONGITUDE[:-4] + ".json"))
+    assert hashlib.sha256(np.ascontiguousarray(Up).tobytes()).hexdigest() == meta["sha256"]
+    assert Up.shape == Uh.shape == (256, 31)
+    assert np.abs(Up @ Up.T - Uh @ Uh.T).max() <= 1e-14
+    bp, off = T.build_tables("pinned")
+    bh, _ = T.build_tables("host")
+    diff = np.nonzero(bp != bh)[0]
+    if diff.size:   # (identical on the host that generated the pinned table)
+        assert diff.min() >= off["LON_T"] and diff.max() < off["LON_T"] + 31 * T.NWIG
+    with pytest.raises(ValueError):
+        T.build_tables("nonsense")

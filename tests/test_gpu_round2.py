@@ -1,0 +1,268 @@
+"""GPU (-m gpu), round 2: the branches and claims round 1 left untested.
+
+* parity on THIS host: a context built with ``longitude_basis="host"`` against the same-process live
+  oracle at 1e-8 (the pinned table reproduces the build container's values instead);
+* the ``M >= 64`` ensemble branch of ``log_likelihood`` (configs[1]) against the reference golden;
+* 16 nt = 4096 draws incl. a non positive-definite element and a z > zmax element (configs[3]);
+* the z-range flag is re-evaluated per call (not sticky);
+* TMA-fed vs cp.async-fed Cholesky operand ring: bit-identical factors and lnlike under load;
+* run-to-run determinism of the full 4096-matrix step.
+"""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+
+from conftest import FID, U_LD
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-8
+
+
+@pytest.fixture(scope="module")
+def spb():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import starry_process_b200 as m
+
+    return m
+
+
+def rel(a, b):
+    return np.abs(a - b) / np.abs(b)
+
+
+def P(t):
+    return ctypes.c_void_p(t.data_ptr())
+
+
+# ------------------------------------------------------------------------- parity on this host
+def test_host_basis_against_live_oracle_1e8(spb, oracle, golden):
+    """with the longitude eigenvector table taken from THIS host's
+    numpy.linalg.eigh (``longitude_basis="host"``: exactly what the reference / oracle computes in
+    this process) the CUDA path meets the 1e-8 north-star tolerance against the live oracle --
+    64 draws of the bench workload in both branches and the four fiducial modes at nt = 1000."""
+    import bench
+    from starry_process_b200 import _tables
+
+    # the product's host table is the oracle's own U_lon, bit for bit (same NumPy call, same process)
+    U_or = oracle.longitude_tensors(15)[0]
+    assert np.array_equal(_tables.longitude_U("host"), U_or)
+    hp, t, flux, _ = bench.synthetic_inputs(4096, seed=1234)
+    ns = 64
+    worst = {}
+    for marg in (True, False):
+        gp = spb.StarryProcess(marginalize_over_inclination=marg, normalized=True,
+                               longitude_basis="host", **{k: hp[k][:ns] for k in hp})
+        assert gp._ctx.longitude_basis == "host"
+        ll = gp.log_likelihood(t, flux, 1e-6, i=60.0, p=1.0, u=U_LD).cpu().numpy()
+        ref = np.array([oracle.OracleProcess(marginalize_over_inclination=marg, normalized=True,
+                                             **{k: hp[k][s] for k in hp}).log_likelihood(
+            t, flux, 1e-6, i=60.0, p=1.0, u=U_LD) for s in range(ns)])
+        assert np.array_equal(np.isneginf(ll), np.isneginf(ref))
+        fin = np.isfinite(ref)
+        worst["bench marg=%d" % marg] = float(rel(ll[fin], ref[fin]).max())
+    g = golden("fiducial_nt1000.npz")
+    for marg in (False, True):
+        for norm in (False, True):
+            gp = spb.StarryProcess(marginalize_over_inclination=marg, normalized=norm,
+                                   longitude_basis="host", **FID)
+            f = g["flux_norm"] if norm else g["flux"]
+            ll = gp.log_likelihood(g["t"], f, 1e-6, i=60.0, p=1.0, u=U_LD).item()
+            ref = oracle.OracleProcess(marginalize_over_inclination=marg, normalized=norm,
+                                       **FID).log_likelihood(g["t"], f, 1e-6, i=60.0, p=1.0, u=U_LD)
+            worst["fiducial m%d n%d" % (marg, norm)] = float(rel(ll, ref))
+    print("host basis vs live oracle (max rel lnlike err):", worst)
+    assert max(worst.values()) <= RTOL, worst
+
+
+def test_pinned_and_host_contexts_coexist(spb):
+    a = spb.get_context(0)
+    b = spb.get_context(0, "host")
+    assert a is not b and a.longitude_basis == "pinned" and b.longitude_basis == "host"
+    assert spb.get_context(0, "host") is b
+    with pytest.raises(ValueError):
+        spb.get_context(0, "nonsense")
+
+
+# ------------------------------------------------------------------------- configs[1]: M >= 64
+def test_ensemble_branch_against_reference_golden(spb, golden):
+    """sp.py:1157-1173 with flux (1024, 1000): one factorisation + spb_cholesky_solve_rows over the
+    whole GPU + the host-side reduction (StarryProcess.log_likelihood, ``Bc == 1 and M >= 64``), in
+    all four modes, with a scalar and a per-point data covariance, against the unmodified
+    reference (oracle/gen_golden_r2.py)."""
+    import bench
+
+    g = golden("ensemble_nt1000.npz")
+    M = int(g["M"])
+    for norm in (False, True):
+        t, f = bench.ensemble_flux(M, normalized=norm)
+        chk = float(np.sum(f * np.cos(np.arange(f.size)).reshape(f.shape)))
+        assert abs(chk - float(g["flux_checksum_n%d" % norm])) <= 1e-9 * abs(chk)  # same inputs
+        for marg in (False, True):
+            key = "m%d_n%d" % (marg, norm)
+            gp = spb.StarryProcess(marginalize_over_inclination=marg, normalized=norm, **FID)
+            ll = gp.log_likelihood(t, f, 1e-6, i=60.0, p=1.0, u=U_LD).item()
+            assert rel(ll, float(g["lnlike_" + key])) <= RTOL, (key, ll)
+            lld = gp.log_likelihood(t, f, g["data_cov_vec"], i=60.0, p=1.0, u=U_LD,
+                                    baseline_mean=1e-4, baseline_var=1e-5).item()
+            assert rel(lld, float(g["lnlike_dvec_" + key])) <= RTOL, (key, lld)
+            l64 = gp.log_likelihood(t, f[:64], 1e-6, i=60.0, p=1.0, u=U_LD).item()
+            assert rel(l64, float(g["lnlike_64_" + key])) <= RTOL, (key, l64)
+            # the branch boundary: 63 curves take the augmented-rows kernel, 64 the split solve;
+            # joint lnlike is additive over curves up to the shared log-determinant bookkeeping
+            l63 = gp.log_likelihood(t, f[:63], 1e-6, i=60.0, p=1.0, u=U_LD).item()
+            l1 = gp.log_likelihood(t, f[63], 1e-6, i=60.0, p=1.0, u=U_LD).item()
+            assert abs((l63 + l1) - l64) <= 1e-10 * abs(l64)
+    # a non positive-definite K on this branch -> -inf, as math.py:82-91 / sp.py:1186-1188
+    gp = spb.StarryProcess(marginalize_over_inclination=True, normalized=False, **FID)
+    t, f = bench.ensemble_flux(128, normalized=False)
+    assert gp.log_likelihood(t, f, -1e-2, u=U_LD).item() == -np.inf
+
+
+# ------------------------------------------------------------------------- configs[3]: nt = 4096
+def test_long_baseline_16_draws(spb, golden):
+    lb = golden("longbaseline_nt4096.npz")
+    r2 = golden("longbaseline_nt4096_r2.npz")
+    t, f = lb["t"], lb["flux"]
+    fn = (1 + f) / np.mean(1 + f) - 1
+    hp = {k: r2[k] for k in ("r", "mu", "sigma", "c", "n")}
+    gp = spb.StarryProcess(marginalize_over_inclination=False, normalized=False, **hp)
+    ll = gp.log_likelihood(t, f, 1e-6, i=60.0, p=1.0, u=r2["u"],
+                           baseline_var=torch.tensor(r2["baseline_var"])).cpu().numpy()
+    ref = r2["lnlike_n0"]
+    assert np.array_equal(np.isneginf(ll), np.isneginf(ref)) and np.isneginf(ll[5])
+    assert int(gp.info[5].item()) & 1 and int((gp.info.cpu().numpy() != 0).sum()) == 1
+    fin = np.isfinite(ref)
+    e0 = rel(ll[fin], ref[fin]).max()
+    gpn = spb.StarryProcess(marginalize_over_inclination=False, normalized=True, **hp)
+    lln = gpn.log_likelihood(t, fn, 1e-6, i=60.0, p=1.0, u=r2["u"]).cpu().numpy()
+    refn = r2["lnlike_n1"]
+    assert np.array_equal(np.isneginf(lln), np.isneginf(refn)) and np.isneginf(lln[11])
+    assert int(gpn.info[11].item()) & 2
+    z = gpn._z.cpu().numpy()
+    assert rel(z, r2["z_n1"]).max() <= 1e-8 and z[11] > 0.023
+    finn = np.isfinite(refn)
+    e1 = rel(lln[finn], refn[finn]).max()
+    print("nt=4096, 16 draws: max rel err unnormalised %.2e, normalised %.2e" % (e0, e1))
+    assert e0 <= RTOL and e1 <= RTOL
+
+
+def test_full_prior_bench_line_against_reference_golden(spb, golden):
+    """bench.py's second line item (the reference's full stability prior): -inf pattern identical,
+    finite values to the noise bound the round-1 broad-prior sweep documents."""
+    import bench
+
+    g = golden("bench_fullprior_seed4321.npz")
+    ns = len(g["r"])
+    hp, t, flux, _ = bench.synthetic_inputs(4096, seed=4321, prior="full")
+    for k in ("r", "mu", "sigma", "c", "n"):
+        assert np.array_equal(g[k], hp[k][:ns])
+    gp = spb.StarryProcess(**{k: hp[k][:ns] for k in hp})
+    ll = gp.log_likelihood(t, flux, 1e-6, i=60.0, p=1.0, u=U_LD).cpu().numpy()
+    ref = g["lnlike_m1_n1"]
+    assert np.array_equal(np.isneginf(ll), np.isneginf(ref))
+    fin = np.isfinite(ref)
+    if fin.any():
+        err = rel(ll[fin], ref[fin])
+        print("full prior: %d finite of %d, max rel err %.2e" % (fin.sum(), ns, err.max()))
+        assert err.max() <= 5e-7   # REF_NOISE_RTOL of tests/test_gpu_parity.py (broad prior, marg.)
+
+
+# ------------------------------------------------------------------------- flags
+def test_z_range_flag_is_reevaluated_per_call(spb):
+    """SPB_INFO_Z_RANGE depends on (t, i, p, u); it must not stick to the process object.
+    The reference re-evaluates z > zmax on every call (sp.py:1178-1183)."""
+    rng = np.random.default_rng(5)
+    t = np.linspace(0, 2, 120)
+    f = 1e-3 * rng.standard_normal(120)
+    gp = spb.StarryProcess(r=20.0, mu=30.0, sigma=5.0, c=0.4, n=10.0,
+                           marginalize_over_inclination=False, normalized=True)
+    incs = np.linspace(1.0, 89.0, 45)
+    zs = []
+    for inc in incs:
+        gp.cov(t, i=float(inc))
+        zs.append(float(gp._z.item()))
+    zs = np.array(zs)
+    assert zs.max() > 0.023 > zs.min(), "test setup: z must cross zmax over inclination"
+    hi, lo = float(incs[zs.argmax()]), float(incs[zs.argmin()])
+    assert gp.log_likelihood(t, f, 1e-6, i=hi).item() == -np.inf
+    assert int(gp.info.item()) & 2
+    ll = gp.log_likelihood(t, f, 1e-6, i=lo).item()      # same object, in-range inclination
+    assert np.isfinite(ll) and not (int(gp.info.item()) & 2)
+    fresh = spb.StarryProcess(r=20.0, mu=30.0, sigma=5.0, c=0.4, n=10.0,
+                              marginalize_over_inclination=False, normalized=True)
+    assert fresh.log_likelihood(t, f, 1e-6, i=lo).item() == ll
+    # cov() / sample() of an out-of-range configuration leave no trace either
+    gp.cov(t, i=hi)
+    assert gp.log_likelihood(t, f, 1e-6, i=lo).item() == ll
+
+
+# ------------------------------------------------------------------------- Cholesky stress
+def _spd_batch(B, n, seed):
+    gen = torch.Generator(device="cuda").manual_seed(seed)
+    A = torch.randn(B, n, 24, dtype=torch.float64, device="cuda", generator=gen)
+    K = torch.bmm(A, A.transpose(1, 2)) / 24
+    K += torch.eye(n, dtype=torch.float64, device="cuda") * 0.7
+    R = torch.randn(B, 1, n, dtype=torch.float64, device="cuda", generator=gen)
+    return K, R
+
+
+@pytest.mark.parametrize("B,n", [(3000, 192), (1200, 320), (700, 1000)])
+def test_cholesky_tma_and_cp_async_rings_bitwise(spb, B, n):
+    """the factor is written with st.global (generic proxy) and re-read through
+    TMA (async proxy) in the next panel; a missing fence.proxy.async shows up as stale operands at
+    small nt (64-column panels follow their producer immediately) and large B (every SM busy).  The
+    TMA-fed ring must reproduce the cp.async-fed ring bit for bit, launch after launch."""
+    ctx = spb.get_context(0)
+    K0, R0 = _spd_batch(B, n, seed=n)
+
+    def run(tma):
+        ctx.set_option("cholesky_tma", tma)
+        K, R = K0.clone(), R0.clone()
+        ll = torch.zeros(B, dtype=torch.float64, device="cuda")
+        info = torch.zeros(B, dtype=torch.int32, device="cuda")
+        assert ctx.lib.spb_cholesky_lnlike(ctx.handle, B, n, P(K), n, n * n, 1, P(R), n, n,
+                                           P(ll), None, None, P(info), None) == 0
+        torch.cuda.synchronize()
+        assert int(info.abs().sum()) == 0
+        return torch.tril(K), R, ll
+
+    try:
+        Lc, Rc, llc = run(0)
+        for rep in range(3):
+            Lt, Rt, llt = run(1)
+            assert torch.equal(llt, llc), "lnlike differs between the TMA and cp.async rings"
+            assert torch.equal(Lt, Lc) and torch.equal(Rt, Rc)
+    finally:
+        ctx.set_option("cholesky_tma", 1)
+    # and against LAPACK on a few elements
+    for b in (0, B // 2, B - 1):
+        L = np.linalg.cholesky(K0[b].cpu().numpy())
+        assert np.abs(Lc[b].cpu().numpy() - L).max() <= 1e-12
+
+
+def test_full_step_is_deterministic_run_to_run(spb, golden):
+    """the same 4096-draw step 20 times -> bit-identical log-likelihoods (the
+    mbarrier hand-offs of the operand ring that racecheck cannot follow would show up here as
+    run-to-run differences under full load)."""
+    import bench
+
+    hp, t, flux, _ = bench.synthetic_inputs(4096, seed=1234)
+    hd = {k: torch.tensor(v, device="cuda") for k, v in hp.items()}
+    td, fd = torch.tensor(t, device="cuda"), torch.tensor(flux, device="cuda")
+    first = None
+    for rep in range(20):
+        ll = spb.StarryProcess(**hd).log_likelihood(td, fd, 1e-6, p=1.0, u=U_LD)
+        if first is None:
+            first = ll.clone()
+            sw = golden("bench_sweep_seed1234.npz")
+            ref = sw["lnlike_m1_n1"]
+            got = first[: len(ref)].cpu().numpy()
+            fin = np.isfinite(ref)
+            assert rel(got[fin], ref[fin]).max() <= RTOL
+        else:
+            assert torch.equal(ll, first), "run %d differs from run 0" % rep
