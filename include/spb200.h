@@ -275,7 +275,9 @@ int spb_dmma_peak(spb_context *ctx, int iters, double *tflops_host, double *ms_h
 /* Run-time switches for A/B measurements and the bit-for-bit stress tests (defaults: everything on;
  * the environment variables SPB_NO_TMA / SPB_NO_CLUSTER set the defaults at spb_create):
  *   "cholesky_tma"     1 | 0   operand ring of the batched Cholesky fed by TMA | by cp.async
- *   "cholesky_cluster" 1 | 0   few matrices: one matrix per thread-block cluster | per CTA       */
+ *   "cholesky_cluster" 1 | 0   few matrices: one matrix per thread-block cluster | per CTA
+ *   "cholesky_tile"    64 | 128  rows per CTA tile of the batched Cholesky (4 warps, 3 CTAs per SM |
+ *                              8 warps, 2 CTAs per SM)                                            */
 int spb_set_option(spb_context *ctx, const char *name, int value);
 int spb_launch_count(const spb_context *ctx, long long *count_host);
 

@@ -27,6 +27,7 @@ struct spb_context {
   // run-time switches (spb_set_option): A/B measurements and the bit-for-bit stress tests
   int opt_no_tma;         // Cholesky operand ring: cp.async instead of TMA
   int opt_no_cluster;     // Cholesky: never use the one-matrix-per-cluster kernel
+  int opt_chol_tile;      // Cholesky batch kernel: rows per tile, 64 (4 warps, 3 CTAs/SM) or 128
   int max_active_clusters[3];   // cudaOccupancyMaxActiveClusters for cluster sizes 8, 4, 2 (-1: unknown)
   // ring of work counters for kernels that claim their work items dynamically (one per launch,
   // zeroed in-stream before the launch, so that concurrent streams never share one)

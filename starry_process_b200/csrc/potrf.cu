@@ -46,12 +46,26 @@ namespace cg = cooperative_groups;
 namespace {
 
 constexpr int NB = 64;         // panel width
-constexpr int TM = 128;        // rows per tile (8 warps x 16 rows)
 constexpr int KC = 16;         // k-chunk per pipeline stage (one 128-byte row segment)
-constexpr int LS = NB + 4;     // smem stride of the diagonal block: 68
+constexpr int LS = NB + 4;     // smem stride of the unpacked diagonal block: 68
 constexpr int DS = 12;         // smem stride of the 8x8 diagonal-inverse blocks
-constexpr int STAGES = 3;      // cp.async ring depth
-constexpr int NTHREADS = 256;
+
+// Tile geometry.  A CTA of TM / 16 warps owns TM rows of a panel at a time (16 rows x 64 columns per
+// warp).  Two instantiations:
+//   TM = 128: 8 warps, 2 CTAs per SM (the round-1 kernel; still used by the cluster kernel);
+//   TM =  64: 4 warps, 3 CTAs per SM.  Finer tiles waste fewer warp slots on the partly filled last
+//             tile of a panel and on the triangular diagonal tile (k-loop slot efficiency at
+//             nt = 1000: 0.94 against 0.82), and three independent matrices per SM overlap one
+//             another's latency-bound phases (diagonal block, TRSM chains, prologues) better than
+//             two.  L_jj is kept PACKED (its 36 lower 8x8 tiles, 18 KB instead of 35 KB) so that
+//             three CTAs fit the shared memory of an SM.
+template <int TM_>
+struct Geo {
+  static constexpr int TM = TM_;
+  static constexpr int NTHREADS = 2 * TM_;
+  static constexpr int NWARPS = TM_ / 16;
+  static constexpr bool PACKED = (TM_ != 128);
+};
 
 enum { KIND_NONE = 0, KIND_DIAG = 1, KIND_PAD = 2, KIND_BELOW = 3, KIND_RHS = 4 };
 enum { MODE_FACTOR = 1, MODE_SOLVE = 0 };
@@ -116,10 +130,39 @@ struct RowMap {
 // k = 4 kk + tg) every half-warp then touches 16 distinct 8-byte banks: conflict-free LDS.64
 // without the 25 % padding, which is what lets three stages fit beside the diagonal block at
 // two CTAs per SM.
+// L_jj storage.  Unpacked: row stride 68 (conflict-free for the m8n8k4 fragment pattern).  Packed:
+// lower 8x8 tiles only, tile (ib, jb) at (ib (ib + 1) / 2 + jb) * 64, element (r, c) of a tile at
+// r * 8 + (c ^ ((r & 2) << 1)): the XOR moves columns 0-3 / 4-7 of rows 2, 3, 6, 7 so that the 16
+// lanes of a half-warp (rows g..g+3, columns 4 q + tg) hit 16 distinct 8-byte banks, and keeps the
+// (2 tg, 2 tg + 1) pairs of the accumulator layout adjacent and 16-byte aligned.
+template <bool PACKED>
+struct LdStore;
+template <>
+struct LdStore<false> {
+  double v[NB * LS];
+  __device__ __forceinline__ double &at(int i, int j) { return v[i * LS + j]; }
+  __device__ __forceinline__ const double &at(int i, int j) const { return v[i * LS + j]; }
+};
+template <>
+struct LdStore<true> {
+  double v[36 * 64];
+  static __device__ __forceinline__ int idx(int i, int j) {
+    const int ib = i >> 3, jb = j >> 3, r = i & 7, c = j & 7;
+    return ((ib * (ib + 1)) / 2 + jb) * 64 + r * 8 + (c ^ ((r & 2) << 1));
+  }
+  __device__ __forceinline__ double &at(int i, int j) { return v[idx(i, j)]; }
+  __device__ __forceinline__ const double &at(int i, int j) const { return v[idx(i, j)]; }
+};
+
+template <int TM_, int STAGES_>
 struct Smem {
-  double As[STAGES][TM][KC];
+  using G = Geo<TM_>;
+  static constexpr int TM = TM_;
+  static constexpr int STAGES = STAGES_;   // operand ring depth (look-ahead = STAGES - 1 chunks)
+  static constexpr int NTHREADS = G::NTHREADS;
+  double As[STAGES][TM_][KC];
   double Bs[STAGES][NB][KC];
-  double Ld[NB][LS];   // diagonal block L_jj (lower), valid after potf2
+  LdStore<G::PACKED> Ld;   // diagonal block L_jj (lower), valid after potf2
   double Dv[NB][DS];   // the 8 inverses of the 8x8 diagonal blocks of L_jj: Dv[8*nb + r][c]
   double red[NTHREADS / 32];
   double dpiv[NB];         // pivots L_ii^2 of the current diagonal block
@@ -150,8 +193,10 @@ __device__ __forceinline__ unsigned long long gtimer() {
 #define PROF_MARK(sm, k)
 #endif
 
-static_assert(offsetof(Smem, Dv) == offsetof(Smem, Ld) + sizeof(double) * NB * LS,
+using SmemCluster = Smem<128, 3>;
+static_assert(offsetof(SmemCluster, Dv) == offsetof(SmemCluster, Ld) + sizeof(double) * NB * LS,
               "Ld and Dv must be adjacent (copied as one block by the cluster kernel)");
+static_assert(sizeof(Smem<64, 3>) <= 75 * 1024, "three 4-warp CTAs must fit the shared memory of an SM");
 
 // element index inside a stage row: the TMA 128-byte swizzle (16-byte chunk index XOR row mod 8),
 // used by the cp.async path as well so that both fill the ring in the same layout
@@ -185,7 +230,8 @@ struct AffRow {
 // constants C_i = s2 (1 - q_i) + offset and D_i = s2 (1 - q_i) + s3 q_i: two FMAs per entry on the
 // accumulator-load path (the re-association moves K' by a few 1e-16 of the rank-one terms, which are
 // themselves ~1e-3 of K: far below the 1e-8 lnlike tolerance).
-__device__ __forceinline__ double aff_apply(const Smem &sm, const AffRow &af, double k, double Ci,
+template <class SM>
+__device__ __forceinline__ double aff_apply(const SM &sm, const AffRow &af, double k, double Ci,
                                             double Di, bool diag_row, int gi, int gc) {
   if (af.norm) k = fma(sm.af[0], k, fma(-Di, af.q[gc], Ci));
   else k += Ci;
@@ -193,7 +239,8 @@ __device__ __forceinline__ double aff_apply(const Smem &sm, const AffRow &af, do
   return k;
 }
 
-__device__ __forceinline__ void init_acc(const Smem &sm, const RowMap &rm, const AffRow &af, bool aff_on,
+template <class SM>
+__device__ __forceinline__ void init_acc(const SM &sm, const RowMap &rm, const AffRow &af, bool aff_on,
                                          int v, int c0, int tg, bool full, double (&accrow)[8][2]) {
   int kind;
   const double *p = rm.row(v, kind);
@@ -307,39 +354,68 @@ __device__ __forceinline__ void init_acc(const Smem &sm, const RowMap &rm, const
 // `init` loads (and, on the fused path, transforms) the accumulators; it runs AFTER the first two
 // chunks have been requested so that its global-load latency -- and the dependent affine FMAs --
 // overlap the cp.async prologue instead of preceding it.
-template <class Init>
-__device__ __forceinline__ void gemm_tile(Smem &sm, const RowMap &rm, int v0, int c0, int nvirt,
-                                          int nt_lim, unsigned &it, double (&acc)[2][8][2],
+// Rows of the DIAGONAL tile are dealt to warps 0-3 in 8-row blocks (w, 7 - w) instead of
+// (2 w, 2 w + 1): block b only needs its first b + 1 column groups, so every warp multiplies
+// (w + 1) + (8 - w) = 9 groups per k-step instead of 4 ... 16 -- the k-loop of the diagonal tile is
+// balanced and finishes in 9/16 of the time of its slowest warp under the natural order.
+// (Only the 4-warp geometry does this: with 8 warps the four warps below the diagonal block set the
+// pace of the tile anyway, and the natural order keeps the round-1 code path.)
+template <bool BAL>
+__device__ __forceinline__ int diag_block(int warp, int mt) {
+  return BAL ? (mt == 0 ? warp : 7 - warp) : 2 * warp + mt;
+}
+
+// Virtual row (RowMap) of m-tile mt, row g of this warp in the tile starting at v0.
+template <bool BAL>
+__device__ __forceinline__ int tile_vrow(bool diag_tile, int v0, int warp, int mt, int g) {
+  return (BAL && diag_tile && warp < 4) ? 8 * diag_block<BAL>(warp, mt) + g
+                                        : v0 + warp * 16 + mt * 8 + g;
+}
+
+template <class SM, class Init>
+__device__ __forceinline__ void gemm_tile(SM &sm, const RowMap &rm, int v0, int c0, int nvirt,
+                                          bool diag_tile, unsigned &it, double (&acc)[2][8][2],
                                           Init init, const CUtensorMap *tmK = nullptr,
                                           int item = 0) {
+  constexpr int TM = SM::TM, NTHREADS = SM::NTHREADS, STAGES = SM::STAGES, LA = SM::STAGES - 1;
+  constexpr bool BAL = SM::G::PACKED;   // 4-warp geometry
+  constexpr int RPP = NTHREADS / 8;      // rows covered by one pass of the per-thread copies
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, tg = lane & 3;
   const int nchunks = c0 / KC;
+  const bool diag_warp = diag_tile && warp < 4;
+  // balanced geometry: tile-relative rows of this warp's two m-tiles and how many 8-column groups
+  // each one needs; natural order (8-warp geometry, the round-1 code path): rows 16 w + 8 mt, and both
+  // m-tiles of a diagonal warp stop at group 2 w + 1
+  const int ar0 = BAL ? tile_vrow<BAL>(diag_tile, v0, warp, 0, 0) - v0 : warp * 16;
+  const int ar1 = BAL ? tile_vrow<BAL>(diag_tile, v0, warp, 1, 0) - v0 : warp * 16 + 8;
+  const int lim0 = diag_warp ? (BAL ? diag_block<BAL>(warp, 0) + 1 : 2 * warp + 2) : 8;
+  const int lim1 = BAL ? (diag_warp ? diag_block<BAL>(warp, 1) + 1 : 8) : lim0;
   PROF_DECL;
   if (nchunks == 0) {
     init();
     PROF_MARK(sm, 1);
     return;
   }
-  const bool warp_live = (v0 + warp * 16) < nvirt;
+  const bool warp_live = diag_warp || (v0 + warp * 16) < nvirt;
 
-  // this thread's cp.async assignments: A: 4 x 16B, B: 2 x 16B per chunk
+  // this thread's cp.async assignments: A: TM / RPP x 16B, B: NB / RPP x 16B per chunk
   const int seg = tid & 7;                 // 16-byte chunk of the 128-byte row segment
-  const int r8 = tid >> 3;                 // 0..31
-  const int sseg = (seg ^ (r8 & 7)) << 1;  // swizzled element offset (row & 7 == r8 & 7)
-  const double *arow[4];
-  int abytes[4];
+  const int r8 = tid >> 3;                 // 0 .. RPP - 1
+  const int sseg = (seg ^ (r8 & 7)) << 1;  // swizzled element offset (row & 7 == r8 & 7: RPP % 8 == 0)
+  const double *arow[TM / RPP];
+  int abytes[TM / RPP];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
+  for (int i = 0; i < TM / RPP; ++i) {
     int kind;
-    double *p = rm.row(v0 + r8 + 32 * i, kind);
+    double *p = rm.row(v0 + r8 + RPP * i, kind);
     arow[i] = p ? p : rm.Kb;
     abytes[i] = p ? 16 : 0;
   }
-  const double *brow[2];
-  int bbytes[2];
+  const double *brow[NB / RPP];
+  int bbytes[NB / RPP];
 #pragma unroll
-  for (int i = 0; i < 2; ++i) {
-    int r = c0 + r8 + 32 * i;
+  for (int i = 0; i < NB / RPP; ++i) {
+    int r = c0 + r8 + RPP * i;
     brow[i] = (r < rm.n) ? rm.Kb + (size_t)r * rm.ld : rm.Kb;
     bbytes[i] = (r < rm.n) ? 16 : 0;
   }
@@ -357,8 +433,9 @@ __device__ __forceinline__ void gemm_tile(Smem &sm, const RowMap &rm, int v0, in
     if (tma_tile) {
       if (tid == 0) {
         mbar_arrive_expect_tx(&sm.full[st], (TM + NB) * KC * (unsigned)sizeof(double));
-        tma_load_3d(&sm.As[st][0][0], tmK, &sm.full[st], ch * KC, c0 + v0, item);
-        tma_load_3d(&sm.As[st][NB][0], tmK, &sm.full[st], ch * KC, c0 + v0 + NB, item);
+#pragma unroll
+        for (int bx = 0; bx < TM / 64; ++bx)   // boxes of 64 rows x 16 columns
+          tma_load_3d(&sm.As[st][64 * bx][0], tmK, &sm.full[st], ch * KC, c0 + v0 + 64 * bx, item);
         tma_load_3d(&sm.Bs[st][0][0], tmK, &sm.full[st], ch * KC, c0, item);
       } else {
         mbar_arrive(&sm.full[st]);
@@ -367,9 +444,9 @@ __device__ __forceinline__ void gemm_tile(Smem &sm, const RowMap &rm, int v0, in
     }
     const int k0 = ch * KC + seg * 2;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) cp_async16(&sm.As[st][r8 + 32 * i][sseg], arow[i] + k0, abytes[i]);
+    for (int i = 0; i < TM / RPP; ++i) cp_async16(&sm.As[st][r8 + RPP * i][sseg], arow[i] + k0, abytes[i]);
 #pragma unroll
-    for (int i = 0; i < 2; ++i) cp_async16(&sm.Bs[st][r8 + 32 * i][sseg], brow[i] + k0, bbytes[i]);
+    for (int i = 0; i < NB / RPP; ++i) cp_async16(&sm.Bs[st][r8 + RPP * i][sseg], brow[i] + k0, bbytes[i]);
     mbar_cp_async_arrive(&sm.full[st]);
     return true;
   };
@@ -380,51 +457,88 @@ __device__ __forceinline__ void gemm_tile(Smem &sm, const RowMap &rm, int v0, in
   for (int kk = 0; kk < KC / 4; ++kk) koff[kk] = swz(g, kk * 4 + tg);
 
   PROF_MARK(sm, 9);
-  issue(0, it, true);
-  if (nchunks > 1) issue(1, it + 1, true);
+#pragma unroll
+  for (int j = 0; j < LA; ++j)
+    if (j < nchunks) issue(j, it + j, true);
   PROF_MARK(sm, 0);
   init();
   PROF_MARK(sm, 1);
   for (int ch = 0; ch < nchunks; ++ch) {
     const unsigned x = it + ch;
     const unsigned st = x % STAGES;
-    // chunk ch + 2 goes to the slot of chunk ch - 1.  If every warp is already past that chunk the
-    // copies are issued NOW (two chunks of latency cover); otherwise after this chunk's math (one
-    // chunk of cover, but a warp never waits for a sibling that is at most one chunk behind).
+    // chunk ch + LA goes to the slot of chunk ch - 1.  If every warp is already past that chunk the
+    // copies are issued NOW (LA chunks of latency cover); otherwise after this chunk's math (one
+    // chunk less, but a warp never waits for a sibling that is at most one chunk behind).
     bool early = false;
-    if (ch + 2 < nchunks) early = issue(ch + 2, x + 2, false);
+    if (ch + LA < nchunks) early = issue(ch + LA, x + LA, false);
     mbar_wait(&sm.full[st], (x / STAGES) & 1u);  // chunk ch landed, for every thread's copies
 #ifdef SPB_POTRF_PROF
     if (ch == 0) PROF_MARK(sm, 2);
 #endif
     if (warp_live) {
-      const double *Aw = &sm.As[st][warp * 16 + g][0];
       const double *Bw = &sm.Bs[st][g][0];
-      if (nt_lim >= 8) {
+      if constexpr (!BAL) {
+        // ---- 8-warp geometry: the round-1 inner loops, verbatim
+        const double *Aw = &sm.As[st][warp * 16 + g][0];
+        if (lim0 >= 8) {
 #pragma unroll
-        for (int kk = 0; kk < KC / 4; ++kk) {
-          double a[2], b[8];
+          for (int kk = 0; kk < KC / 4; ++kk) {
+            double a[2], b[8];
 #pragma unroll
-          for (int mt = 0; mt < 2; ++mt) a[mt] = negate(Aw[mt * 8 * KC + koff[kk]]);
+            for (int mt = 0; mt < 2; ++mt) a[mt] = negate(Aw[mt * 8 * KC + koff[kk]]);
 #pragma unroll
-          for (int nt = 0; nt < 8; ++nt) b[nt] = Bw[nt * 8 * KC + koff[kk]];
+            for (int nt = 0; nt < 8; ++nt) b[nt] = Bw[nt * 8 * KC + koff[kk]];
 #pragma unroll
-          for (int mt = 0; mt < 2; ++mt)
+            for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-            for (int nt = 0; nt < 8; ++nt) dmma_m8n8k4(acc[mt][nt][0], acc[mt][nt][1], a[mt], b[nt]);
+              for (int nt = 0; nt < 8; ++nt) dmma_m8n8k4(acc[mt][nt][0], acc[mt][nt][1], a[mt], b[nt]);
+          }
+        } else {
+#pragma unroll
+          for (int kk = 0; kk < KC / 4; ++kk) {
+            double a[2];
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) a[mt] = negate(Aw[mt * 8 * KC + koff[kk]]);
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) {
+              if (nt < lim0) {
+                const double b = Bw[nt * 8 * KC + koff[kk]];
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt) dmma_m8n8k4(acc[mt][nt][0], acc[mt][nt][1], a[mt], b);
+              }
+            }
+          }
         }
       } else {
+        const double *Aw0 = &sm.As[st][ar0 + g][0];
+        const double *Aw1 = &sm.As[st][ar1 + g][0];
+        if (!diag_warp) {
 #pragma unroll
-        for (int kk = 0; kk < KC / 4; ++kk) {
-          double a[2];
+          for (int kk = 0; kk < KC / 4; ++kk) {
+            double a[2], b[8];
+            a[0] = negate(Aw0[koff[kk]]);
+            a[1] = negate(Aw1[koff[kk]]);
 #pragma unroll
-          for (int mt = 0; mt < 2; ++mt) a[mt] = negate(Aw[mt * 8 * KC + koff[kk]]);
+            for (int nt = 0; nt < 8; ++nt) b[nt] = Bw[nt * 8 * KC + koff[kk]];
 #pragma unroll
-          for (int nt = 0; nt < 8; ++nt) {
-            if (nt < nt_lim) {
-              const double b = Bw[nt * 8 * KC + koff[kk]];
+            for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-              for (int mt = 0; mt < 2; ++mt) dmma_m8n8k4(acc[mt][nt][0], acc[mt][nt][1], a[mt], b);
+              for (int nt = 0; nt < 8; ++nt) dmma_m8n8k4(acc[mt][nt][0], acc[mt][nt][1], a[mt], b[nt]);
+          }
+        } else {
+          // rows of the diagonal block: m-tile mt only reaches the diagonal in its first lim_mt
+          // 8-column groups; the rest of the warp tile is never consumed and is not multiplied
+#pragma unroll
+          for (int kk = 0; kk < KC / 4; ++kk) {
+            const double a0 = negate(Aw0[koff[kk]]);
+            const double a1 = negate(Aw1[koff[kk]]);
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) {
+              if (nt < lim0 || nt < lim1) {   // warp-uniform
+                const double b = Bw[nt * 8 * KC + koff[kk]];
+                if (nt < lim0) dmma_m8n8k4(acc[0][nt][0], acc[0][nt][1], a0, b);
+                if (nt < lim1) dmma_m8n8k4(acc[1][nt][0], acc[1][nt][1], a1, b);
+              }
             }
           }
         }
@@ -432,7 +546,7 @@ __device__ __forceinline__ void gemm_tile(Smem &sm, const RowMap &rm, int v0, in
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&sm.empty[st]);
-    if (!early && ch + 2 < nchunks) issue(ch + 2, x + 2, true);
+    if (!early && ch + LA < nchunks) issue(ch + LA, x + LA, true);
   }
   it += nchunks;
   PROF_MARK(sm, 3);
@@ -452,7 +566,8 @@ __device__ __forceinline__ double c_to_a(double d0, double d1, int q, int lane) 
 // block column X_kb = P_kb Dinv_kb^T is known it is pushed into every later block,
 // P_nb -= X_kb L[nb,kb]^T, so each step issues 4 (7 - kb) independent DMMAs and only two A
 // fragments per m-tile are live (the left-looking form kept all 16 and serialised 2 nb DMMAs).
-__device__ __forceinline__ void trsm_warp(const Smem &sm, double (&acc)[2][8][2], int lane) {
+template <class SM>
+__device__ __forceinline__ void trsm_warp(const SM &sm, double (&acc)[2][8][2], int lane) {
   const int g = lane >> 2, tg = lane & 3;
 #pragma unroll
   for (int kb = 0; kb < 8; ++kb) {
@@ -474,7 +589,7 @@ __device__ __forceinline__ void trsm_warp(const Smem &sm, double (&acc)[2][8][2]
     for (int nb = kb + 1; nb < 8; ++nb) {
 #pragma unroll
       for (int q = 0; q < 2; ++q) {
-        const double b = sm.Ld[nb * 8 + g][kb * 8 + q * 4 + tg];
+        const double b = sm.Ld.at(nb * 8 + g, kb * 8 + q * 4 + tg);
 #pragma unroll
         for (int mt = 0; mt < 2; ++mt) dmma_m8n8k4(acc[mt][nb][0], acc[mt][nb][1], xa[mt][q], b);
       }
@@ -517,23 +632,25 @@ __device__ __forceinline__ void store_rows(const RowMap &rm, int v, int c0, int 
   }
 }
 
-// The inverses of the eight 8x8 diagonal blocks of sm.Ld: warp w, lane c < 8 -> column c of
-// block w.
-__device__ __forceinline__ void diag_inverses(Smem &sm) {
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  if (lane < 8) {
-    const int o = warp * 8;
+// The inverses of the eight 8x8 diagonal blocks of sm.Ld: thread (blk, c) with c < 8 -> column c of
+// block blk (MODE_SOLVE only).
+template <class SM>
+__device__ __forceinline__ void diag_inverses(SM &sm) {
+  const int tid = threadIdx.x;
+  if (tid < 64) {
+    const int blk = tid >> 3, c = tid & 7;
+    const int o = blk * 8;
     double x[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      double s = (i == lane) ? 1.0 : 0.0;
+      double sacc = (i == c) ? 1.0 : 0.0;
 #pragma unroll
       for (int k = 0; k < 8; ++k)
-        if (k < i && k >= lane) s -= sm.Ld[o + i][o + k] * x[k];
-      x[i] = (i >= lane) ? s / sm.Ld[o + i][o + i] : 0.0;
+        if (k < i && k >= c) sacc -= sm.Ld.at(o + i, o + k) * x[k];
+      x[i] = (i >= c) ? sacc / sm.Ld.at(o + i, o + i) : 0.0;
     }
 #pragma unroll
-    for (int i = 0; i < 8; ++i) sm.Dv[o + i][lane] = x[i];
+    for (int i = 0; i < 8; ++i) sm.Dv[o + i][c] = x[i];
   }
   __syncthreads();
 }
@@ -623,18 +740,26 @@ __device__ __forceinline__ double potf2_tile8(double &v0, double &v1, double &w0
 // is  8 pivots -> barrier -> 2 DMMAs -> barrier -> 2 DMMAs.  Warps 4-7 (rows below the block) keep
 // their accumulators in registers and wait at the CTA barrier that follows.
 // Produces sm.Ld (lower; strictly-upper 8x8 tiles untouched), sm.Dv and the pivots sm.dpiv = L_ii^2.
-__device__ __forceinline__ void potf2_regs(Smem &sm, double (&acc)[2][8][2], int warp, int lane) {
+template <class SM>
+__device__ __forceinline__ void potf2_regs(SM &sm, double (&acc)[2][8][2], int warp, int lane) {
   const int g = lane >> 2, tg = lane & 3;
+  // 8-row blocks of the diagonal tile held by this warp (see diag_block): m-tile 0 -> block warp,
+  // m-tile 1 -> block 7 - warp; block b lives in columns 0 .. 8 b + 7
+  constexpr bool BAL = SM::G::PACKED;
+  const int rb[2] = {diag_block<BAL>(warp, 0), diag_block<BAL>(warp, 1)};
   bool bad = false;
   PROF_DECL;
 #pragma unroll
   for (int s = 0; s < 8; ++s) {
     PROF_MARK(sm, 14);
-    if (warp == (s >> 1)) {
+    // owner of diagonal tile s.  balanced: warp s (m-tile 0) for s < 4, warp 7 - s (m-tile 1) for
+    // s >= 4; natural: warp s / 2, m-tile s % 2
+    if (warp == (BAL ? ((s < 4) ? s : 7 - s) : (s >> 1))) {
       double w0, w1;
-      const double dg = potf2_tile8(acc[s & 1][s][0], acc[s & 1][s][1], w0, w1, lane, bad);
-      *reinterpret_cast<double2 *>(&sm.Ld[8 * s + g][8 * s + 2 * tg]) =
-          make_double2(acc[s & 1][s][0], acc[s & 1][s][1]);
+      const int omt = BAL ? (s < 4 ? 0 : 1) : (s & 1);   // compile-time after unrolling
+      double &t0 = acc[omt][s][0], &t1 = acc[omt][s][1];
+      const double dg = potf2_tile8(t0, t1, w0, w1, lane, bad);
+      *reinterpret_cast<double2 *>(&sm.Ld.at(8 * s + g, 8 * s + 2 * tg)) = make_double2(t0, t1);
       *reinterpret_cast<double2 *>(&sm.Dv[8 * s + g][2 * tg]) = make_double2(w0, w1);
       if (tg == 0) sm.dpiv[8 * s + g] = dg;
       PROF_MARK(sm, 11);
@@ -647,13 +772,13 @@ __device__ __forceinline__ void potf2_regs(Smem &sm, double (&acc)[2][8][2], int
         double xq[2];
 #pragma unroll
         for (int mt = 0; mt < 2; ++mt)
-          xq[mt] = negate(sm.Ld[16 * warp + 8 * mt + g][8 * (s - 1) + 4 * q + tg]);
+          xq[mt] = negate(sm.Ld.at(8 * max(rb[mt], s) + g, 8 * (s - 1) + 4 * q + tg));
 #pragma unroll
         for (int nt = s + 1; nt < 8; ++nt) {
-          const double b = sm.Ld[8 * nt + g][8 * (s - 1) + 4 * q + tg];
+          const double b = sm.Ld.at(8 * nt + g, 8 * (s - 1) + 4 * q + tg);
 #pragma unroll
           for (int mt = 0; mt < 2; ++mt)
-            if (nt <= 2 * warp + mt) dmma_m8n8k4(acc[mt][nt][0], acc[mt][nt][1], xq[mt], b);
+            if (nt <= rb[mt]) dmma_m8n8k4(acc[mt][nt][0], acc[mt][nt][1], xq[mt], b);
         }
       }
     }
@@ -664,7 +789,7 @@ __device__ __forceinline__ void potf2_regs(Smem &sm, double (&acc)[2][8][2], int
       const double d0 = sm.Dv[8 * s + g][tg], d1 = sm.Dv[8 * s + g][4 + tg];
 #pragma unroll
       for (int mt = 0; mt < 2; ++mt) {
-        if (2 * warp + mt > s) {
+        if (rb[mt] > s) {
           const double a0 = c_to_a(acc[mt][s][0], acc[mt][s][1], 0, lane);
           const double a1 = c_to_a(acc[mt][s][0], acc[mt][s][1], 1, lane);
           double x0 = 0.0, x1 = 0.0;
@@ -672,7 +797,7 @@ __device__ __forceinline__ void potf2_regs(Smem &sm, double (&acc)[2][8][2], int
           dmma_m8n8k4(x0, x1, a1, d1);
           acc[mt][s][0] = x0;
           acc[mt][s][1] = x1;
-          *reinterpret_cast<double2 *>(&sm.Ld[16 * warp + 8 * mt + g][8 * s + 2 * tg]) =
+          *reinterpret_cast<double2 *>(&sm.Ld.at(8 * rb[mt] + g, 8 * s + 2 * tg)) =
               make_double2(x0, x1);
           xa[mt][0] = negate(c_to_a(x0, x1, 0, lane));
           xa[mt][1] = negate(c_to_a(x0, x1, 1, lane));
@@ -684,10 +809,10 @@ __device__ __forceinline__ void potf2_regs(Smem &sm, double (&acc)[2][8][2], int
     if (s < 7) {  // critical path: column s + 1 only
 #pragma unroll
       for (int q = 0; q < 2; ++q) {
-        const double b = sm.Ld[8 * (s + 1) + g][8 * s + 4 * q + tg];
+        const double b = sm.Ld.at(8 * (s + 1) + g, 8 * s + 4 * q + tg);
 #pragma unroll
         for (int mt = 0; mt < 2; ++mt)
-          if (s + 1 <= 2 * warp + mt)
+          if (s + 1 <= rb[mt])
             dmma_m8n8k4(acc[mt][s + 1][0], acc[mt][s + 1][1], xa[mt][q], b);
       }
     }
@@ -696,7 +821,9 @@ __device__ __forceinline__ void potf2_regs(Smem &sm, double (&acc)[2][8][2], int
   PROF_MARK(sm, 14);
 }
 
-__device__ __forceinline__ double block_sum(Smem &sm, double v) {
+template <class SM>
+__device__ __forceinline__ double block_sum(SM &sm, double v) {
+  constexpr int NTHREADS = SM::NTHREADS;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   v = warp_sum(v);
   __syncthreads();
@@ -709,10 +836,12 @@ __device__ __forceinline__ double block_sum(Smem &sm, double v) {
   return t;
 }
 
-__global__ void __launch_bounds__(NTHREADS, 2)
+template <int TM, int STAGES, int MIN_CTAS>
+__global__ void __launch_bounds__(Geo<TM>::NTHREADS, MIN_CTAS)
     potrf_lnlike_kernel(PotrfParams p, const __grid_constant__ CUtensorMap tmK) {
+  constexpr int NTHREADS = Geo<TM>::NTHREADS;
   extern __shared__ __align__(1024) unsigned char smem_raw[];   // TMA 128-byte swizzle: 1 KB aligned
-  Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
+  Smem<TM, STAGES> &sm = *reinterpret_cast<Smem<TM, STAGES> *>(smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, tg = lane & 3;
 
   int nitems;
@@ -808,20 +937,20 @@ __global__ void __launch_bounds__(NTHREADS, 2)
             if (c0 + i < p.n) v = rm.Kb[(size_t)(c0 + i) * p.ld + c0 + j];
             else v = (i == j) ? 1.0 : 0.0;
           }
-          sm.Ld[i][j] = v;
+          sm.Ld.at(i, j) = v;
         }
         __syncthreads();
         diag_inverses(sm);
       }
       for (int v0 = 0; v0 < nvirt; v0 += TM) {
-        // MODE_FACTOR, first tile: rows 0..63 are the diagonal block (warps 0-3), rows 64..127 the
-        // first rows below it (warps 4-7)
+        // MODE_FACTOR, first tile: rows 0..63 are the diagonal block (warps 0-3, 8-row blocks dealt
+        // as (w, 7 - w): tile_vrow); with TM = 128 rows 64..127 are the first rows below it (warps 4-7)
         const bool diag_tile = (p.mode == MODE_FACTOR) && (v0 == 0);
-        gemm_tile(sm, rm, v0, c0, nvirt, (diag_tile && warp < 4) ? 2 * warp + 2 : 8, it, acc, [&]() {
+        gemm_tile(sm, rm, v0, c0, nvirt, diag_tile, it, acc, [&]() {
 #pragma unroll
           for (int mt = 0; mt < 2; ++mt)
-            init_acc(sm, rm, af, p.aff_on != 0, v0 + warp * 16 + mt * 8 + g, c0, tg, full_panel,
-                     acc[mt]);
+            init_acc(sm, rm, af, p.aff_on != 0, tile_vrow<Geo<TM>::PACKED>(diag_tile, v0, warp, mt, g),
+                     c0, tg, full_panel, acc[mt]);
         }, p.use_tma ? &tmK : nullptr, item);   // acc = K - L L^T = P
 #ifdef SPB_POTRF_PROF
         _pt = clock64();
@@ -836,7 +965,7 @@ __global__ void __launch_bounds__(NTHREADS, 2)
           // write L_jj back (lower triangle, valid rows/cols only)
           for (int idx = tid; idx < NB * NB; idx += NTHREADS) {
             const int i = idx >> 6, j = idx & 63;
-            if (j <= i && c0 + i < p.n) rm.Kb[(size_t)(c0 + i) * p.ld + c0 + j] = sm.Ld[i][j];
+            if (j <= i && c0 + i < p.n) rm.Kb[(size_t)(c0 + i) * p.ld + c0 + j] = sm.Ld.at(i, j);
           }
           PROF_MARK(sm, 4);
         }
@@ -890,6 +1019,338 @@ __global__ void __launch_bounds__(NTHREADS, 2)
 }
 
 // ------------------------------------------------------------------------------------------
+// Warp-specialised batch kernel: 4 COMPUTE warps (one 64-row tile at a time, 16 rows x 64 columns
+// per warp, exactly the arithmetic of potrf_lnlike_kernel<64, ...>) + 1 PRODUCER warp that does
+// nothing but feed the operand ring.
+//
+// Why (scripts/micro/ring_micro.cu, measured on B200): with the copies requested from inside the
+// compute warps -- whichever thread does it -- the k-loop of a lone CTA reaches 78 % of the DMMA
+// peak (88 % with two CTAs per SM): the issuing warp waits for the slowest sibling to release a
+// slot, pays the TMA issue latency, and everyone then waits for that warp.  With a dedicated
+// producer warp the same loop reaches 91 % (93 %).  The producer walks the same sequence of
+// (panel, tile, chunk) as the consumers, bounded only by the empty[] barriers, so the ring never
+// drains between tiles or panels; the only true dependence -- chunks that read columns written
+// during the previous panel -- is an mbarrier (`panel`) the compute warps arrive on after their
+// stores and fence.proxy.async.  Tiles that mix matrix rows with appended right-hand-side rows (and
+// every tile of MODE_SOLVE) are copied by the 32 producer lanes with cp.async into the same swizzle.
+// ------------------------------------------------------------------------------------------
+constexpr int WS_TM = 64;
+constexpr int WS_NCT = 128;              // compute threads
+constexpr int WS_NTHREADS = WS_NCT + 32;
+
+template <int STAGES_>
+struct SmemWS : Smem<WS_TM, STAGES_> {
+  uint64_t panel;   // panel complete (its global stores fenced): 1 arrival (compute thread 0)
+};
+
+__device__ __forceinline__ void cbar() {  // the 128 compute threads (named barrier 2)
+  asm volatile("bar.sync 2, 128;\n" ::: "memory");
+}
+
+template <class SM>
+__device__ __forceinline__ double block_sum_ws(SM &sm, double v) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  v = warp_sum(v);
+  cbar();
+  if (lane == 0) sm.red[warp] = v;
+  cbar();
+  double t = 0.0;
+#pragma unroll
+  for (int w = 0; w < WS_NCT / 32; ++w) t += sm.red[w];
+  cbar();
+  return t;
+}
+
+template <int STAGES, int MIN_CTAS>
+__global__ void __launch_bounds__(WS_NTHREADS, MIN_CTAS)
+    potrf_ws_kernel(PotrfParams p, const __grid_constant__ CUtensorMap tmK) {
+  constexpr int TM = WS_TM;
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  using SM = SmemWS<STAGES>;
+  SM &sm = *reinterpret_cast<SM *>(smem_raw);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, tg = lane & 3;
+  const bool producer = (warp == WS_NCT / 32);
+
+  const int nitems = (p.mode == MODE_FACTOR) ? p.B : (p.M + p.rows_per_cta - 1) / p.rows_per_cta;
+  if (tid == 0) {
+#pragma unroll
+    for (int st = 0; st < STAGES; ++st) {
+      mbar_init(&sm.full[st], 32);          // the 32 producer lanes (lane 0 carries the TMA bytes)
+      mbar_init(&sm.empty[st], WS_NCT / 32);  // one arrival per compute warp
+    }
+    mbar_init(&sm.panel, 1);
+  }
+  __syncthreads();
+  unsigned it = 0;       // running k-chunk count (ring slot / phase), identical in both roles
+  unsigned npanel = 0;   // running count of completed panels (phase of sm.panel)
+
+  for (int item = blockIdx.x; item < nitems;) {
+    RowMap rm;
+    rm.n = p.n;
+    rm.ld = p.ld;
+    rm.ldr = p.ldr;
+    rm.mode = p.mode;
+    double *quad_out;
+    if (p.mode == MODE_FACTOR) {
+      rm.Kb = p.K + (size_t)item * p.strideK;
+      rm.Rb = p.R ? p.R + (size_t)item * p.strideR : nullptr;
+      rm.M = p.R ? p.M : 0;
+      rm.rb = 0;
+      rm.nrhs = rm.M;
+      quad_out = p.quad ? p.quad + (size_t)item * p.M : nullptr;
+    } else {
+      rm.Kb = p.K;
+      rm.Rb = p.R;
+      rm.M = p.M;
+      rm.rb = item * p.rows_per_cta;
+      rm.nrhs = min(p.rows_per_cta, p.M - rm.rb);
+      quad_out = p.quad;
+    }
+
+    if (producer) {
+      // ================================ producer warp ================================
+      for (int c0 = 0; c0 < p.n; c0 += NB) {
+        rm.c0 = c0;
+        rm.nbelow = max(0, p.n - c0 - NB);
+        const int nvirt = (p.mode == MODE_FACTOR) ? NB + rm.nbelow + rm.M : rm.nrhs;
+        const int nchunks = c0 / KC;
+        // chunks >= dep read columns that the PREVIOUS panel of this matrix wrote
+        const int dep = (p.mode == MODE_FACTOR && c0 >= NB) ? (c0 - NB) / KC : nchunks;
+        bool waited = false;
+        for (int v0 = 0; v0 < nvirt; v0 += TM) {
+          const bool tma_tile = p.use_tma && p.mode == MODE_FACTOR && (c0 + v0 + TM <= p.n);
+          // rows copied by this lane on the cp.async path: A rows lane, lane + 32; B rows likewise
+          const double *arow[TM / 32], *brow[NB / 32];
+          int abytes[TM / 32], bbytes[NB / 32];
+          if (!tma_tile) {
+#pragma unroll
+            for (int i = 0; i < TM / 32; ++i) {
+              int kind;
+              double *q = rm.row(v0 + lane + 32 * i, kind);
+              arow[i] = q ? q : rm.Kb;
+              abytes[i] = q ? 16 : 0;
+            }
+#pragma unroll
+            for (int i = 0; i < NB / 32; ++i) {
+              const int r = c0 + lane + 32 * i;
+              brow[i] = (r < rm.n) ? rm.Kb + (size_t)r * rm.ld : rm.Kb;
+              bbytes[i] = (r < rm.n) ? 16 : 0;
+            }
+          }
+          for (int ch = 0; ch < nchunks; ++ch) {
+            if (!waited && ch >= dep) {
+              // previous panel complete and visible to the async proxy (npanel panels done so far)
+              mbar_wait(&sm.panel, (npanel + 1u) & 1u);
+              waited = true;
+            }
+            const unsigned x = it + ch;
+            const unsigned st = x % STAGES;
+            mbar_wait(&sm.empty[st], ((x / STAGES) + 1u) & 1u);   // slot released by every warp
+            if (tma_tile) {
+              if (lane == 0) {
+                mbar_arrive_expect_tx(&sm.full[st], (TM + NB) * KC * (unsigned)sizeof(double));
+                tma_load_3d(&sm.As[st][0][0], &tmK, &sm.full[st], ch * KC, c0 + v0, item);
+                tma_load_3d(&sm.Bs[st][0][0], &tmK, &sm.full[st], ch * KC, c0, item);
+              } else {
+                mbar_arrive(&sm.full[st]);
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < TM / 32; ++i) {
+                const int r = lane + 32 * i;
+#pragma unroll
+                for (int sg = 0; sg < 8; ++sg)
+                  cp_async16(&sm.As[st][r][(sg ^ (r & 7)) << 1], arow[i] + ch * KC + 2 * sg, abytes[i]);
+              }
+#pragma unroll
+              for (int i = 0; i < NB / 32; ++i) {
+                const int r = lane + 32 * i;
+#pragma unroll
+                for (int sg = 0; sg < 8; ++sg)
+                  cp_async16(&sm.Bs[st][r][(sg ^ (r & 7)) << 1], brow[i] + ch * KC + 2 * sg, bbytes[i]);
+              }
+              mbar_cp_async_arrive(&sm.full[st]);
+            }
+          }
+          it += nchunks;
+        }
+        if (p.mode == MODE_FACTOR && c0 >= NB && !waited) {   // (nchunks > dep always: defensive)
+          mbar_wait(&sm.panel, (npanel + 1u) & 1u);
+        }
+        if (p.mode == MODE_FACTOR) npanel += 1;
+      }
+    } else {
+      // ================================ compute warps ================================
+      AffRow af;
+      af.q = nullptr;
+      af.dg = nullptr;
+      af.dg_vec = 0;
+      af.norm = false;
+      if (p.aff_on && p.mode == MODE_FACTOR) {
+        af.norm = (p.aff.scal != nullptr) && (p.aff.q != nullptr);
+        if (af.norm) af.q = p.aff.q + (size_t)item * p.n;
+        if (p.aff.diag) {
+          af.dg = p.aff.diag + (size_t)item * p.aff.diag_stride;
+          af.dg_vec = (p.aff.diag_kind == 1);
+        }
+        if (tid == 0) {
+          sm.af[0] = af.norm ? p.aff.scal[4 * (size_t)item + 0] : 1.0;
+          sm.af[1] = af.norm ? p.aff.scal[4 * (size_t)item + 1] : 0.0;
+          sm.af[2] = af.norm ? p.aff.scal[4 * (size_t)item + 2] : 0.0;
+          sm.af[3] = p.aff.offset ? p.aff.offset[(size_t)item * p.aff.offset_stride] : 0.0;
+        }
+      }
+      if (tid == 0) sm.bad = 0;
+      if (quad_out) {
+        if (p.mode == MODE_FACTOR) {
+          for (int m = tid; m < rm.M; m += WS_NCT) quad_out[m] = 0.0;
+        } else {
+          for (int m = tid; m < rm.nrhs; m += WS_NCT) quad_out[rm.rb + m] = 0.0;
+        }
+      }
+      cbar();
+
+      double logdet_part = 0.0, quad_part = 0.0;
+      double acc[2][8][2];
+      int koff[KC / 4];
+#pragma unroll
+      for (int kk = 0; kk < KC / 4; ++kk) koff[kk] = swz(g, kk * 4 + tg);
+
+      for (int c0 = 0; c0 < p.n; c0 += NB) {
+        rm.c0 = c0;
+        rm.nbelow = max(0, p.n - c0 - NB);
+        const int nvirt = (p.mode == MODE_FACTOR) ? NB + rm.nbelow + rm.M : rm.nrhs;
+        const int nchunks = c0 / KC;
+        const bool full_panel = (c0 + NB <= p.n);
+        if (p.mode == MODE_SOLVE) {
+          // fetch L_jj (identity-padded) and invert its 8x8 diagonal blocks
+          for (int idx = tid; idx < NB * NB; idx += WS_NCT) {
+            const int i = idx >> 6, j = idx & 63;
+            double v = 0.0;
+            if (j <= i) {
+              if (c0 + i < p.n) v = rm.Kb[(size_t)(c0 + i) * p.ld + c0 + j];
+              else v = (i == j) ? 1.0 : 0.0;
+            }
+            sm.Ld.at(i, j) = v;
+          }
+          cbar();
+          if (tid < 64) {
+            const int blk = tid >> 3, c = tid & 7, o = blk * 8;
+            double xs[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              double sacc = (i == c) ? 1.0 : 0.0;
+#pragma unroll
+              for (int k = 0; k < 8; ++k)
+                if (k < i && k >= c) sacc -= sm.Ld.at(o + i, o + k) * xs[k];
+              xs[i] = (i >= c) ? sacc / sm.Ld.at(o + i, o + i) : 0.0;
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) sm.Dv[o + i][c] = xs[i];
+          }
+          cbar();
+        }
+        for (int v0 = 0; v0 < nvirt; v0 += TM) {
+          const bool diag_tile = (p.mode == MODE_FACTOR) && (v0 == 0);
+          const bool warp_live = diag_tile || (v0 + warp * 16) < nvirt;
+          // accumulators <- K (or residual) rows: the loads overlap the wait for the first chunk
+#pragma unroll
+          for (int mt = 0; mt < 2; ++mt)
+            init_acc(sm, rm, af, p.aff_on != 0, tile_vrow<true>(diag_tile, v0, warp, mt, g), c0, tg,
+                     full_panel, acc[mt]);
+          // ---- k-loop: acc -= A[rows][k] L[c0 + cols][k], operands from the ring
+          const int ar0 = tile_vrow<true>(diag_tile, v0, warp, 0, 0) - v0;
+          const int ar1 = tile_vrow<true>(diag_tile, v0, warp, 1, 0) - v0;
+          const int lim0 = diag_tile ? diag_block<true>(warp, 0) + 1 : 8;
+          const int lim1 = diag_tile ? diag_block<true>(warp, 1) + 1 : 8;
+          for (int ch = 0; ch < nchunks; ++ch) {
+            const unsigned x = it + ch;
+            const unsigned st = x % STAGES;
+            mbar_wait(&sm.full[st], (x / STAGES) & 1u);
+            if (warp_live) {
+              const double *Aw0 = &sm.As[st][ar0 + g][0];
+              const double *Aw1 = &sm.As[st][ar1 + g][0];
+              const double *Bw = &sm.Bs[st][g][0];
+              if (!diag_tile) {
+#pragma unroll
+                for (int kk = 0; kk < KC / 4; ++kk) {
+                  double a[2], b[8];
+                  a[0] = negate(Aw0[koff[kk]]);
+                  a[1] = negate(Aw1[koff[kk]]);
+#pragma unroll
+                  for (int nt = 0; nt < 8; ++nt) b[nt] = Bw[nt * 8 * KC + koff[kk]];
+#pragma unroll
+                  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                    for (int nt = 0; nt < 8; ++nt)
+                      dmma_m8n8k4(acc[mt][nt][0], acc[mt][nt][1], a[mt], b[nt]);
+                }
+              } else {
+#pragma unroll
+                for (int kk = 0; kk < KC / 4; ++kk) {
+                  const double a0 = negate(Aw0[koff[kk]]);
+                  const double a1 = negate(Aw1[koff[kk]]);
+#pragma unroll
+                  for (int nt = 0; nt < 8; ++nt) {
+                    if (nt < lim0 || nt < lim1) {   // warp-uniform
+                      const double b = Bw[nt * 8 * KC + koff[kk]];
+                      if (nt < lim0) dmma_m8n8k4(acc[0][nt][0], acc[0][nt][1], a0, b);
+                      if (nt < lim1) dmma_m8n8k4(acc[1][nt][0], acc[1][nt][1], a1, b);
+                    }
+                  }
+                }
+              }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sm.empty[st]);
+          }
+          it += nchunks;
+          if (diag_tile) {
+            potf2_regs(sm, acc, warp, lane);
+            cbar();  // L_jj and the inverses of its diagonal tiles are in shared memory
+            if (tid < min(NB, p.n - c0)) logdet_part += 0.5 * log(sm.dpiv[tid]);
+            for (int idx = tid; idx < NB * NB; idx += WS_NCT) {
+              const int i = idx >> 6, j = idx & 63;
+              if (j <= i && c0 + i < p.n) rm.Kb[(size_t)(c0 + i) * p.ld + c0 + j] = sm.Ld.at(i, j);
+            }
+          } else if ((v0 + warp * 16) < nvirt) {
+            trsm_warp(sm, acc, lane);
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt)
+              store_rows(rm, v0 + warp * 16 + mt * 8 + g, c0, tg, acc[mt], quad_part, quad_out);
+          }
+        }
+        // this thread's st.global of the panel must be visible to the async proxy (TMA) before the
+        // producer is told that the panel is complete
+        fence_proxy_async_global();
+        cbar();  // Ld/Dv are rewritten by the next panel; every thread's stores + fence are done
+        if (p.mode == MODE_FACTOR && tid == 0) mbar_arrive(&sm.panel);
+      }
+
+      // ---- reductions -> lnlike
+      const double quad = block_sum_ws(sm, quad_part);
+      const double logdet = block_sum_ws(sm, logdet_part);
+      if (p.mode == MODE_FACTOR && tid == 0) {
+        const bool bad = sm.bad != 0;
+        double ll = -0.5 * quad - (double)rm.M * logdet -
+                    0.5 * (double)p.n * (double)rm.M * 1.8378770664093453;  // log(2 pi)
+        const int prev = p.info ? (p.info[item] & ~SPB_INFO_NOT_PD) : 0;
+        if (bad || (prev & (SPB_INFO_Z_RANGE | SPB_INFO_BOUNDS)) || ll != ll) ll = -INFINITY;
+        if (p.lnlike) p.lnlike[item] = ll;
+        if (p.logdet) p.logdet[item] = bad ? NAN : logdet;
+        if (p.info) p.info[item] = prev | (bad ? SPB_INFO_NOT_PD : 0);
+      }
+      if (tid == 0) sm.next_item = (int)gridDim.x + (int)atomicAdd(p.counter, 1u);
+    }
+    // both roles: the producer has requested every chunk of this matrix, the compute warps have
+    // consumed them; the next work item is published
+    __syncthreads();
+    // (both roles advanced `it` identically: they walk the same panels / tiles / chunks)
+    item = sm.next_item;   // rewritten only at the end of the next matrix, long after this read
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // Small batches (B <= #SM / 2): ONE MATRIX PER THREAD-BLOCK CLUSTER of 8, 4 or 2 CTAs (SMs).
 //
 // A lone CTA needs 2.3 ms for a 1000 x 1000 matrix (one SM's tensor pipe, every serial phase
@@ -916,9 +1377,10 @@ __device__ __forceinline__ void cluster_barrier() {
 }
 
 template <int CLUSTER>
-__global__ void __launch_bounds__(NTHREADS, 1) potrf_cluster_kernel(PotrfParams p) {
+__global__ void __launch_bounds__(Geo<128>::NTHREADS, 1) potrf_cluster_kernel(PotrfParams p) {
+  constexpr int TM = 128, NTHREADS = Geo<128>::NTHREADS, STAGES = 3;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
+  Smem<128, 3> &sm = *reinterpret_cast<Smem<128, 3> *>(smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, tg = lane & 3;
   const int rank = (int)cluster_rank();
   const int item = blockIdx.x / CLUSTER;
@@ -982,10 +1444,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) potrf_cluster_kernel(PotrfParams 
     // ---- first tile of this CTA: k-loop (needs nothing from this panel)
     if (have_tile) {
       const int v0 = rank * TM;
-      gemm_tile(sm, rm, v0, c0, nvirt, (rank == 0 && warp < 4) ? 2 * warp + 2 : 8, it, acc, [&]() {
+      gemm_tile(sm, rm, v0, c0, nvirt, rank == 0, it, acc, [&]() {
 #pragma unroll
         for (int mt = 0; mt < 2; ++mt)
-          init_acc(sm, rm, af, p.aff_on != 0, v0 + warp * 16 + mt * 8 + g, c0, tg, full_panel, acc[mt]);
+          init_acc(sm, rm, af, p.aff_on != 0, tile_vrow<false>(rank == 0, v0, warp, mt, g), c0, tg,
+                   full_panel, acc[mt]);
       });
     }
     if (rank == 0) {
@@ -994,7 +1457,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) potrf_cluster_kernel(PotrfParams 
       if (tid < min(NB, p.n - c0)) logdet_part += 0.5 * log(sm.dpiv[tid]);
       for (int idx = tid; idx < NB * NB; idx += NTHREADS) {
         const int i = idx >> 6, j = idx & 63;
-        if (j <= i && c0 + i < p.n) rm.Kb[(size_t)(c0 + i) * p.ld + c0 + j] = sm.Ld[i][j];
+        if (j <= i && c0 + i < p.n) rm.Kb[(size_t)(c0 + i) * p.ld + c0 + j] = sm.Ld.at(i, j);
       }
       __threadfence();
     }
@@ -1004,16 +1467,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) potrf_cluster_kernel(PotrfParams 
       // (distributed shared memory; Ld and Dv are adjacent in Smem): the same operands as CTA 0
       // and the batch kernel use, hence bit-identical rows, and no second trip through L2
       const double2 *src = reinterpret_cast<const double2 *>(
-          cg::this_cluster().map_shared_rank(&sm.Ld[0][0], 0));
-      double2 *dst = reinterpret_cast<double2 *>(&sm.Ld[0][0]);
-      for (int idx = tid; idx < (NB * LS + NB * DS) / 2; idx += NTHREADS) dst[idx] = src[idx];
+          cg::this_cluster().map_shared_rank(&sm.Ld.v[0], 0));
+      double2 *dst = reinterpret_cast<double2 *>(&sm.Ld.v[0]);
+      for (int idx = tid; idx < (int)((sizeof(sm.Ld) + sizeof(sm.Dv)) / sizeof(double2)); idx += NTHREADS)
+        dst[idx] = src[idx];
       __syncthreads();
     }
     // ---- finish the first tile, then any further tiles of this CTA
     for (int ti = rank; ti < ntiles; ti += CLUSTER) {
       const int v0 = ti * TM;
       if (ti != rank) {
-        gemm_tile(sm, rm, v0, c0, nvirt, 8, it, acc, [&]() {
+        gemm_tile(sm, rm, v0, c0, nvirt, false, it, acc, [&]() {
 #pragma unroll
           for (int mt = 0; mt < 2; ++mt)
             init_acc(sm, rm, af, p.aff_on != 0, v0 + warp * 16 + mt * 8 + g, c0, tg, full_panel, acc[mt]);
@@ -1083,12 +1547,41 @@ static int potrf_launch(spb_context *ctx, PotrfParams &p, void *stream) {
   }
   SPB_CHECK_CUDA(cudaSetDevice(ctx->device));
   p.scratch = nullptr;
-  const size_t smem = sizeof(Smem);
+  const size_t smem = sizeof(Smem<128, 3>);   // cluster kernel and the TM = 128 batch kernel
+  // 0 = default: the 8-warp / 2-CTAs-per-SM geometry.  Measured inside the bench step on B200
+  // (profiles/r02_potrf_geometries.log): 55.9 ms per 4096 matrices against 57.5 ms for the 4-warp /
+  // 3-CTAs-per-SM geometry and 61.1 ms for the warp-specialised kernel -- the finer geometries win
+  // the k-loop (micro-benchmarks: 93 % of the DMMA peak with a producer warp against 88 %) but lose
+  // it again in the latency-bound phases, which stretch under two siblings instead of one.
+  int tile = ctx->opt_chol_tile;
+  if (tile == 0) tile = 128;
   static spb_once_flag attr_once;
   {
     const int st = spb_once_per_device(attr_once, ctx->device, [&]() -> int {
-      SPB_CHECK_CUDA(cudaFuncSetAttribute(potrf_lnlike_kernel,
-                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+#define SPB_POTRF_ATTR(TM_, S_, C_)                                                              \
+  SPB_CHECK_CUDA(cudaFuncSetAttribute(potrf_lnlike_kernel<TM_, S_, C_>,                          \
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize,               \
+                                      (int)sizeof(Smem<TM_, S_>)));                              \
+  SPB_CHECK_CUDA(cudaFuncSetAttribute(potrf_lnlike_kernel<TM_, S_, C_>,                          \
+                                      cudaFuncAttributePreferredSharedMemoryCarveout,            \
+                                      cudaSharedmemCarveoutMaxShared))
+      SPB_POTRF_ATTR(128, 3, 2);
+      SPB_POTRF_ATTR(64, 3, 3);
+      SPB_POTRF_ATTR(64, 5, 2);
+      SPB_POTRF_ATTR(64, 4, 2);
+      SPB_POTRF_ATTR(128, 6, 1);
+#undef SPB_POTRF_ATTR
+#define SPB_WS_ATTR(S_, C_)                                                                      \
+  SPB_CHECK_CUDA(cudaFuncSetAttribute(potrf_ws_kernel<S_, C_>,                                   \
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize,               \
+                                      (int)sizeof(SmemWS<S_>)));                                 \
+  SPB_CHECK_CUDA(cudaFuncSetAttribute(potrf_ws_kernel<S_, C_>,                                   \
+                                      cudaFuncAttributePreferredSharedMemoryCarveout,            \
+                                      cudaSharedmemCarveoutMaxShared))
+      SPB_WS_ATTR(3, 3);
+      SPB_WS_ATTR(4, 2);
+      SPB_WS_ATTR(5, 2);
+#undef SPB_WS_ATTR
       SPB_CHECK_CUDA(cudaFuncSetAttribute(potrf_cluster_kernel<8>,
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       SPB_CHECK_CUDA(cudaFuncSetAttribute(potrf_cluster_kernel<4>,
@@ -1102,7 +1595,7 @@ static int potrf_launch(spb_context *ctx, PotrfParams &p, void *stream) {
   int nitems = (p.mode == MODE_FACTOR) ? p.B : (p.M + p.rows_per_cta - 1) / p.rows_per_cta;
   // few matrices: one 8-CTA cluster per matrix instead of one CTA (see potrf_cluster_kernel)
   int cs = 0;
-  if (!ctx->opt_no_cluster && p.mode == MODE_FACTOR && p.n > 2 * TM && ctx->d_scratch &&
+  if (!ctx->opt_no_cluster && p.mode == MODE_FACTOR && p.n > 2 * 128 && ctx->d_scratch &&
       p.B * 2 <= ctx->num_sms) {
     // largest cluster size whose clusters are all co-resident (a second wave of clusters would
     // cost more than a smaller cluster: GPCs host a whole number of clusters), asked of the driver
@@ -1114,7 +1607,7 @@ static int potrf_launch(spb_context *ctx, PotrfParams &p, void *stream) {
           const int c = 8 >> k;
           cudaLaunchConfig_t q = {};
           q.gridDim = dim3((unsigned)(c * ctx->num_sms));
-          q.blockDim = dim3(NTHREADS);
+          q.blockDim = dim3(Geo<128>::NTHREADS);
           q.dynamicSmemBytes = smem;
           cudaLaunchAttribute a[1];
           a[0].id = cudaLaunchAttributeClusterDimension;
@@ -1143,7 +1636,7 @@ static int potrf_launch(spb_context *ctx, PotrfParams &p, void *stream) {
     p.counter = nullptr;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(p.B * cs));
-    cfg.blockDim = dim3(NTHREADS);
+    cfg.blockDim = dim3(Geo<128>::NTHREADS);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = (cudaStream_t)stream;
     cudaLaunchAttribute attr[1];
@@ -1159,13 +1652,20 @@ static int potrf_launch(spb_context *ctx, PotrfParams &p, void *stream) {
     SPB_LAUNCH_CHECK(ctx);
     return 0;
   }
-  int grid = nitems < 2 * ctx->num_sms ? nitems : 2 * ctx->num_sms;
+  // geometry variants (spb_set_option "cholesky_tile"): 128 -> TM 128, 3 stages, 2 CTAs/SM;
+  // 64 -> TM 64, 3 stages, 3 CTAs/SM; experiments: 645 -> TM 64, 5 stages, 2 CTAs/SM;
+  // 644 -> TM 64, 4 stages, 2 CTAs/SM; 1286 -> TM 128, 6 stages, 1 CTA/SM
+  // warp-specialised kernel (producer warp): 163 -> 3 stages, 3 CTAs/SM; 164 -> 4 stages, 2 CTAs/SM;
+  // 165 -> 5 stages, 2 CTAs/SM
+  const int per_sm = (tile == 64 || tile == 163) ? 3 : (tile == 1286) ? 1 : 2;
+  const int tm_rows = (tile == 128 || tile == 1286) ? 128 : 64;
+  int grid = nitems < per_sm * ctx->num_sms ? nitems : per_sm * ctx->num_sms;
   // tensor map of the batch of matrices for the TMA-fed operand ring: (columns, rows, matrix),
   // boxes of 16 columns x 64 rows, 128-byte swizzle
   CUtensorMap tmK;
   memset(&tmK, 0, sizeof(tmK));
   p.use_tma = 0;
-  if (!ctx->opt_no_tma && p.mode == MODE_FACTOR && p.n >= TM + NB) {
+  if (!ctx->opt_no_tma && p.mode == MODE_FACTOR && p.n >= tm_rows + NB) {
     const unsigned long long sk = p.strideK > 0 ? (unsigned long long)p.strideK : (unsigned long long)p.n * p.ld;
     int st = spb_encode_tmap_3d_f64(&tmK, p.K, (unsigned long long)p.ld, (unsigned long long)p.n,
                                     (unsigned long long)p.B, (unsigned long long)p.ld * 8, sk * 8, KC,
@@ -1175,7 +1675,20 @@ static int potrf_launch(spb_context *ctx, PotrfParams &p, void *stream) {
   p.counter = ctx->d_counters +
       (__atomic_fetch_add(&ctx->counter_next, 1u, __ATOMIC_RELAXED) % SPB_NUM_COUNTERS);
   SPB_CHECK_CUDA(cudaMemsetAsync(p.counter, 0, sizeof(unsigned int), (cudaStream_t)stream));
-  potrf_lnlike_kernel<<<grid, NTHREADS, smem, (cudaStream_t)stream>>>(p, tmK);
+#define SPB_POTRF_GO(TM_, S_, C_)                                                               \
+  potrf_lnlike_kernel<TM_, S_, C_><<<grid, Geo<TM_>::NTHREADS, sizeof(Smem<TM_, S_>), (cudaStream_t)stream>>>(p, tmK)
+  if (tile == 163)
+    potrf_ws_kernel<3, 3><<<grid, WS_NTHREADS, sizeof(SmemWS<3>), (cudaStream_t)stream>>>(p, tmK);
+  else if (tile == 164)
+    potrf_ws_kernel<4, 2><<<grid, WS_NTHREADS, sizeof(SmemWS<4>), (cudaStream_t)stream>>>(p, tmK);
+  else if (tile == 165)
+    potrf_ws_kernel<5, 2><<<grid, WS_NTHREADS, sizeof(SmemWS<5>), (cudaStream_t)stream>>>(p, tmK);
+  else if (tile == 128) SPB_POTRF_GO(128, 3, 2);
+  else if (tile == 645) SPB_POTRF_GO(64, 5, 2);
+  else if (tile == 644) SPB_POTRF_GO(64, 4, 2);
+  else if (tile == 1286) SPB_POTRF_GO(128, 6, 1);
+  else SPB_POTRF_GO(64, 3, 3);
+#undef SPB_POTRF_GO
   SPB_LAUNCH_CHECK(ctx);
   return 0;
 }
@@ -1259,7 +1772,10 @@ extern "C" int spb_cholesky_solve_rows(spb_context *ctx, int nt, const double *L
   // spread the RHS rows over the whole GPU in multiples of 16 rows (one warp's share)
   // one full 128-row tile per work item (a tile costs the same DMMA time however many of its
   // rows are live, so smaller items would only replicate the streaming of L)
-  p.rows_per_cta = TM;
+  {
+    const int tile = ctx->opt_chol_tile ? ctx->opt_chol_tile : 128;
+    p.rows_per_cta = (tile == 128 || tile == 1286) ? 128 : 64;
+  }
   return potrf_launch(ctx, p, stream);
 }
 
