@@ -84,6 +84,12 @@ size_t spb_ylm_moments_workspace_bytes(const spb_context *ctx, int B);
 int spb_ylm_moments(spb_context *ctx, int B, const double *r_deg, const double *a, const double *b,
                     const double *c, const double *n, double *mean_ylm, double *cov_ylm,
                     int32_t *info, void *workspace, size_t workspace_bytes, void *stream);
+/* Same with a UNIFORM prior on the spot radius over [r - dr, r + dr] (size.py:55-89, 116-125:
+ * Spot.get_e, Spot.get_eigE): dr_deg (B) in degrees, or NULL for the delta prior above.          */
+int spb_ylm_moments_dr(spb_context *ctx, int B, const double *r_deg, const double *dr_deg,
+                       const double *a, const double *b, const double *c, const double *n,
+                       double *mean_ylm, double *cov_ylm, int32_t *info, void *workspace,
+                       size_t workspace_bytes, void *stream);
 
 /* Cholesky factor of cov_ylm and prior draws -- sp.py:265-271, 489-509.
  *   L_ylm : (B,256,256) out, lower triangle (upper zeroed);  unit_normals: (B, nsamples, 256)

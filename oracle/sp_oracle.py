@@ -638,6 +638,32 @@ def Matern32Kernel(t1, t2, tau):
     return (1 + x) * np.exp(-x)
 
 
+def spot_profile_mean(theta, r, dr, sfac=300):
+    """size.py:55-62 (Spot.get_e): the sigmoid spot profile averaged over a uniform radius prior."""
+    with np.errstate(over="ignore"):
+        chim = np.exp(sfac * (r - dr - theta))
+        chip = np.exp(sfac * (r + dr - theta))
+        return 1.0 / (2 * dr * sfac) * np.log((1 + chim) / (1 + chip))
+
+
+def spot_profile_second_moment(theta, r, dr, sfac=300, cutoff=1.5):
+    """size.py:64-89 (Spot.get_eigE up to the matrix square root): E[b(theta_i) b(theta_j)] under the
+    uniform radius prior, evaluated for theta < cutoff (r + dr) only and zero beyond."""
+    kmax = int(np.argmax(theta / (r + dr) > cutoff))
+    t = theta[:kmax].reshape(1, -1)
+    with np.errstate(over="ignore", invalid="ignore", divide="ignore"):
+        chim = np.exp(sfac * (r - dr - t))
+        chip = np.exp(sfac * (r + dr - t))
+        ex = np.exp(sfac * (t - t.T))
+        term = np.log(1 + chim) - np.log(1 + chip)
+        C0 = (ex * term - term.T) / (1 - ex + 1.0e-15)
+        C0[np.arange(kmax), np.arange(kmax)] = (1 / (1 + chip) + chim / (1 + chim) - term - 1).reshape(-1)
+    C0 /= 2 * dr * sfac
+    C = np.zeros((theta.shape[0], theta.shape[0]))
+    C[:kmax, :kmax] = C0
+    return C
+
+
 class OracleProcess(object):
     """Eager NumPy restatement of ``StarryProcess`` (sp.py:38-284) for the lnlike hot path."""
 
@@ -646,7 +672,7 @@ class OracleProcess(object):
                  marginalize_over_inclination=DEFAULTS["marginalize_over_inclination"],
                  normalized=DEFAULTS["normalized"], covpts=DEFAULTS["covpts"], native="port",
                  skip_longitude_eigh=False, q_ulp_noise_seed=None, tau=None,
-                 temporal_kernel=Matern32Kernel, **kwargs):
+                 temporal_kernel=Matern32Kernel, dr=None, **kwargs):
         self.nat = get_native(native)
         # sp.py:225-232
         self.tau = None if tau is None else float(check_bounds("tau", tau, 0, np.inf))
@@ -676,11 +702,22 @@ class OracleProcess(object):
         # --- SizeIntegral (delta prior), size.py:93-115
         theta, Bp, idx = spot_Bp(ydeg)
         self.r = float(check_bounds("r", r * ang, 0, 0.5 * np.pi))
-        zz = 300 * (theta - self.r)           # size.py:45-47 (sfac = 300)
-        bprof = 1 / (1 + np.exp(-zz)) - 1
-        q_size = np.zeros(self.N)
-        q_size[idx] = Bp @ bprof
-        eig_size = q_size.reshape(-1, 1)
+        if dr is None:
+            zz = 300 * (theta - self.r)           # size.py:45-47 (sfac = 300)
+            bprof = 1 / (1 + np.exp(-zz)) - 1
+            q_size = np.zeros(self.N)
+            q_size[idx] = Bp @ bprof
+            eig_size = q_size.reshape(-1, 1)
+            self.dr = 0.0
+        else:
+            # uniform prior on the spot radius over [r - dr, r + dr], size.py:116-125
+            self.dr = float(check_bounds("dr", dr * ang, 0, 0.5 * np.pi))
+            q_size = np.zeros(self.N)
+            q_size[idx] = Bp @ spot_profile_mean(theta, self.r, self.dr)
+            self.Etilde = Bp @ spot_profile_second_moment(theta, self.r, self.dr) @ Bp.T
+            eig_size = np.zeros((self.N, self.N))
+            eig_size[np.ix_(idx, idx)] = matrix_sqrt(self.Etilde)
+        self.q_size = q_size
 
         # --- LatitudeIntegral, latitude.py:171-212
         abmin = kwargs.get("abmin", DEFAULTS["abmin"])

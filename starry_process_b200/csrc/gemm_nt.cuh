@@ -40,6 +40,8 @@ struct Desc {
   long long strideVec;
   const double *diag;      // (M)
   const int *rkeep;        // optional (batch): sqrtC chunk-skip rule, see k-loop
+  const double *ldeg;      // optional (batch, 16, 16): acc is multiplied by ldeg[b][l(m)][l(n)] first
+                           // (spot-size second moment of the uniform-dr prior, moments.cu)
   double alpha;
   double beta;             // EPI_AXPBY: C = alpha acc + beta C (C is not read when beta == 0)
 };
@@ -218,6 +220,11 @@ __global__ void __launch_bounds__(NTHREADS, 2) gemm_nt_kernel(Desc d) {
         } else {  // EPI_SYRK_COV
           if (n <= m) {
             const double *vb = d.vec + (size_t)b * d.strideVec;
+            if (d.ldeg) {
+              // degree of a Ylm index: l = floor(sqrt(n)), exact for n < 2^52
+              const int lm_ = (int)sqrt((double)m), ln_ = (int)sqrt((double)n);
+              v *= d.ldeg[(size_t)b * 256 + lm_ * 16 + ln_];
+            }
             v = d.scale[b] * (v - vb[m] * vb[n]);
             if (m == n) v += d.diag[m];
             Cb[(size_t)m * d.ldc + n] = v;

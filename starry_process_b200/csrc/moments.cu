@@ -33,6 +33,8 @@ constexpr int JS = 33;  // Jacobi smem stride
 
 struct K1Params {
   const double *r_deg, *a, *b, *c, *n;
+  const double *dr_deg;  // (B) half-width of the uniform spot-radius prior, or nullptr (delta prior)
+  double *E2;            // (B,16,16) spot-size second moment Etilde (dr prior only)
   int B;
   const double *tab;
   double *mom1;      // (B,256)   first moment before the contrast scaling
@@ -157,15 +159,99 @@ __global__ void __launch_bounds__(NT1, 2) moments_k1a(K1Params p) {
   const double tol = 1e-6;
   bool bad = !(r >= -tol && r <= 0.5 * 3.14159265358979323846 + tol) || !(aa >= -tol && aa <= 1 + tol) ||
              !(bb >= -tol && bb <= 1 + tol) || !(nn >= -tol);
+  const bool has_dr = p.dr_deg != nullptr;
+  const double dr = has_dr ? p.dr_deg[b] * ang : 0.0;
+  if (has_dr) bad = bad || !(dr >= -tol && dr <= 0.5 * 3.14159265358979323846 + tol);   // size.py:120
   if (aa < 1e-12) aa = 1e-12;  // latitude.py:180-182 (abmin)
   if (bb < 1e-12) bb = 1e-12;
 
-  // ---- spot profile, size.py:45-53 (sfac = 300)
+  // ---- spot profile, size.py:45-53 (sfac = 300); uniform radius prior: its mean over
+  // [r - dr, r + dr], size.py:55-62 (Spot.get_e)
   for (int s = tid; s < 1000; s += NT1) {
-    const double z = 300.0 * (tab[SPB_TAB_THETA + s] - r);
-    sm.bprof[s] = 1.0 / (1.0 + exp(-z)) - 1.0;
+    const double th = tab[SPB_TAB_THETA + s];
+    if (has_dr) {
+      const double chim = exp(300.0 * (r - dr - th));
+      const double chip = exp(300.0 * (r + dr - th));
+      sm.bprof[s] = 1.0 / (2 * dr * 300.0) * log((1 + chim) / (1 + chip));
+    } else {
+      const double z = 300.0 * (th - r);
+      sm.bprof[s] = 1.0 / (1.0 + exp(-z)) - 1.0;
+    }
   }
   __syncthreads();
+  if (has_dr) {
+    // ---- spot-size SECOND moment Etilde = Bp C Bp^T (16 x 16), size.py:64-86 (Spot.get_eigE before
+    // its matrix square root): C_ij = E[b(theta_i) b(theta_j)] under the uniform radius prior, only
+    // for theta < cutoff (r + dr), cutoff = 1.5.  The reference then carries sqrt(Etilde) through
+    // the latitude / longitude integrals and re-compresses twice; all of it is linear in the second
+    // moment, so the Ylm covariance is  Etilde[l1][l2] * (delta-prior second moment with q_l = 1)
+    // -- applied as a Hadamard factor in the SYRK epilogue (measured against the unmodified
+    // reference: 5e-14 relative on cov_ylm; its 1e-15 eigenvalue clips are below that).
+    //   W = C Bp^T in 256-row chunks (one row per thread, staged in sm.Y), then Etilde += Bp W.
+    int kmax = 0;   // numpy argmax of a boolean array: first True, 0 when none
+    for (int s = 0; s < 1000; ++s)
+      if (tab[SPB_TAB_THETA + s] / (r + dr) > 1.5) {
+        kmax = s;
+        break;
+      }
+    double *Wst = &sm.Y[0][0];          // [256][16] staging (Y is not live yet)
+    double *Bst = Wst + 256 * 16;       // [16][64]  Bp tile
+    double eacc = 0.0;                  // thread (l1, l2) = (tid / 16, tid % 16)
+    const double inv2 = 1.0 / (2 * dr * 300.0);
+    for (int i0 = 0; i0 < kmax; i0 += NT1) {
+      const int i = i0 + tid;
+      const bool live = i < kmax;
+      const double ti = live ? tab[SPB_TAB_THETA + i] : 0.0;
+      double term_i = 0.0, diag_i = 0.0;
+      if (live) {
+        const double chim = exp(300.0 * (r - dr - ti)), chip = exp(300.0 * (r + dr - ti));
+        term_i = log(1 + chim) - log(1 + chip);
+        diag_i = 1 / (1 + chip) + chim / (1 + chim) - term_i - 1;
+      }
+      double wrow[16];
+#pragma unroll
+      for (int l = 0; l < 16; ++l) wrow[l] = 0.0;
+      for (int j0 = 0; j0 < kmax; j0 += 64) {
+        __syncthreads();
+        for (int k = tid; k < 16 * 64; k += NT1) {
+          const int l = k >> 6, jj = k & 63;
+          Bst[k] = (j0 + jj < kmax) ? tab[SPB_TAB_BP + (size_t)l * 1000 + j0 + jj] : 0.0;
+        }
+        __syncthreads();
+        if (live) {
+          const int jn = min(64, kmax - j0);
+          for (int jj = 0; jj < jn; ++jj) {
+            const int j = j0 + jj;
+            const double tj = tab[SPB_TAB_THETA + j];
+            double cij;
+            if (j == i) {
+              cij = diag_i;
+            } else {
+              const double chim = exp(300.0 * (r - dr - tj)), chip = exp(300.0 * (r + dr - tj));
+              const double term_j = log(1 + chim) - log(1 + chip);
+              const double ex = exp(300.0 * (tj - ti));
+              cij = (ex * term_j - term_i) / (1 - ex + 1.0e-15);
+            }
+            cij *= inv2;
+#pragma unroll
+            for (int l = 0; l < 16; ++l) wrow[l] = fma(cij, Bst[l * 64 + jj], wrow[l]);
+          }
+        }
+      }
+      __syncthreads();
+#pragma unroll
+      for (int l = 0; l < 16; ++l) Wst[tid * 16 + l] = live ? wrow[l] : 0.0;
+      __syncthreads();
+      {
+        const int l1 = tid >> 4, l2 = tid & 15;
+        const int in = min(NT1, kmax - i0);
+        const double *bp = tab + SPB_TAB_BP + (size_t)l1 * 1000 + i0;
+        for (int ii = 0; ii < in; ++ii) eacc = fma(bp[ii], Wst[ii * 16 + l2], eacc);
+      }
+    }
+    p.E2[(size_t)b * 256 + tid] = bad ? NAN : eacc;
+    __syncthreads();
+  }
   for (int row = warp; row < 16; row += NT1 / 32) {
     const double *bp = tab + SPB_TAB_BP + (size_t)row * 1000;
     double acc = 0.0;
@@ -627,7 +713,8 @@ __global__ void __launch_bounds__(NT1) moments_k1c(K1Params p) {
   __syncthreads();
   int l1, m1;
   lm_of(tid, l1, m1);
-  const double qsl = p.qs[(size_t)b * 16 + l1];
+  // dr prior: the spot-size factor enters as Etilde[l1][l2] in the SYRK epilogue instead
+  const double qsl = p.dr_deg ? 1.0 : p.qs[(size_t)b * 16 + l1];
   const bool bad = (p.info[b] & SPB_INFO_BOUNDS) != 0;
   const double *H = p.tab + SPB_TAB_LAT_H + (size_t)tid * 32;
   double out[32];
@@ -763,7 +850,7 @@ int k2_upload_items(int device, int *nitems_out) {
 constexpr int MOM_CHUNK = 1024;  // samples per pass (bounds the sqrtC_lon workspace to 2 GB)
 
 struct MomWs {
-  double *mom1, *S_lat, *scale, *X, *Sred, *qs;
+  double *mom1, *S_lat, *scale, *X, *Sred, *qs, *E2;
   int *rkeep;
 };
 
@@ -782,7 +869,9 @@ size_t mom_ws_layout(int B, unsigned char *base, MomWs *ws) {
   size_t o_X = take((size_t)Bc * 256 * 992 * 8);
   size_t o_Sred = take((size_t)B * 1024 * 8);
   size_t o_qs = take((size_t)B * 16 * 8);
+  size_t o_E2 = take((size_t)B * 256 * 8);
   if (ws) {
+    ws->E2 = reinterpret_cast<double *>(base + o_E2);
     ws->Sred = reinterpret_cast<double *>(base + o_Sred);
     ws->qs = reinterpret_cast<double *>(base + o_qs);
     ws->mom1 = reinterpret_cast<double *>(base + o_mom1);
@@ -866,6 +955,14 @@ extern "C" int spb_ylm_moments(spb_context *ctx, int B, const double *r_deg, con
                                const double *b, const double *c, const double *n, double *mean_ylm,
                                double *cov_ylm, int32_t *info, void *workspace,
                                size_t workspace_bytes, void *stream_) {
+  return spb_ylm_moments_dr(ctx, B, r_deg, nullptr, a, b, c, n, mean_ylm, cov_ylm, info, workspace,
+                            workspace_bytes, stream_);
+}
+
+extern "C" int spb_ylm_moments_dr(spb_context *ctx, int B, const double *r_deg, const double *dr_deg,
+                                  const double *a, const double *b, const double *c, const double *n,
+                                  double *mean_ylm, double *cov_ylm, int32_t *info, void *workspace,
+                                  size_t workspace_bytes, void *stream_) {
   SPB_REQUIRE(ctx != nullptr && B > 0, "ylm_moments: bad arguments");
   SPB_REQUIRE(ctx->tables_count == SPB_TAB_TOTAL, "ylm_moments: context has no constant tables");
   SPB_REQUIRE(workspace_bytes >= mom_ws_layout(B, nullptr, nullptr) && workspace != nullptr,
@@ -890,6 +987,8 @@ extern "C" int spb_ylm_moments(spb_context *ctx, int B, const double *r_deg, con
   SPB_REQUIRE(k1_upload_perm(ctx->device) == 0, "ylm_moments: constant upload failed");
   K1Params p1;
   p1.r_deg = r_deg;
+  p1.dr_deg = dr_deg;
+  p1.E2 = ws.E2;
   p1.a = a;
   p1.b = b;
   p1.c = c;
@@ -947,6 +1046,7 @@ extern "C" int spb_ylm_moments(spb_context *ctx, int B, const double *r_deg, con
     d.strideVec = 256;
     d.diag = ctx->d_tables + SPB_TAB_LAMBDA;
     d.rkeep = ws.rkeep + b0;
+    d.ldeg = dr_deg ? ws.E2 + (size_t)b0 * 256 : nullptr;
     d.alpha = 1.0;
     int st = gnt::launch<gnt::EPI_SYRK_COV>(ctx, d, stream);
     if (st) return st;

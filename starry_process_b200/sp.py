@@ -16,9 +16,8 @@ SURVEY.md section 8(f) ranks 2 and 3 are covered as well: ``sample``, ``predict`
 from the same Cholesky / GEMM / assembly kernels, and time-variable surfaces (``tau``,
 ``temporal_kernel``: temporal.py:8-16, sp.py:697-698, 893-894, 510-516).
 
-Out of scope in this drop-in (callers, listed under "next"): the uniform
-spot-size prior (``dr``), gradients, pixel-space moments and visualisation.  They raise
-``NotImplementedError``.
+The uniform spot-size prior (``dr``, size.py:55-89, 116-125) is
+supported.  Out of scope in this drop-in: pixel-space moments and visualisation.
 """
 import ctypes
 import math
@@ -169,8 +168,6 @@ class StarryProcess(object):
             a = b = None
         else:
             raise ValueError("Must provide either `a` and `b` *or* `mu` and `sigma`.")
-        if dr is not None:
-            raise NotImplementedError("uniform spot-size prior (dr) is outside the lnlike hot path")
         # sp.py:225-232; the reference accepts any callable f(t1, t2, tau): the CUDA assembly
         # implements the two kernels the reference ships (temporal.py)
         self._time_variable = tau is not None
@@ -215,6 +212,8 @@ class StarryProcess(object):
         self._lib = self._ctx.lib
 
         params = dict(r=r, c=c, n=n)
+        if dr is not None:     # uniform prior on the spot radius over [r - dr, r + dr], size.py:116-125
+            params["dr"] = dr
         if self._time_variable:
             params["tau"] = tau
         if a is None:
@@ -228,6 +227,9 @@ class StarryProcess(object):
                     if not (isinstance(v, torch.Tensor) and v.is_cuda)}
         if "r" in hostvals:
             _check_bounds("r", np.asarray(hostvals["r"], dtype=np.float64) * np.pi / 180, 0,
+                          0.5 * np.pi)
+        if "dr" in hostvals:
+            _check_bounds("dr", np.asarray(hostvals["dr"], dtype=np.float64) * np.pi / 180, 0,
                           0.5 * np.pi)
         if "a" in hostvals:
             _check_bounds("a", hostvals["a"], 0, 1)
@@ -248,6 +250,7 @@ class StarryProcess(object):
         self._B = B
         self._r, self._c, self._n = tens["r"], tens["c"], tens["n"]
         self._tau = tens.get("tau", None)
+        self._dr = tens.get("dr", None)
         if a is None:
             self._a = torch.empty(B, dtype=torch.float64, device=self.device)
             self._b = torch.empty(B, dtype=torch.float64, device=self.device)
@@ -332,9 +335,10 @@ class StarryProcess(object):
             nbytes = self._lib.spb_ylm_moments_workspace_bytes(self._ctx.handle, B)
             ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
             ev = self._mark("moments")
-            _lib.check(self._lib.spb_ylm_moments(
-                self._ctx.handle, B, _ptr(self._r), _ptr(self._a), _ptr(self._b), _ptr(self._c),
-                _ptr(self._n), _ptr(mean), _ptr(cov), _ptr(self._info), _ptr(ws), nbytes, _stream()))
+            _lib.check(self._lib.spb_ylm_moments_dr(
+                self._ctx.handle, B, _ptr(self._r), _ptr(self._dr), _ptr(self._a), _ptr(self._b),
+                _ptr(self._c), _ptr(self._n), _ptr(mean), _ptr(cov), _ptr(self._info), _ptr(ws),
+                nbytes, _stream()))
             self._mark_end(ev)
             del ws
         self._mean_ylm, self._cov_ylm = mean, cov
@@ -1120,7 +1124,7 @@ class StarryProcessSum(StarryProcess):
         self._cho_cov_ylm = None
         self._z = None
         self._rTA1_cache = {}
-        self._a = self._b = self._r = self._c = self._n = None
+        self._a = self._b = self._r = self._c = self._n = self._dr = None
 
     def _compute_moments(self):
         return
