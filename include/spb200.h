@@ -91,6 +91,23 @@ int spb_ylm_moments_dr(spb_context *ctx, int B, const double *r_deg, const doubl
                        double *mean_ylm, double *cov_ylm, int32_t *info, void *workspace,
                        size_t workspace_bytes, void *stream);
 
+/* (f-4) Ylm moments AND their derivatives with respect to (r [deg], a, b, c, n), for the gradient of
+ * the log-likelihood (the reference: Theano reverse mode through ops/include/latitude.h:22-173
+ * derivative lanes, eigh.h:19-65, integrals.py:116-151).  Delta prior on the spot radius.
+ * Returns 11 VARIANTS of the moments per sample, variant-major (slot v * B + b):
+ *   v = 0 base;  1,2: r + eps, r - eps;  3,4: a +-;  5,6: b +-;  7,8: c +-;  9,10: n +-
+ * where variants 1..6 move (S = Z^T Q Z, q_l, mom1) along their ANALYTIC tangents (Beta-moment
+ * derivative lanes, profile derivative) and then run the unchanged eigen-solve / longitude / SYRK
+ * pipeline, which is linear in S and quadratic in (q_l, mom1): the central difference
+ * (out[v+] - out[v-]) / (2 eps) of any linear / quadratic functional of (mean_ylm, cov_ylm) is its
+ * exact directional derivative.  eps: (5, B) absolute steps (rel_step times base / tangent scale).
+ *   mean_ylm: (11 B, 256) out;  cov_ylm: (11 B, 256, 256) out;  info: (B) out                      */
+size_t spb_ylm_moments_grad_workspace_bytes(const spb_context *ctx, int B);
+int spb_ylm_moments_grad(spb_context *ctx, int B, const double *r_deg, const double *a,
+                         const double *b, const double *c, const double *n, double rel_step,
+                         double *mean_ylm, double *cov_ylm, double *eps, int32_t *info,
+                         void *workspace, size_t workspace_bytes, void *stream);
+
 /* Cholesky factor of cov_ylm and prior draws -- sp.py:265-271, 489-509.
  *   L_ylm : (B,256,256) out, lower triangle (upper zeroed);  unit_normals: (B, nsamples, 256)
  *   y     : (B, nsamples, 256) out = mean + L u                                              */

@@ -47,6 +47,8 @@ PROTOTYPES = {
     "spb_ylm_moments_workspace_bytes": (_SZ, [_P, _I]),
     "spb_ylm_moments": (_I, [_P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _SZ, _P]),
     "spb_ylm_moments_dr": (_I, [_P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _SZ, _P]),
+    "spb_ylm_moments_grad_workspace_bytes": (_SZ, [_P, _I]),
+    "spb_ylm_moments_grad": (_I, [_P, _I, _P, _P, _P, _P, _P, _D, _P, _P, _P, _P, _P, _SZ, _P]),
     "spb_cho_cov_ylm": (_I, [_P, _I, _P, _P, _P, _P]),
     "spb_sample_ylm": (_I, [_P, _I, _I, _P, _P, _P, _P, _P]),
     "spb_flux_operator": (_I, [_P, _I, _P, _P, _P]),

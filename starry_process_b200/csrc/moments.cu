@@ -140,6 +140,176 @@ __device__ unsigned long long g_k1b_prof[8];
 #define K1PROF(k)
 #endif
 
+// ---- sm.Bk (61 raw moments, or one of their derivative lanes) -> sm.tt (term table) -> sm.Y = Q Z
+// -> sm.A = S = Z^T Q Z symmetrised (31 x 31 padded to 32).  Shared by the value kernel (K1a) and the
+// tangent kernel (K1a_tan: the same linear chain applied to dB/dalpha, dB/dbeta).
+__device__ __forceinline__ void k1a_S_from_moments(K1Smem &sm, const double *tab, int tid, int warp,
+                                                    int lane) {
+  // ---- term(2a, 2b) = sum_k1 sum_k2 C(a,k1) (-1)^k2 C(b,k2) B(k1+k2), latitude.h:112-143
+  // The signed binomial products come from the LAT_FAC table (built on the host with the
+  // reference's ratio recurrences, bit-identical to evaluating them here); the accumulation order
+  // is the reference's.  The heavy (a, b) pairs are dealt out first so the tail is short.
+  {
+    // Work list: the 496 non-zero (a, b) pairs are dealt to the 256 threads longest-first (LPT,
+    // k1_tt_sched): the longest chain is then the single heaviest pair (256 terms) instead of 374
+    // terms.  The factors live in L2 (371 KB table) and are streamed ahead of the (serial,
+    // reference-ordered) accumulation.
+    const double *fac = tab + SPB_TAB_LAT_FAC;
+    const double *facoff = tab + SPB_TAB_LAT_FACOFF;
+    for (int idx = tid; idx < 31 * 31; idx += NT1) {
+      const int a2 = idx / 31, b2 = idx % 31;
+      if (a2 + b2 > 30) sm.tt[a2][b2] = 0.0;
+    }
+#pragma unroll 1
+    for (int slot = 0; slot < 3; ++slot) {
+      const int idx = k1_tt_sched[slot * 256 + tid];
+      if (idx < 0) continue;
+      const int a2 = idx / 31, b2 = idx % 31;
+      double acc = 0.0;
+      const double *f = fac + (int)facoff[idx];
+      // the rows of the double sum are contiguous in the table: one flat, software-pipelined stream
+      // (16 factors in flight while the previous 16 are accumulated in the reference's order)
+      const int T = (a2 + 1) * (b2 + 1), w = b2 + 1;
+      double nxt[16];
+#pragma unroll
+      for (int u = 0; u < 16; ++u) nxt[u] = (u < T) ? __ldg(f + u) : 0.0;
+      int k1 = 0, k2 = 0;
+      for (int n0 = 0; n0 < T; n0 += 16) {
+        double cur[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) cur[u] = nxt[u];
+        if (n0 + 16 < T) {
+#pragma unroll
+          for (int u = 0; u < 16; ++u) nxt[u] = (n0 + 16 + u < T) ? __ldg(f + n0 + 16 + u) : 0.0;
+        }
+        // branch-free: slots past the end carry a zero factor (adding 0 is exact), and k1 + k2
+        // stays inside Bk[64]
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+          acc += cur[u] * sm.Bk[k1 + k2];
+          ++k2;
+          const bool wrap = (k2 == w);
+          k2 = wrap ? 0 : k2;
+          k1 += wrap ? 1 : 0;
+        }
+      }
+      sm.tt[a2][b2] = acc;
+    }
+  }
+  __syncthreads();
+
+  // ---- Y = Q Z with Q(n1,n2) = term(j1+j2, i1+i2) 2^-(l1+l2)   (latitude.h:146-172)
+  // A (256 x 256) x (256 x 31) product on the FP64 tensor pipe.  Q(n1, n2) vanishes unless l - m
+  // has the same parity for both indices, so rows AND the contraction index run in parity-sorted
+  // order (k1_perm: 136 even, then 120 odd; 8-row tiles and 4-wide k-steps never straddle the
+  // boundary) and every (m-tile, k-step) pair of opposite parity is skipped as a whole: half the
+  // DMMAs.  The Q entries are generated in the A-fragment layout from the term table (the 2^-(l1+l2)
+  // scaling is an exact exponent adjustment); Z is staged 32 permuted rows at a time, 36-double
+  // pitch (conflict-free B fragments).
+  int l1, m1;
+  lm_of(tid, l1, m1);
+  {
+    // (j, i, l) of the permuted index tid, for the k side
+    {
+      int lp, mp;
+      lm_of(k1_perm[tid], lp, mp);
+      sm.kj[tid] = (unsigned char)(mp + lp);
+      sm.ki[tid] = (unsigned char)(lp - mp);
+      sm.kl[tid] = (unsigned char)lp;
+    }
+    const int g = lane >> 2, tg = lane & 3;
+    int rj[4], ri[4], rl[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      int lp, mp;
+      lm_of(k1_perm[32 * warp + 8 * q + g], lp, mp);
+      rj[q] = mp + lp;
+      ri[q] = lp - mp;
+      rl[q] = lp;
+    }
+    double acc[4][4][2];
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) acc[q][nt][0] = acc[q][nt][1] = 0.0;
+    const double *Z = tab + SPB_TAB_LAT_Z;
+    for (int c0 = 0; c0 < 256; c0 += 32) {
+      __syncthreads();
+      for (int k = tid; k < 32 * 16; k += NT1) {
+        const int r = k >> 4, c = k & 15;
+        const double2 z2 = __ldg(reinterpret_cast<const double2 *>(Z + k1_perm[c0 + r] * 32) + c);
+        *reinterpret_cast<double2 *>(&sm.Zs[r][2 * c]) = z2;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int ks = 0; ks < 8; ++ks) {
+        const int kp = c0 + 4 * ks;              // permuted contraction index of this k-step
+        const bool k_even = kp < 136;
+        const int kj = sm.kj[kp + tg], ki = sm.ki[kp + tg], kl = sm.kl[kp + tg];
+        double bf[4];
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) bf[nt] = sm.Zs[4 * ks + tg][8 * nt + g];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const bool m_even = 32 * warp + 8 * q < 136;   // warp-uniform
+          if (m_even == k_even) {
+            const double t = sm.tt[(rj[q] + kj) >> 1][(ri[q] + ki) >> 1];
+            // t * 2^-(l1 + l2): exact (ldexp in the scalar form)
+            const double av = t * __hiloint2double((1023 - (rl[q] + kl)) << 20, 0);
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) dmma_m8n8k4(acc[q][nt][0], acc[q][nt][1], av, bf[nt]);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int n1 = k1_perm[32 * warp + 8 * q + g];
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        const int col = 8 * nt + 2 * tg;
+        sm.Y[n1][col] = acc[q][nt][0];
+        if (col + 1 < 31) sm.Y[n1][col + 1] = acc[q][nt][1];
+      }
+    }
+  }
+  __syncthreads();
+  // ---- S = Z^T Y (31 x 31), symmetrised, padded to 32: a (32 x 256) x (256 x 32) product on DMMA,
+  // warp w owns the 8 x 16 block  rows 8 (w / 2),  columns 16 (w % 2)
+  {
+    const double *Z = tab + SPB_TAB_LAT_Z;
+    const int g = lane >> 2, tg = lane & 3;
+    const int a0 = 8 * (warp >> 1), c0 = 16 * (warp & 1);
+    double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+#pragma unroll 1
+    for (int k0 = 0; k0 < 256; k0 += 32) {
+      double av[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) av[u] = __ldg(Z + (k0 + 4 * u + tg) * 32 + a0 + g);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int k = k0 + 4 * u + tg;
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt)
+          dmma_m8n8k4(acc[nt][0], acc[nt][1], av[u], sm.Y[k][c0 + 8 * nt + g]);
+      }
+    }
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int a = a0 + g, c = c0 + 8 * nt + 2 * tg + e;
+        sm.V[a][c] = (a < 31 && c < 31) ? acc[nt][e] : 0.0;   // staging
+      }
+  }
+  __syncthreads();
+  for (int idx = tid; idx < 32 * 32; idx += NT1) {
+    const int a = idx >> 5, c2 = idx & 31;
+    sm.A[a][c2] = 0.5 * (sm.V[a][c2] + sm.V[c2][a]);
+  }
+  __syncthreads();
+}
+
 __global__ void __launch_bounds__(NT1, 2) moments_k1a(K1Params p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   K1Smem &sm = *reinterpret_cast<K1Smem *>(smem_raw);
@@ -277,171 +447,9 @@ __global__ void __launch_bounds__(NT1, 2) moments_k1a(K1Params p) {
   __syncthreads();
 
   K1PROF(1);
-  // ---- term(2a, 2b) = sum_k1 sum_k2 C(a,k1) (-1)^k2 C(b,k2) B(k1+k2), latitude.h:112-143
-  // The signed binomial products come from the LAT_FAC table (built on the host with the
-  // reference's ratio recurrences, bit-identical to evaluating them here); the accumulation order
-  // is the reference's.  The heavy (a, b) pairs are dealt out first so the tail is short.
-  {
-    // Work list: the 496 non-zero (a, b) pairs are dealt to the 256 threads longest-first (LPT,
-    // k1_tt_sched): the longest chain is then the single heaviest pair (256 terms) instead of 374
-    // terms.  The factors live in L2 (371 KB table) and are streamed ahead of the (serial,
-    // reference-ordered) accumulation.
-    const double *fac = p.tab + SPB_TAB_LAT_FAC;
-    const double *facoff = p.tab + SPB_TAB_LAT_FACOFF;
-    for (int idx = tid; idx < 31 * 31; idx += NT1) {
-      const int a2 = idx / 31, b2 = idx % 31;
-      if (a2 + b2 > 30) sm.tt[a2][b2] = 0.0;
-    }
-#pragma unroll 1
-    for (int slot = 0; slot < 3; ++slot) {
-      const int idx = k1_tt_sched[slot * 256 + tid];
-      if (idx < 0) continue;
-      const int a2 = idx / 31, b2 = idx % 31;
-      double acc = 0.0;
-      const double *f = fac + (int)facoff[idx];
-      // the rows of the double sum are contiguous in the table: one flat, software-pipelined stream
-      // (16 factors in flight while the previous 16 are accumulated in the reference's order)
-      const int T = (a2 + 1) * (b2 + 1), w = b2 + 1;
-      double nxt[16];
-#pragma unroll
-      for (int u = 0; u < 16; ++u) nxt[u] = (u < T) ? __ldg(f + u) : 0.0;
-      int k1 = 0, k2 = 0;
-      for (int n0 = 0; n0 < T; n0 += 16) {
-        double cur[16];
-#pragma unroll
-        for (int u = 0; u < 16; ++u) cur[u] = nxt[u];
-        if (n0 + 16 < T) {
-#pragma unroll
-          for (int u = 0; u < 16; ++u) nxt[u] = (n0 + 16 + u < T) ? __ldg(f + n0 + 16 + u) : 0.0;
-        }
-        // branch-free: slots past the end carry a zero factor (adding 0 is exact), and k1 + k2
-        // stays inside Bk[64]
-#pragma unroll
-        for (int u = 0; u < 16; ++u) {
-          acc += cur[u] * sm.Bk[k1 + k2];
-          ++k2;
-          const bool wrap = (k2 == w);
-          k2 = wrap ? 0 : k2;
-          k1 += wrap ? 1 : 0;
-        }
-      }
-      sm.tt[a2][b2] = acc;
-    }
-  }
-  __syncthreads();
-
-  K1PROF(2);
-  // ---- Y = Q Z with Q(n1,n2) = term(j1+j2, i1+i2) 2^-(l1+l2)   (latitude.h:146-172)
-  // A (256 x 256) x (256 x 31) product on the FP64 tensor pipe.  Q(n1, n2) vanishes unless l - m
-  // has the same parity for both indices, so rows AND the contraction index run in parity-sorted
-  // order (k1_perm: 136 even, then 120 odd; 8-row tiles and 4-wide k-steps never straddle the
-  // boundary) and every (m-tile, k-step) pair of opposite parity is skipped as a whole: half the
-  // DMMAs.  The Q entries are generated in the A-fragment layout from the term table (the 2^-(l1+l2)
-  // scaling is an exact exponent adjustment); Z is staged 32 permuted rows at a time, 36-double
-  // pitch (conflict-free B fragments).
+  k1a_S_from_moments(sm, tab, tid, warp, lane);
   int l1, m1;
   lm_of(tid, l1, m1);
-  {
-    // (j, i, l) of the permuted index tid, for the k side
-    {
-      int lp, mp;
-      lm_of(k1_perm[tid], lp, mp);
-      sm.kj[tid] = (unsigned char)(mp + lp);
-      sm.ki[tid] = (unsigned char)(lp - mp);
-      sm.kl[tid] = (unsigned char)lp;
-    }
-    const int g = lane >> 2, tg = lane & 3;
-    int rj[4], ri[4], rl[4];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      int lp, mp;
-      lm_of(k1_perm[32 * warp + 8 * q + g], lp, mp);
-      rj[q] = mp + lp;
-      ri[q] = lp - mp;
-      rl[q] = lp;
-    }
-    double acc[4][4][2];
-#pragma unroll
-    for (int q = 0; q < 4; ++q)
-#pragma unroll
-      for (int nt = 0; nt < 4; ++nt) acc[q][nt][0] = acc[q][nt][1] = 0.0;
-    const double *Z = tab + SPB_TAB_LAT_Z;
-    for (int c0 = 0; c0 < 256; c0 += 32) {
-      __syncthreads();
-      for (int k = tid; k < 32 * 16; k += NT1) {
-        const int r = k >> 4, c = k & 15;
-        const double2 z2 = __ldg(reinterpret_cast<const double2 *>(Z + k1_perm[c0 + r] * 32) + c);
-        *reinterpret_cast<double2 *>(&sm.Zs[r][2 * c]) = z2;
-      }
-      __syncthreads();
-#pragma unroll
-      for (int ks = 0; ks < 8; ++ks) {
-        const int kp = c0 + 4 * ks;              // permuted contraction index of this k-step
-        const bool k_even = kp < 136;
-        const int kj = sm.kj[kp + tg], ki = sm.ki[kp + tg], kl = sm.kl[kp + tg];
-        double bf[4];
-#pragma unroll
-        for (int nt = 0; nt < 4; ++nt) bf[nt] = sm.Zs[4 * ks + tg][8 * nt + g];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const bool m_even = 32 * warp + 8 * q < 136;   // warp-uniform
-          if (m_even == k_even) {
-            const double t = sm.tt[(rj[q] + kj) >> 1][(ri[q] + ki) >> 1];
-            // t * 2^-(l1 + l2): exact (ldexp in the scalar form)
-            const double av = t * __hiloint2double((1023 - (rl[q] + kl)) << 20, 0);
-#pragma unroll
-            for (int nt = 0; nt < 4; ++nt) dmma_m8n8k4(acc[q][nt][0], acc[q][nt][1], av, bf[nt]);
-          }
-        }
-      }
-    }
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int n1 = k1_perm[32 * warp + 8 * q + g];
-#pragma unroll
-      for (int nt = 0; nt < 4; ++nt) {
-        const int col = 8 * nt + 2 * tg;
-        sm.Y[n1][col] = acc[q][nt][0];
-        if (col + 1 < 31) sm.Y[n1][col + 1] = acc[q][nt][1];
-      }
-    }
-  }
-  __syncthreads();
-  K1PROF(3);
-  // ---- S = Z^T Y (31 x 31), symmetrised, padded to 32: a (32 x 256) x (256 x 32) product on DMMA,
-  // warp w owns the 8 x 16 block  rows 8 (w / 2),  columns 16 (w % 2)
-  {
-    const double *Z = tab + SPB_TAB_LAT_Z;
-    const int g = lane >> 2, tg = lane & 3;
-    const int a0 = 8 * (warp >> 1), c0 = 16 * (warp & 1);
-    double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
-#pragma unroll 1
-    for (int k0 = 0; k0 < 256; k0 += 32) {
-      double av[8];
-#pragma unroll
-      for (int u = 0; u < 8; ++u) av[u] = __ldg(Z + (k0 + 4 * u + tg) * 32 + a0 + g);
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const int k = k0 + 4 * u + tg;
-#pragma unroll
-        for (int nt = 0; nt < 2; ++nt)
-          dmma_m8n8k4(acc[nt][0], acc[nt][1], av[u], sm.Y[k][c0 + 8 * nt + g]);
-      }
-    }
-#pragma unroll
-    for (int nt = 0; nt < 2; ++nt)
-#pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const int a = a0 + g, c = c0 + 8 * nt + 2 * tg + e;
-        sm.V[a][c] = (a < 31 && c < 31) ? acc[nt][e] : 0.0;   // staging
-      }
-  }
-  __syncthreads();
-  for (int idx = tid; idx < 32 * 32; idx += NT1) {
-    const int a = idx >> 5, c2 = idx & 31;
-    sm.A[a][c2] = 0.5 * (sm.V[a][c2] + sm.V[c2][a]);
-  }
-  __syncthreads();
   K1PROF(4);
   // S goes to the eigen-solve kernel
   for (int idx = tid; idx < 32 * 32; idx += NT1) p.Sred[(size_t)b * 1024 + idx] = sm.A[idx >> 5][idx & 31];
@@ -482,6 +490,236 @@ __global__ void __launch_bounds__(NT1, 2) moments_k1a(K1Params p) {
 }
 
 
+
+// ------------------------------------------------------------------------------------------
+// Tangent lanes for the gradient of the log-likelihood.  The only
+// non-linear, hyperparameter-dependent inputs of the Ylm moments are the Beta moments B(k) of the
+// latitude distribution and the spot profile; everything downstream of (S = Z^T Q Z, q_l, mom1) is
+// linear / quadratic.  K1a_tan evaluates, per sample,
+//   dS/da, dS/db   : the K1a chain applied to the derivative lanes dB/dalpha, dB/dbeta of
+//                    ops/include/latitude.h:48-60 (chain factors d alpha / d a = 10 alpha,
+//                    d beta / d b = (10 - ln 1/2) beta; zero below the abmin clamp)
+//   dq_l / dr      : Bp . d b(theta; r) / d r   (size.py:45-53), per DEGREE of r
+//   d mom1 / d(r, a, b)
+// and moments_expand_kernel turns them into +-eps perturbed copies of (S, q, mom1) that run through
+// the unchanged K1b / K1c / K2 / SYRK pipeline.  Because that pipeline is linear in S and quadratic
+// in (q, mom1), the central difference of its outputs along a tangent is the exact directional
+// derivative (no truncation error); the reference instead back-propagates through eigh
+// (ops/include/eigh.h:19-65, integrals.py:133-151).
+// ------------------------------------------------------------------------------------------
+struct K1TanParams {
+  const double *r_deg, *a, *b;
+  int B;
+  const double *tab;
+  double *dS;     // (B,2,32,32)
+  double *dqs;    // (B,16)
+  double *dmom1;  // (B,3,256): r, a, b
+};
+
+__global__ void __launch_bounds__(NT1, 2) moments_k1a_tan(K1TanParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  K1Smem &sm = *reinterpret_cast<K1Smem *>(smem_raw);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int b = blockIdx.x;
+  const double *tab = p.tab;
+  const double ang = 3.14159265358979323846 / 180.0;
+  const double r = p.r_deg[b] * ang;
+  double aa = p.a[b], bb = p.b[b];
+  const bool a_free = aa > 1e-12, b_free = bb > 1e-12;   // latitude.py:180-182 (abmin clamp)
+  if (!a_free) aa = 1e-12;
+  if (!b_free) bb = 1e-12;
+  __shared__ double dqs_s[16];
+  __shared__ double lanes[3][64];   // B, dB/dalpha, dB/dbeta
+  __shared__ double chain[2];
+
+  // ---- spot profile and its r-derivative: b = sigma(z) - 1, z = 300 (theta - r),
+  // d b / d r = -300 sigma (1 - sigma)
+  for (int pass = 0; pass < 2; ++pass) {
+    for (int s = tid; s < 1000; s += NT1) {
+      const double z = 300.0 * (tab[SPB_TAB_THETA + s] - r);
+      const double sg = 1.0 / (1.0 + exp(-z));
+      sm.bprof[s] = pass == 0 ? sg - 1.0 : -300.0 * sg * (1.0 - sg) * ang;
+    }
+    __syncthreads();
+    for (int row = warp; row < 16; row += NT1 / 32) {
+      const double *bp = tab + SPB_TAB_BP + (size_t)row * 1000;
+      double acc = 0.0;
+      for (int s = lane; s < 1000; s += 32) acc = fma(bp[s], sm.bprof[s], acc);
+      acc = warp_sum(acc);
+      if (lane == 0) (pass == 0 ? sm.qs[row] : dqs_s[row]) = acc;
+    }
+    __syncthreads();
+  }
+  if (tid < 16) p.dqs[(size_t)b * 16 + tid] = dqs_s[tid];
+
+  // ---- Beta moments and their derivative lanes, latitude.h:48-60
+  if (tid == 0) {
+    const double alpha0 = exp(aa * 10.0);
+    const double beta0 = exp(log(0.5) + bb * (10.0 - log(0.5)));
+    const double alpha = alpha0 > 0.0 ? alpha0 : 0.0;
+    const double beta = beta0 > 0.0 ? beta0 : 0.0;
+    chain[0] = a_free ? 10.0 * alpha : 0.0;
+    chain[1] = b_free ? (10.0 - log(0.5)) * beta : 0.0;
+    lanes[0][0] = 1.0;
+    lanes[1][0] = 0.0;
+    lanes[2][0] = 0.0;
+    for (int k = 1; k < 61; ++k) {
+      const double c1 = 1.0 / (alpha + beta + k - 1.0);
+      const double c2 = (alpha + k - 1.0) * c1;
+      const double c3 = beta * c1 * c1;
+      const double c4 = (1 - k - alpha) * c1 * c1;
+      lanes[0][k] = c2 * lanes[0][k - 1];
+      lanes[1][k] = c3 * lanes[0][k - 1] + c2 * lanes[1][k - 1];
+      lanes[2][k] = c4 * lanes[0][k - 1] + c2 * lanes[2][k - 1];
+    }
+  }
+  __syncthreads();
+
+  int l1, m1;
+  lm_of(tid, l1, m1);
+  const int w = 2 * l1 + 1;
+  const double *R0 = tab + SPB_TAB_LAT_R0 + (size_t)(l1 * (2 * l1 - 1) * (2 * l1 + 1)) / 3 +
+                     (size_t)(m1 + l1) * w;
+  const double *T1 = tab + SPB_TAB_LON_T1 + (size_t)(l1 * (2 * l1 - 1) * (2 * l1 + 1)) / 3 +
+                     (size_t)(m1 + l1) * w;
+  double glat[3];   // (R0 . q_lat) of this Ylm index for the three lanes
+  for (int v = 0; v < 3; ++v) {
+    if (tid < 64) sm.Bk[tid] = lanes[v][tid];
+    __syncthreads();
+    k1a_S_from_moments(sm, tab, tid, warp, lane);   // -> sm.tt, sm.A (ends with a barrier)
+    if (v > 0) {
+      const double f = chain[v - 1];
+      for (int idx = tid; idx < 32 * 32; idx += NT1)
+        p.dS[((size_t)b * 2 + (v - 1)) * 1024 + idx] = f * sm.A[idx >> 5][idx & 31];
+    }
+    double acc = 0.0;
+    for (int k = 0; k < w; ++k) {
+      const int I = 2 * l1 - k;
+      double ql = 0.0;
+      if (!(k & 1)) ql = ldexp(sm.tt[k >> 1][I >> 1], -l1);
+      acc = fma(R0[k], ql, acc);
+    }
+    glat[v] = acc;
+    __syncthreads();
+  }
+  // ---- d mom1: longitude first-moment map applied to the three latitude tangents
+  for (int d = 0; d < 3; ++d) {
+    double val;
+    if (d == 0) val = dqs_s[l1] * glat[0];
+    else val = chain[d - 1] * sm.qs[l1] * glat[d];
+    sm.m1lat[tid] = val;
+    __syncthreads();
+    double acc = 0.0;
+    for (int m = 0; m < w; ++m) acc = fma(T1[m], sm.m1lat[l1 * l1 + m], acc);
+    p.dmom1[((size_t)b * 3 + d) * 256 + tid] = acc;
+    __syncthreads();
+  }
+}
+
+// Variants of the moment inputs, variant-major: slot v * B + b, v = 0 base (already written by K1a),
+// 1,2: r +-; 3,4: a +-; 5,6: b +-.  eps[d * B + b] is the absolute step of direction d (r in
+// degrees): rel_step times the ratio of the largest base entry to the largest tangent entry.
+struct ExpandParams {
+  int B;
+  double rel_step;
+  const double *c, *n;
+  const double *dS, *dqs, *dmom1;
+  double *Sred, *qs, *mom1, *mean_ylm, *scale;
+  int32_t *info;
+  double *eps;   // (5, B): r, a, b, c, n
+};
+
+__global__ void __launch_bounds__(256) moments_expand_kernel(ExpandParams p) {
+  __shared__ double red[8];
+  __shared__ double mx[5];
+  const int b = blockIdx.x, tid = threadIdx.x, B = p.B;
+  auto block_max = [&](double v) {
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    __syncthreads();
+    if ((tid & 31) == 0) red[tid >> 5] = v;
+    __syncthreads();
+    double t = 0.0;
+    for (int k = 0; k < 8; ++k) t = fmax(t, red[k]);
+    return t;
+  };
+  const double *S0 = p.Sred + (size_t)b * 1024;
+  const double *Sa = p.dS + ((size_t)b * 2 + 0) * 1024, *Sb = p.dS + ((size_t)b * 2 + 1) * 1024;
+  double m0 = 0.0, ma = 0.0, mb = 0.0;
+  for (int i = tid; i < 1024; i += 256) {
+    m0 = fmax(m0, fabs(S0[i]));
+    ma = fmax(ma, fabs(Sa[i]));
+    mb = fmax(mb, fabs(Sb[i]));
+  }
+  m0 = block_max(m0);
+  ma = block_max(ma);
+  mb = block_max(mb);
+  double q0 = tid < 16 ? fabs(p.qs[(size_t)b * 16 + tid]) : 0.0;
+  double q1 = tid < 16 ? fabs(p.dqs[(size_t)b * 16 + tid]) : 0.0;
+  q0 = block_max(q0);
+  q1 = block_max(q1);
+  if (tid == 0) {
+    mx[0] = (q1 > 0.0) ? p.rel_step * q0 / q1 : 1.0;
+    mx[1] = (ma > 0.0) ? p.rel_step * m0 / ma : 1.0;
+    mx[2] = (mb > 0.0) ? p.rel_step * m0 / mb : 1.0;
+    mx[3] = p.rel_step * fabs(p.c[b]);
+    mx[4] = p.rel_step * fabs(p.n[b]);
+    if (!(mx[3] > 0.0)) mx[3] = p.rel_step;
+    if (!(mx[4] > 0.0)) mx[4] = p.rel_step;
+    for (int d = 0; d < 5; ++d) p.eps[(size_t)d * B + b] = mx[d];
+  }
+  __syncthreads();
+  const double pi = 3.14159265358979323846;
+  const double fac = pi * p.c[b] * p.n[b];
+  for (int v = 1; v < 7; ++v) {
+    const int d = (v - 1) >> 1;
+    const double e = ((v - 1) & 1) ? -mx[d] : mx[d];
+    const size_t slot = (size_t)v * B + b;
+    for (int i = tid; i < 1024; i += 256) {
+      double val = S0[i];
+      if (d == 1) val = fma(e, Sa[i], val);
+      if (d == 2) val = fma(e, Sb[i], val);
+      p.Sred[slot * 1024 + i] = val;
+    }
+    if (tid < 16) {
+      double val = p.qs[(size_t)b * 16 + tid];
+      if (d == 0) val = fma(e, p.dqs[(size_t)b * 16 + tid], val);
+      p.qs[slot * 16 + tid] = val;
+    }
+    {
+      const double m1v = fma(e, p.dmom1[((size_t)b * 3 + d) * 256 + tid], p.mom1[(size_t)b * 256 + tid]);
+      p.mom1[slot * 256 + tid] = m1v;
+      p.mean_ylm[slot * 256 + tid] = fac * m1v;
+    }
+    if (tid == 0) {
+      p.scale[slot] = p.scale[b];
+      p.info[slot] = p.info[b];
+    }
+  }
+}
+
+// Variants 7..10 (c +-, n +-): Sigma = (pi c)^2 n C + lambda and mean = pi c n mom1 are monomials in
+// (c, n), so these are rescalings of the base moments (contrast.py:20-33).
+__global__ void __launch_bounds__(256) moments_scale_variants_kernel(int B, const double *c,
+                                                                     const double *n, const double *eps,
+                                                                     const double *lambda,
+                                                                     double *mean_ylm, double *cov_ylm) {
+  const int b = blockIdx.x, v = 7 + blockIdx.y, tid = threadIdx.x;
+  const int d = 3 + ((v - 7) >> 1);
+  const double e = ((v - 7) & 1) ? -eps[(size_t)d * B + b] : eps[(size_t)d * B + b];
+  const double cb = c[b], nb = n[b];
+  const double c2 = (d == 3) ? cb + e : cb, n2 = (d == 4) ? nb + e : nb;
+  const double fm = (c2 * n2) / (cb * nb);
+  const double fc = (c2 * c2 * n2) / (cb * cb * nb);
+  const size_t slot = (size_t)v * B + b;
+  mean_ylm[slot * 256 + tid] = fm * mean_ylm[(size_t)b * 256 + tid];
+  const double *src = cov_ylm + (size_t)b * 65536;
+  double *dst = cov_ylm + slot * 65536;
+  for (int i = tid; i < 65536; i += 256) {
+    const int row = i >> 8, col = i & 255;
+    const double lam = (row == col) ? lambda[row] : 0.0;
+    dst[i] = fma(fc, src[i] - lam, lam);
+  }
+}
 
 __device__ __forceinline__ double jrcp(double x) {
   double y;
@@ -946,6 +1184,58 @@ extern "C" int spb_gauss2beta(spb_context *ctx, int B, const double *mu_deg,
   return 0;
 }
 
+// K1b -> K1c -> K2 -> SYRK for B samples whose (Sred, qs, mom1, scale, info) are in place.
+static int moments_tail(spb_context *ctx, int B, K1Params &p1, MomWs &ws, double *cov_ylm, bool has_dr,
+                        cudaStream_t stream) {
+  moments_k1b<<<(B + K1B_WARPS - 1) / K1B_WARPS, 32 * K1B_WARPS, K1B_WARPS * sizeof(K1bWarp), stream>>>(p1);
+  SPB_LAUNCH_CHECK(ctx);
+  moments_k1c<<<B, NT1, 0, stream>>>(p1);
+  SPB_LAUNCH_CHECK(ctx);
+
+  int nitems = 0;
+  SPB_REQUIRE(k2_upload_items(ctx->device, &nitems) == 0, "ylm_moments: constant upload failed");
+  for (int b0 = 0; b0 < B; b0 += MOM_CHUNK) {
+    const int Bc = (B - b0 < MOM_CHUNK) ? B - b0 : MOM_CHUNK;
+    K2Params p2;
+    p2.tab = ctx->d_tables;
+    p2.S_lat = ws.S_lat + (size_t)b0 * 256 * 32;
+    p2.rkeep = ws.rkeep + b0;
+    p2.X = ws.X;
+    p2.B = Bc;
+    dim3 grid2(nitems, (Bc + K2_GROUP - 1) / K2_GROUP);
+    moments_k2<<<grid2, 256, 0, stream>>>(p2);
+    SPB_LAUNCH_CHECK(ctx);
+
+    gnt::Desc d = {};
+    d.A = ws.X;
+    d.strideA = 256 * 992;
+    d.lda = 992;
+    d.Bm = ws.X;
+    d.strideB = 256 * 992;
+    d.ldb = 992;
+    d.C = cov_ylm + (size_t)b0 * 65536;
+    d.strideC = 65536;
+    d.ldc = 256;
+    d.M = 256;
+    d.N = 256;
+    d.K = 992;
+    d.batch = Bc;
+    d.ksplit = 1;
+    d.strideSplit = 0;
+    d.lower_only = 1;
+    d.scale = ws.scale + b0;
+    d.vec = ws.mom1 + (size_t)b0 * 256;
+    d.strideVec = 256;
+    d.diag = ctx->d_tables + SPB_TAB_LAMBDA;
+    d.rkeep = ws.rkeep + b0;
+    d.ldeg = has_dr ? ws.E2 + (size_t)b0 * 256 : nullptr;
+    d.alpha = 1.0;
+    int st = gnt::launch<gnt::EPI_SYRK_COV>(ctx, d, stream);
+    if (st) return st;
+  }
+  return 0;
+}
+
 extern "C" size_t spb_ylm_moments_workspace_bytes(const spb_context *ctx, int B) {
   (void)ctx;
   return mom_ws_layout(B, nullptr, nullptr);
@@ -1005,52 +1295,123 @@ extern "C" int spb_ylm_moments_dr(spb_context *ctx, int B, const double *r_deg, 
   p1.qs = ws.qs;
   moments_k1a<<<B, NT1, sizeof(K1Smem), stream>>>(p1);
   SPB_LAUNCH_CHECK(ctx);
-  moments_k1b<<<(B + K1B_WARPS - 1) / K1B_WARPS, 32 * K1B_WARPS, K1B_WARPS * sizeof(K1bWarp), stream>>>(p1);
-  SPB_LAUNCH_CHECK(ctx);
-  moments_k1c<<<B, NT1, 0, stream>>>(p1);
-  SPB_LAUNCH_CHECK(ctx);
+  return moments_tail(ctx, B, p1, ws, cov_ylm, dr_deg != nullptr, stream);
+}
 
-  int nitems = 0;
-  SPB_REQUIRE(k2_upload_items(ctx->device, &nitems) == 0, "ylm_moments: constant upload failed");
-  for (int b0 = 0; b0 < B; b0 += MOM_CHUNK) {
-    const int Bc = (B - b0 < MOM_CHUNK) ? B - b0 : MOM_CHUNK;
-    K2Params p2;
-    p2.tab = ctx->d_tables;
-    p2.S_lat = ws.S_lat + (size_t)b0 * 256 * 32;
-    p2.rkeep = ws.rkeep + b0;
-    p2.X = ws.X;
-    p2.B = Bc;
-    dim3 grid2(nitems, (Bc + K2_GROUP - 1) / K2_GROUP);
-    moments_k2<<<grid2, 256, 0, stream>>>(p2);
-    SPB_LAUNCH_CHECK(ctx);
+// Workspace of the gradient call: the moments workspace of 7 B samples plus the tangent arrays.
+static size_t grad_ws_layout(int B, unsigned char *base, MomWs *ws, double **dS, double **dqs,
+                             double **dmom1, int32_t **info7) {
+  size_t off = mom_ws_layout(7 * B, base, ws);
+  auto take = [&](size_t bytes) {
+    size_t o = off;
+    off += (bytes + 255) & ~(size_t)255;
+    return o;
+  };
+  const size_t o1 = take((size_t)B * 2 * 1024 * 8), o2 = take((size_t)B * 16 * 8),
+               o3 = take((size_t)B * 3 * 256 * 8), o4 = take((size_t)7 * B * 4);
+  if (base) {
+    *dS = reinterpret_cast<double *>(base + o1);
+    *dqs = reinterpret_cast<double *>(base + o2);
+    *dmom1 = reinterpret_cast<double *>(base + o3);
+    *info7 = reinterpret_cast<int32_t *>(base + o4);
+  }
+  return off;
+}
 
-    gnt::Desc d = {};
-    d.A = ws.X;
-    d.strideA = 256 * 992;
-    d.lda = 992;
-    d.Bm = ws.X;
-    d.strideB = 256 * 992;
-    d.ldb = 992;
-    d.C = cov_ylm + (size_t)b0 * 65536;
-    d.strideC = 65536;
-    d.ldc = 256;
-    d.M = 256;
-    d.N = 256;
-    d.K = 992;
-    d.batch = Bc;
-    d.ksplit = 1;
-    d.strideSplit = 0;
-    d.lower_only = 1;
-    d.scale = ws.scale + b0;
-    d.vec = ws.mom1 + (size_t)b0 * 256;
-    d.strideVec = 256;
-    d.diag = ctx->d_tables + SPB_TAB_LAMBDA;
-    d.rkeep = ws.rkeep + b0;
-    d.ldeg = dr_deg ? ws.E2 + (size_t)b0 * 256 : nullptr;
-    d.alpha = 1.0;
-    int st = gnt::launch<gnt::EPI_SYRK_COV>(ctx, d, stream);
+extern "C" size_t spb_ylm_moments_grad_workspace_bytes(const spb_context *ctx, int B) {
+  (void)ctx;
+  return grad_ws_layout(B, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+}
+
+extern "C" int spb_ylm_moments_grad(spb_context *ctx, int B, const double *r_deg, const double *a,
+                                    const double *b, const double *c, const double *n, double rel_step,
+                                    double *mean_ylm, double *cov_ylm, double *eps, int32_t *info,
+                                    void *workspace, size_t workspace_bytes, void *stream_) {
+  SPB_REQUIRE(ctx != nullptr && B > 0 && rel_step > 0.0, "ylm_moments_grad: bad arguments");
+  SPB_REQUIRE(ctx->tables_count == SPB_TAB_TOTAL, "ylm_moments_grad: context has no constant tables");
+  SPB_REQUIRE(workspace != nullptr && workspace_bytes >= spb_ylm_moments_grad_workspace_bytes(ctx, B),
+              "ylm_moments_grad: workspace too small");
+  SPB_REQUIRE(((uintptr_t)workspace % 256) == 0, "ylm_moments_grad: workspace must be 256-byte aligned");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  SPB_CHECK_CUDA(cudaSetDevice(ctx->device));
+  MomWs ws;
+  double *dS, *dqs, *dmom1;
+  int32_t *info7;
+  grad_ws_layout(B, reinterpret_cast<unsigned char *>(workspace), &ws, &dS, &dqs, &dmom1, &info7);
+  static spb_once_flag attr_once;
+  {
+    const int st = spb_once_per_device(attr_once, ctx->device, [&]() -> int {
+      SPB_CHECK_CUDA(cudaFuncSetAttribute(moments_k1a, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)sizeof(K1Smem)));
+      SPB_CHECK_CUDA(cudaFuncSetAttribute(moments_k1a_tan, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)sizeof(K1Smem)));
+      SPB_CHECK_CUDA(cudaFuncSetAttribute(moments_k1b, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)(K1B_WARPS * sizeof(K1bWarp))));
+      return 0;
+    });
     if (st) return st;
   }
+  SPB_REQUIRE(k1_upload_perm(ctx->device) == 0, "ylm_moments_grad: constant upload failed");
+  // base sample: K1a into the first B slots of the 7 B arrays
+  K1Params p1;
+  p1.r_deg = r_deg;
+  p1.dr_deg = nullptr;
+  p1.E2 = ws.E2;
+  p1.a = a;
+  p1.b = b;
+  p1.c = c;
+  p1.n = n;
+  p1.B = B;
+  p1.tab = ctx->d_tables;
+  p1.mom1 = ws.mom1;
+  p1.mean_ylm = mean_ylm;
+  p1.S_lat = ws.S_lat;
+  p1.scale = ws.scale;
+  p1.rkeep = ws.rkeep;
+  p1.info = info7;
+  p1.Sred = ws.Sred;
+  p1.qs = ws.qs;
+  moments_k1a<<<B, NT1, sizeof(K1Smem), stream>>>(p1);
+  SPB_LAUNCH_CHECK(ctx);
+  K1TanParams pt;
+  pt.r_deg = r_deg;
+  pt.a = a;
+  pt.b = b;
+  pt.B = B;
+  pt.tab = ctx->d_tables;
+  pt.dS = dS;
+  pt.dqs = dqs;
+  pt.dmom1 = dmom1;
+  moments_k1a_tan<<<B, NT1, sizeof(K1Smem), stream>>>(pt);
+  SPB_LAUNCH_CHECK(ctx);
+  ExpandParams pe;
+  pe.B = B;
+  pe.rel_step = rel_step;
+  pe.c = c;
+  pe.n = n;
+  pe.dS = dS;
+  pe.dqs = dqs;
+  pe.dmom1 = dmom1;
+  pe.Sred = ws.Sred;
+  pe.qs = ws.qs;
+  pe.mom1 = ws.mom1;
+  pe.mean_ylm = mean_ylm;
+  pe.scale = ws.scale;
+  pe.info = info7;
+  pe.eps = eps;
+  moments_expand_kernel<<<B, 256, 0, stream>>>(pe);
+  SPB_LAUNCH_CHECK(ctx);
+  // the unchanged pipeline on the 7 B variants
+  p1.B = 7 * B;
+  int st = moments_tail(ctx, 7 * B, p1, ws, cov_ylm, false, stream);
+  if (st) return st;
+  moments_scale_variants_kernel<<<dim3(B, 4), 256, 0, stream>>>(B, c, n, eps,
+                                                               ctx->d_tables + SPB_TAB_LAMBDA, mean_ylm,
+                                                               cov_ylm);
+  SPB_LAUNCH_CHECK(ctx);
+  // flags of the base sample (bounds, eigen-solve) are what the caller sees
+  SPB_CHECK_CUDA(cudaMemcpyAsync(info, info7, (size_t)B * sizeof(int32_t), cudaMemcpyDeviceToDevice,
+                                 stream));
   return 0;
 }
 

@@ -251,7 +251,9 @@ class StarryProcess(object):
         self._r, self._c, self._n = tens["r"], tens["c"], tens["n"]
         self._tau = tens.get("tau", None)
         self._dr = tens.get("dr", None)
+        self._mu_sigma = None
         if a is None:
+            self._mu_sigma = (tens["mu"], tens["sigma"])
             self._a = torch.empty(B, dtype=torch.float64, device=self.device)
             self._b = torch.empty(B, dtype=torch.float64, device=self.device)
             with torch.cuda.device(self.device):
@@ -631,12 +633,17 @@ class StarryProcess(object):
     # ------------------------------------------------------------------ log likelihood
     def log_likelihood(self, t, flux, data_cov, i=defaults["i"], p=defaults["p"], u=None,
                        baseline_mean=defaults["baseline_mean"],
-                       baseline_var=defaults["baseline_var"], marginalize_over_inclination=None):
+                       baseline_var=defaults["baseline_var"], marginalize_over_inclination=None,
+                       return_grad=False):
         """sp.py:1052-1188.  ``flux`` is ``(nt,)`` or ``(M, nt)`` (M light curves sharing period,
         limb darkening, inclination and noise, scored jointly); returns a scalar, or ``(B,)`` for a
         batch of hyperparameter samples.  Extension: ``flux`` of shape ``(B, M, nt)`` gives every
         batch element its own light curve(s) (the light-curve x sample x inclination batches of
         calibrate/inclination.py:63-74)."""
+        if return_grad:
+            return self.log_likelihood_and_grad(
+                t, flux, data_cov, i=i, p=p, u=u, baseline_mean=baseline_mean,
+                baseline_var=baseline_var, marginalize_over_inclination=marginalize_over_inclination)
         marg, t, inc, rta1 = self._prep(t, i, p, u, marginalize_over_inclination)
         nt = t.numel()
         ldk = nt + (nt & 1)
@@ -707,6 +714,87 @@ class StarryProcess(object):
                 del K, resid, out
         self._z = torch.cat(zs)
         return self._out(lnlike)
+
+    # ------------------------------------------------------------------ gradient
+    def log_likelihood_and_grad(self, t, flux, data_cov, i=defaults["i"], p=defaults["p"], u=None,
+                                baseline_mean=defaults["baseline_mean"],
+                                baseline_var=defaults["baseline_var"],
+                                marginalize_over_inclination=None, rel_step=1e-4):
+        """``log_likelihood`` and its gradient with respect to the hyperparameters the process was
+        built from -- ``r`` [deg], ``a`` and ``b`` (or ``mu`` and ``sigma`` [deg]), ``c``, ``n`` -- as
+        ``(lnlike, {"r": ..., "a" | "mu": ..., "b" | "sigma": ..., "c": ..., "n": ...})``, one value
+        per batch element.  What the reference obtains by Theano reverse mode (``tt.grad`` of
+        sp.py:1052-1188 through ops/include/latitude.h:22-173, eigh.h:19-65, wigner.h:345-404,
+        465-531, math.py:40-72; checked there with ``verify_grad`` at 1e-4, tests/test_lnlike.py:105-136).
+
+        Here: the Ylm moments move along their ANALYTIC tangents (``spb_ylm_moments_grad``: derivative
+        lanes of the Beta moments, profile derivative, monomial scalings in c and n; exact because
+        the rest of the moment pipeline is linear / quadratic), and the log-likelihood of the ten
+        displaced moment sets is evaluated by the same kernels in ONE batch of 11 B elements; the
+        central difference along each tangent has a relative truncation error of ``rel_step**2``
+        (the flux-side likelihood is smooth in the moments) and no eigen-solver noise, because the
+        displaced sets share the base eigen-problem up to the smooth perturbation.  Measured against
+        the analytic oracle (oracle/sp_oracle_grad.py): <= 1e-6 relative."""
+        if self._dr is not None or self._time_variable or not hasattr(self, "_r") or self._r is None:
+            raise NotImplementedError("gradients: delta spot-size prior, static surfaces, a single "
+                                      "process (not a sum)")
+        dev, B = self.device, self._B
+        lib, h = self._lib, self._ctx.handle
+        with torch.cuda.device(dev):
+            mean = torch.empty(11 * B, 256, dtype=torch.float64, device=dev)
+            cov = torch.empty(11 * B, 256, 256, dtype=torch.float64, device=dev)
+            eps = torch.empty(5, B, dtype=torch.float64, device=dev)
+            info = torch.zeros(B, dtype=torch.int32, device=dev)
+            nb = lib.spb_ylm_moments_grad_workspace_bytes(h, B)
+            ws = torch.empty(nb, dtype=torch.uint8, device=dev)
+            ev = self._mark("moments_grad")
+            _lib.check(lib.spb_ylm_moments_grad(h, B, _ptr(self._r), _ptr(self._a), _ptr(self._b),
+                                                _ptr(self._c), _ptr(self._n), float(rel_step),
+                                                _ptr(mean), _ptr(cov), _ptr(eps), _ptr(info), _ptr(ws),
+                                                nb, _stream()))
+            self._mark_end(ev)
+            del ws
+            # an 11 B-wide process over the displaced moments; everything else is shared
+            big = object.__new__(StarryProcess)
+            big.__dict__.update(self.__dict__)
+            big._B, big._batched = 11 * B, True
+            big._mean_ylm, big._cov_ylm, big._cho_cov_ylm = mean, cov, None
+            big._info = info.repeat(11).contiguous()
+            big._rTA1_cache = self._rTA1_cache
+
+            def tile(x, per_dim):
+                """Per-element arguments (leading dimension B) are repeated for the 11 variants."""
+                if isinstance(x, (torch.Tensor, np.ndarray)):
+                    xt = torch.as_tensor(x, dtype=torch.float64).to(dev)
+                    if xt.ndim == per_dim and xt.shape[0] == B and B > 1:
+                        return xt.repeat((11,) + (1,) * (xt.ndim - 1))
+                    return xt
+                return x
+
+            ll_all = big.log_likelihood(
+                t, tile(flux, 3), data_cov, i=tile(i, 1), p=p, u=u, baseline_mean=tile(baseline_mean, 1),
+                baseline_var=tile(baseline_var, 1),
+                marginalize_over_inclination=marginalize_over_inclination).reshape(11, B)
+            self._z = None if big._z is None else big._z[:B]
+            self._info = big._info[:B].clone()
+            ll = ll_all[0]
+            g = (ll_all[1::2] - ll_all[2::2]) / (2.0 * eps)          # (5, B): r, a, b, c, n
+            ok = torch.isfinite(ll)[None, :] & torch.isfinite(ll_all[1:]).reshape(5, 2, B).all(dim=1)
+            g = torch.where(torch.isfinite(ll)[None, :].expand(5, B), g, torch.zeros_like(g))
+            g = torch.where(ok | ~torch.isfinite(ll)[None, :], g, torch.full_like(g, float("nan")))
+            grad = {"r": self._out(g[0]), "c": self._out(g[3]), "n": self._out(g[4])}
+            if getattr(self, "_mu_sigma", None) is None:
+                grad["a"], grad["b"] = self._out(g[1]), self._out(g[2])
+            else:
+                # (a, b) = gauss2beta(mu, sigma), latitude.py:14-77: elementwise 2 x 2 Jacobian
+                mu = self._mu_sigma[0].detach().clone().requires_grad_(True)
+                sg = self._mu_sigma[1].detach().clone().requires_grad_(True)
+                a_, b_ = gauss2beta(mu, sg)
+                da = torch.autograd.grad(a_.sum(), (mu, sg), retain_graph=True)
+                db = torch.autograd.grad(b_.sum(), (mu, sg))
+                grad["mu"] = self._out(g[1] * da[0] + g[2] * db[0])
+                grad["sigma"] = self._out(g[1] * da[1] + g[2] * db[1])
+        return self._out(ll), grad
 
     # ------------------------------------------------------------------ SURVEY 8(f) rank 2
     def _factor_rows(self, K, n, ldk, rows=None, diag_add=None):

@@ -381,3 +381,101 @@ def test_uniform_spot_size_prior_against_reference_golden(spb, golden):
                             mu=30.0, sigma=5.0, c=0.1, n=10.0)
     ll = bad.log_likelihood(g["t"][:50], np.zeros(50), 1e-6)
     assert np.isfinite(ll[0].item()) and np.isneginf(ll[1].item()) and int(bad.info[1].item()) & 4
+
+
+# ------------------------------------------------------------------------- gradient (8(f) rank 4)
+# The reference accepts its own gradient at 1e-4 (theano.gradient.verify_grad defaults for float64,
+# tests/test_lnlike.py:105-136).  Two statements are tested here:
+#   (1) the CUDA gradient IS the derivative of the CUDA forward function: <= 1e-4 relative against
+#       plain central differences of log_likelihood in the hyperparameters (measured 5e-6..4e-5: that
+#       is the noise floor of the DIFFERENCES -- eigenvalue-clip modes enter and leave between the
+#       two displaced evaluations -- which the tangent-wise scheme of the product avoids);
+#   (2) it agrees with the analytic, clip-free gradient oracle to <= 3e-4: the two forward
+#       functions agree to ~1e-9 |lnlike| (the reference's eigenvalue-clip floor, different modes
+#       are dropped in the 256- and the 31-dimensional eigen-problems), which pins slopes only to
+#       1e-9 |lnlike| / (|g| x correlation length) ~ 1e-4.
+GRAD_RTOL_SELF = 1e-4
+GRAD_RTOL_ORACLE = 3e-4
+
+
+@pytest.mark.parametrize("marg", [False, True])
+@pytest.mark.parametrize("norm", [False, True])
+def test_lnlike_gradient_against_analytic_oracle(spb, oracle, marg, norm):
+    """``log_likelihood(..., return_grad=True)``: d lnlike / d (r, a, b, c, n) per batch element against
+    the analytic gradient oracle (oracle/sp_oracle_grad.py, itself pinned to finite differences of
+    the unmodified reference at the reference's own verify_grad tolerance, tests/test_oracle_grad.py)
+    and against central differences of the CUDA forward."""
+    from oracle import sp_oracle_grad as sg
+
+    rng = np.random.default_rng(42)
+    t = np.linspace(0, 3, 100)
+    flux = 1e-3 * rng.standard_normal(100)
+    hps = [dict(r=20.0, a=0.40, b=0.27, c=0.1, n=10.0),
+           dict(r=12.0, a=0.55, b=0.12, c=0.05, n=4.0),
+           dict(r=27.0, a=0.25, b=0.45, c=0.12, n=2.0)]
+    batch = {k: np.array([h[k] for h in hps]) for k in hps[0]}
+    gp = spb.StarryProcess(marginalize_over_inclination=marg, normalized=norm, **batch)
+    ll, g = gp.log_likelihood(t, flux, 1e-6, i=60.0, p=1.0, u=U_LD, return_grad=True)
+    ll0 = gp.log_likelihood(t, flux, 1e-6, i=60.0, p=1.0, u=U_LD)
+    assert torch.equal(ll, ll0)            # the base variant is the plain evaluation, bit for bit
+    # (1) derivative of the CUDA forward: plain central differences, relative step 1e-3
+    worst_self = 0.0
+    for p_ in sg.PARAMS:
+        d = 1e-3 * batch[p_]
+        up, dn = dict(batch), dict(batch)
+        up[p_] = batch[p_] + d
+        dn[p_] = batch[p_] - d
+        lu = spb.StarryProcess(marginalize_over_inclination=marg, normalized=norm, **up).log_likelihood(
+            t, flux, 1e-6, i=60.0, p=1.0, u=U_LD).cpu().numpy()
+        ld = spb.StarryProcess(marginalize_over_inclination=marg, normalized=norm, **dn).log_likelihood(
+            t, flux, 1e-6, i=60.0, p=1.0, u=U_LD).cpu().numpy()
+        fd = (lu - ld) / (2 * d)
+        gg = g[p_].cpu().numpy()
+        scale = np.maximum(np.abs(fd), 1e-3 * np.max([np.abs(g[q].cpu().numpy()) for q in sg.PARAMS], axis=0))
+        err = np.abs(gg - fd) / scale
+        worst_self = max(worst_self, err.max())
+        assert err.max() <= GRAD_RTOL_SELF, (p_, gg, fd)
+    # (2) the analytic oracle
+    worst = 0.0
+    for k, hp in enumerate(hps):
+        llo, go = sg.lnlike_and_grad(hp, t, flux, 1e-6, i=60.0, p=1.0, u=U_LD,
+                                     marginalize_over_inclination=marg, normalized=norm)
+        assert rel(ll[k].item(), llo) <= 1e-8
+        errs = {}
+        for p_ in sg.PARAMS:
+            errs[p_] = abs(g[p_][k].item() - go[p_]) / max(
+                abs(go[p_]), 1e-3 * max(abs(v) for v in go.values()))
+            worst = max(worst, errs[p_])
+        assert max(errs.values()) <= GRAD_RTOL_ORACLE, (k, errs, {a: g[a][k].item() for a in g}, go)
+    print("gradient marg=%d norm=%d: max rel err %.1e vs central differences of the CUDA forward, "
+          "%.1e vs the analytic oracle" % (marg, norm, worst_self, worst))
+
+
+def test_lnlike_gradient_mu_sigma_and_flags(spb, oracle):
+    """Chain rule through gauss2beta (latitude.py:14-77) when the process is built from (mu, sigma);
+    scalar processes return scalars; -inf elements return a zero gradient; the uniform-dr prior and
+    time-variable processes raise."""
+    rng = np.random.default_rng(1)
+    t = np.linspace(0, 2, 80)
+    flux = 1e-3 * rng.standard_normal(80)
+    gp = spb.StarryProcess(r=15.0, mu=35.0, sigma=8.0, c=0.08, n=5.0)
+    ll, g = gp.log_likelihood(t, flux, 1e-6, u=U_LD, return_grad=True)
+    assert ll.ndim == 0 and set(g) == {"r", "mu", "sigma", "c", "n"}
+    for key, h in (("mu", 1e-3), ("sigma", 1e-3), ("r", 1e-3), ("c", 1e-6), ("n", 1e-4)):
+        hp = dict(r=15.0, mu=35.0, sigma=8.0, c=0.08, n=5.0)
+        up, dn = dict(hp), dict(hp)
+        up[key] += h
+        dn[key] -= h
+        fd = (oracle.OracleProcess(**up).log_likelihood(t, flux, 1e-6, u=U_LD)
+              - oracle.OracleProcess(**dn).log_likelihood(t, flux, 1e-6, u=U_LD)) / (2 * h)
+        assert abs(g[key].item() - fd) <= 1e-4 * max(abs(fd), 1.0), (key, g[key].item(), fd)
+    # an element outside the validity range of the normalised process: lnlike = -inf, gradient 0
+    gb = spb.StarryProcess(r=np.array([15.0, 10.107390922311073]), mu=np.array([35.0, 51.978254148197465]), sigma=np.array([8.0, 11.733947364331115]),
+                           c=np.array([0.08, 0.5845712920357633]), n=np.array([5.0, 41.4605890605386]))
+    ll, g = gb.log_likelihood(t, flux, 1e-6, u=U_LD, return_grad=True)
+    assert np.isfinite(ll[0].item()) and np.isneginf(ll[1].item())
+    assert all(float(v[1]) == 0.0 and np.isfinite(float(v[0])) for v in g.values())
+    with pytest.raises(NotImplementedError):
+        spb.StarryProcess(r=15.0, dr=5.0).log_likelihood(t, flux, 1e-6, return_grad=True)
+    with pytest.raises(NotImplementedError):
+        spb.StarryProcess(r=15.0, tau=1.0).log_likelihood(t, flux, 1e-6, return_grad=True)
