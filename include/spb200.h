@@ -80,6 +80,23 @@ int spb_log_jac(spb_context *ctx, int B, const double *a, const double *b, doubl
  *   cov_ylm           : (B, 256, 256)  out
  *   info              : (B)            out (bit mask above)
  * ------------------------------------------------------------------------------------------- */
+/* Keyword options of the moment integrals that the reference threads through its constructor
+ * (sp.py:241-262, defaults.py:4-35).  A NULL pointer / zero field selects the reference default.
+ *   Bp            (16, 1000) spot profile operator S A (size.py:10-43) for a lower spherical-harmonic
+ *                 degree: rows l > ydeg zero.  The degree-15 machinery then evaluates the ydeg < 15
+ *                 process exactly (the latitude / longitude rotations are block-diagonal in l), the
+ *                 caller reads the leading (ydeg+1)^2 block of mean_ylm / cov_ylm
+ *   lambda        (256) diagonal jitter: epsy for l < 15, epsy15 for l = 15 (contrast.py:26-32); zero
+ *                 for l > ydeg when a lower degree is embedded
+ *   abmin, log_alpha_max, log_beta_max      latitude.py:171-200                                  */
+typedef struct {
+  const double *Bp;
+  const double *lambda;
+  double abmin;
+  double log_alpha_max;
+  double log_beta_max;
+} spb_moments_options;
+
 size_t spb_ylm_moments_workspace_bytes(const spb_context *ctx, int B);
 int spb_ylm_moments(spb_context *ctx, int B, const double *r_deg, const double *a, const double *b,
                     const double *c, const double *n, double *mean_ylm, double *cov_ylm,
@@ -88,8 +105,12 @@ int spb_ylm_moments(spb_context *ctx, int B, const double *r_deg, const double *
  * Spot.get_e, Spot.get_eigE): dr_deg (B) in degrees, or NULL for the delta prior above.          */
 int spb_ylm_moments_dr(spb_context *ctx, int B, const double *r_deg, const double *dr_deg,
                        const double *a, const double *b, const double *c, const double *n,
-                       double *mean_ylm, double *cov_ylm, int32_t *info, void *workspace,
-                       size_t workspace_bytes, void *stream);
+                       const spb_moments_options *opt, double *mean_ylm, double *cov_ylm,
+                       int32_t *info, void *workspace, size_t workspace_bytes, void *stream);
+int spb_gauss2beta_opt(spb_context *ctx, int B, const double *mu_deg, const double *sigma_deg,
+                       const spb_moments_options *opt, double *a, double *b, void *stream);
+int spb_log_jac_opt(spb_context *ctx, int B, const double *a, const double *b, double sigma_max_deg,
+                    const spb_moments_options *opt, double *log_jac, void *stream);
 
 /* (f-4) Ylm moments AND their derivatives with respect to (r [deg], a, b, c, n), for the gradient of
  * the log-likelihood (the reference: Theano reverse mode through ops/include/latitude.h:22-173
@@ -104,9 +125,10 @@ int spb_ylm_moments_dr(spb_context *ctx, int B, const double *r_deg, const doubl
  *   mean_ylm: (11 B, 256) out;  cov_ylm: (11 B, 256, 256) out;  info: (B) out                      */
 size_t spb_ylm_moments_grad_workspace_bytes(const spb_context *ctx, int B);
 int spb_ylm_moments_grad(spb_context *ctx, int B, const double *r_deg, const double *a,
-                         const double *b, const double *c, const double *n, double rel_step,
-                         double *mean_ylm, double *cov_ylm, double *eps, int32_t *info,
-                         void *workspace, size_t workspace_bytes, void *stream);
+                         const double *b, const double *c, const double *n,
+                         const spb_moments_options *opt, double rel_step, double *mean_ylm,
+                         double *cov_ylm, double *eps, int32_t *info, void *workspace,
+                         size_t workspace_bytes, void *stream);
 
 /* Cholesky factor of cov_ylm and prior draws -- sp.py:265-271, 489-509.
  *   L_ylm : (B,256,256) out, lower triangle (upper zeroed);  unit_normals: (B, nsamples, 256)

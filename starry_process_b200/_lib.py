@@ -27,6 +27,12 @@ class NoiseModel(_c.Structure):
     ]
 
 
+class MomentsOptions(_c.Structure):
+    """spb_moments_options (include/spb200.h)."""
+    _fields_ = [("Bp", _P), ("lambda_", _P), ("abmin", _D), ("log_alpha_max", _D),
+                ("log_beta_max", _D)]
+
+
 class Affine(_c.Structure):
     """spb_affine (include/spb200.h)."""
     _fields_ = [
@@ -46,9 +52,13 @@ PROTOTYPES = {
     "spb_log_jac": (_I, [_P, _I, _P, _P, _D, _P, _P]),
     "spb_ylm_moments_workspace_bytes": (_SZ, [_P, _I]),
     "spb_ylm_moments": (_I, [_P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _SZ, _P]),
-    "spb_ylm_moments_dr": (_I, [_P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _SZ, _P]),
+    "spb_ylm_moments_dr": (_I, [_P, _I, _P, _P, _P, _P, _P, _P, _c.POINTER(MomentsOptions), _P, _P,
+                                _P, _P, _SZ, _P]),
+    "spb_gauss2beta_opt": (_I, [_P, _I, _P, _P, _c.POINTER(MomentsOptions), _P, _P, _P]),
+    "spb_log_jac_opt": (_I, [_P, _I, _P, _P, _D, _c.POINTER(MomentsOptions), _P, _P]),
     "spb_ylm_moments_grad_workspace_bytes": (_SZ, [_P, _I]),
-    "spb_ylm_moments_grad": (_I, [_P, _I, _P, _P, _P, _P, _P, _D, _P, _P, _P, _P, _P, _SZ, _P]),
+    "spb_ylm_moments_grad": (_I, [_P, _I, _P, _P, _P, _P, _P, _c.POINTER(MomentsOptions), _D, _P, _P,
+                                  _P, _P, _P, _SZ, _P]),
     "spb_cho_cov_ylm": (_I, [_P, _I, _P, _P, _P, _P]),
     "spb_sample_ylm": (_I, [_P, _I, _I, _P, _P, _P, _P, _P]),
     "spb_flux_operator": (_I, [_P, _I, _P, _P, _P]),

@@ -326,6 +326,19 @@ def _matrix_sqrt(Q, neig):
     return U @ np.diag(sw)
 
 
+def spot_operator(ydeg):
+    """size.py:10-43: ``Bp = S A`` (ydeg + 1, 1000), the smoothed least-squares Legendre fit of a spot
+    profile sampled on ``theta = linspace(0, pi, 1000)``.  The fit degree enters ``A`` (the Legendre
+    polynomials are not orthogonal on the grid), so a lower ``ydeg`` has its own operator."""
+    theta = np.linspace(0, np.pi, SPTS)
+    cost = np.cos(theta)
+    B = np.hstack([np.sqrt(2 * l + 1) * _legendre(l)(cost).reshape(-1, 1) for l in range(ydeg + 1)])
+    A = np.linalg.solve(B.T @ B + 1e-9 * np.eye(ydeg + 1), B.T)
+    ll = np.arange(ydeg + 1)
+    S = np.exp(-0.5 * ll * (ll + 1) * 0.075 ** 2)
+    return S[:, None] * A
+
+
 _CACHE = {}
 LONGITUDE_BASES = ("pinned", "host")
 

@@ -33,6 +33,8 @@ constexpr int JS = 33;  // Jacobi smem stride
 
 struct K1Params {
   const double *r_deg, *a, *b, *c, *n;
+  const double *Bp;      // (16,1000) spot profile operator (context table, or a per-process one for ydeg < 15)
+  double abmin, lam, lbm;   // latitude.py:178-200: clamp of a, b; log_alpha_max; log_beta_max
   const double *dr_deg;  // (B) half-width of the uniform spot-radius prior, or nullptr (delta prior)
   double *E2;            // (B,16,16) spot-size second moment Etilde (dr prior only)
   int B;
@@ -332,8 +334,8 @@ __global__ void __launch_bounds__(NT1, 2) moments_k1a(K1Params p) {
   const bool has_dr = p.dr_deg != nullptr;
   const double dr = has_dr ? p.dr_deg[b] * ang : 0.0;
   if (has_dr) bad = bad || !(dr >= -tol && dr <= 0.5 * 3.14159265358979323846 + tol);   // size.py:120
-  if (aa < 1e-12) aa = 1e-12;  // latitude.py:180-182 (abmin)
-  if (bb < 1e-12) bb = 1e-12;
+  if (aa < p.abmin) aa = p.abmin;  // latitude.py:180-182 (abmin)
+  if (bb < p.abmin) bb = p.abmin;
 
   // ---- spot profile, size.py:45-53 (sfac = 300); uniform radius prior: its mean over
   // [r - dr, r + dr], size.py:55-62 (Spot.get_e)
@@ -385,7 +387,7 @@ __global__ void __launch_bounds__(NT1, 2) moments_k1a(K1Params p) {
         __syncthreads();
         for (int k = tid; k < 16 * 64; k += NT1) {
           const int l = k >> 6, jj = k & 63;
-          Bst[k] = (j0 + jj < kmax) ? tab[SPB_TAB_BP + (size_t)l * 1000 + j0 + jj] : 0.0;
+          Bst[k] = (j0 + jj < kmax) ? p.Bp[(size_t)l * 1000 + j0 + jj] : 0.0;
         }
         __syncthreads();
         if (live) {
@@ -415,7 +417,7 @@ __global__ void __launch_bounds__(NT1, 2) moments_k1a(K1Params p) {
       {
         const int l1 = tid >> 4, l2 = tid & 15;
         const int in = min(NT1, kmax - i0);
-        const double *bp = tab + SPB_TAB_BP + (size_t)l1 * 1000 + i0;
+        const double *bp = p.Bp + (size_t)l1 * 1000 + i0;
         for (int ii = 0; ii < in; ++ii) eacc = fma(bp[ii], Wst[ii * 16 + l2], eacc);
       }
     }
@@ -423,7 +425,7 @@ __global__ void __launch_bounds__(NT1, 2) moments_k1a(K1Params p) {
     __syncthreads();
   }
   for (int row = warp; row < 16; row += NT1 / 32) {
-    const double *bp = tab + SPB_TAB_BP + (size_t)row * 1000;
+    const double *bp = p.Bp + (size_t)row * 1000;
     double acc = 0.0;
     for (int s = lane; s < 1000; s += 32) acc = fma(bp[s], sm.bprof[s], acc);
     acc = warp_sum(acc);
@@ -433,8 +435,8 @@ __global__ void __launch_bounds__(NT1, 2) moments_k1a(K1Params p) {
   K1PROF(0);
   // ---- Beta moments, latitude.py:197-200 and latitude.h:48-60
   if (tid == 0) {
-    const double alpha0 = exp(aa * 10.0);
-    const double beta0 = exp(log(0.5) + bb * (10.0 - log(0.5)));
+    const double alpha0 = exp(aa * p.lam);
+    const double beta0 = exp(log(0.5) + bb * (p.lbm - log(0.5)));
     const double alpha = alpha0 > 0.0 ? alpha0 : 0.0;  // ops/latitude/latitude.cc:47-48
     const double beta = beta0 > 0.0 ? beta0 : 0.0;
     sm.Bk[0] = 1.0;
@@ -509,6 +511,8 @@ __global__ void __launch_bounds__(NT1, 2) moments_k1a(K1Params p) {
 // ------------------------------------------------------------------------------------------
 struct K1TanParams {
   const double *r_deg, *a, *b;
+  const double *Bp;
+  double abmin, lam, lbm;
   int B;
   const double *tab;
   double *dS;     // (B,2,32,32)
@@ -525,9 +529,9 @@ __global__ void __launch_bounds__(NT1, 2) moments_k1a_tan(K1TanParams p) {
   const double ang = 3.14159265358979323846 / 180.0;
   const double r = p.r_deg[b] * ang;
   double aa = p.a[b], bb = p.b[b];
-  const bool a_free = aa > 1e-12, b_free = bb > 1e-12;   // latitude.py:180-182 (abmin clamp)
-  if (!a_free) aa = 1e-12;
-  if (!b_free) bb = 1e-12;
+  const bool a_free = aa > p.abmin, b_free = bb > p.abmin;   // latitude.py:180-182 (abmin clamp)
+  if (!a_free) aa = p.abmin;
+  if (!b_free) bb = p.abmin;
   __shared__ double dqs_s[16];
   __shared__ double lanes[3][64];   // B, dB/dalpha, dB/dbeta
   __shared__ double chain[2];
@@ -542,7 +546,7 @@ __global__ void __launch_bounds__(NT1, 2) moments_k1a_tan(K1TanParams p) {
     }
     __syncthreads();
     for (int row = warp; row < 16; row += NT1 / 32) {
-      const double *bp = tab + SPB_TAB_BP + (size_t)row * 1000;
+      const double *bp = p.Bp + (size_t)row * 1000;
       double acc = 0.0;
       for (int s = lane; s < 1000; s += 32) acc = fma(bp[s], sm.bprof[s], acc);
       acc = warp_sum(acc);
@@ -554,12 +558,12 @@ __global__ void __launch_bounds__(NT1, 2) moments_k1a_tan(K1TanParams p) {
 
   // ---- Beta moments and their derivative lanes, latitude.h:48-60
   if (tid == 0) {
-    const double alpha0 = exp(aa * 10.0);
-    const double beta0 = exp(log(0.5) + bb * (10.0 - log(0.5)));
+    const double alpha0 = exp(aa * p.lam);
+    const double beta0 = exp(log(0.5) + bb * (p.lbm - log(0.5)));
     const double alpha = alpha0 > 0.0 ? alpha0 : 0.0;
     const double beta = beta0 > 0.0 ? beta0 : 0.0;
-    chain[0] = a_free ? 10.0 * alpha : 0.0;
-    chain[1] = b_free ? (10.0 - log(0.5)) * beta : 0.0;
+    chain[0] = a_free ? p.lam * alpha : 0.0;
+    chain[1] = b_free ? (p.lbm - log(0.5)) * beta : 0.0;
     lanes[0][0] = 1.0;
     lanes[1][0] = 0.0;
     lanes[2][0] = 0.0;
@@ -1123,7 +1127,7 @@ size_t mom_ws_layout(int B, unsigned char *base, MomWs *ws) {
 
 // gauss2beta, latitude.py:62-77
 __global__ void gauss2beta_kernel(int B, const double *mu, const double *sigma, double *a,
-                                  double *b) {
+                                  double *b, double lam, double lbm) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B) return;
   const double ang = 3.14159265358979323846 / 180.0;
@@ -1134,21 +1138,21 @@ __global__ void gauss2beta_kernel(int B, const double *mu, const double *sigma, 
   const double term = 1.0 / (16 * v * (ch * ch * ch * ch));
   const double alpha = (2 + 4 * v + (3 + 8 * v) * c1 + 2 * c2 + c3) * term;
   const double beta = (c1 + 2 * v * (3 + c2) - c3) * term;
-  a[i] = log(alpha) / 10.0;
-  b[i] = fmax(0.0, (log(beta) - log(0.5)) / (10.0 - log(0.5)));
+  a[i] = log(alpha) / lam;
+  b[i] = fmax(0.0, (log(beta) - log(0.5)) / (lbm - log(0.5)));
 }
 
 // log |d(a, b) / d(mu, sigma)|, latitude.py:221-241 (mode and width of the latitude pdf from the
 // Beta shape parameters) and 281-316; -inf when sigma > sigma_max.
 __global__ void log_jac_kernel(int B, const double *a, const double *b, double sigma_max_rad,
-                               double *out) {
+                               double *out, double abmin, double lam, double lbm) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B) return;
   double aa = a[i], bb = b[i];
-  if (aa < 1e-12) aa = 1e-12;  // latitude.py:178-182 (abmin)
-  if (bb < 1e-12) bb = 1e-12;
-  const double al = exp(aa * 10.0);
-  const double be = exp(log(0.5) + bb * (10.0 - log(0.5)));
+  if (aa < abmin) aa = abmin;  // latitude.py:178-182 (abmin)
+  if (bb < abmin) bb = abmin;
+  const double al = exp(aa * lam);
+  const double be = exp(log(0.5) + bb * (lbm - log(0.5)));
   double term = 4 * al * al - 8 * al - 6 * be + 4 * al * be + be * be + 5;
   const double mu = 2 * atan(sqrt(2 * al + be - 2 - sqrt(term)));
   const double cm = cos(mu), sn = sin(mu);
@@ -1165,28 +1169,58 @@ __global__ void log_jac_kernel(int B, const double *a, const double *b, double s
 
 }  // namespace
 
+// Options of the moment integrals that the reference threads through as keywords (sp.py:241-262):
+// NULL or zero-initialised fields mean the reference defaults (defaults.py:4-35).
+static void resolve_options(const spb_context *ctx, const spb_moments_options *opt, const double **Bp,
+                            const double **lambda, double *abmin, double *lam, double *lbm) {
+  *Bp = (opt && opt->Bp) ? opt->Bp : ctx->d_tables + SPB_TAB_BP;
+  *lambda = (opt && opt->lambda) ? opt->lambda : ctx->d_tables + SPB_TAB_LAMBDA;
+  *abmin = (opt && opt->abmin > 0.0) ? opt->abmin : 1e-12;
+  *lam = (opt && opt->log_alpha_max > 0.0) ? opt->log_alpha_max : 10.0;
+  *lbm = (opt && opt->log_beta_max > 0.0) ? opt->log_beta_max : 10.0;
+}
+
 extern "C" int spb_log_jac(spb_context *ctx, int B, const double *a, const double *b,
                            double sigma_max_deg, double *log_jac, void *stream) {
+  return spb_log_jac_opt(ctx, B, a, b, sigma_max_deg, nullptr, log_jac, stream);
+}
+
+extern "C" int spb_log_jac_opt(spb_context *ctx, int B, const double *a, const double *b,
+                               double sigma_max_deg, const spb_moments_options *opt, double *log_jac,
+                               void *stream) {
   SPB_REQUIRE(ctx != nullptr && B > 0, "log_jac: bad arguments");
   SPB_CHECK_CUDA(cudaSetDevice(ctx->device));
+  const double *Bp, *lambda;
+  double abmin, lam, lbm;
+  resolve_options(ctx, opt, &Bp, &lambda, &abmin, &lam, &lbm);
   log_jac_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
-      B, a, b, sigma_max_deg * 3.14159265358979323846 / 180.0, log_jac);
+      B, a, b, sigma_max_deg * 3.14159265358979323846 / 180.0, log_jac, abmin, lam, lbm);
   SPB_LAUNCH_CHECK(ctx);
   return 0;
 }
 
 extern "C" int spb_gauss2beta(spb_context *ctx, int B, const double *mu_deg,
                               const double *sigma_deg, double *a, double *b, void *stream) {
+  return spb_gauss2beta_opt(ctx, B, mu_deg, sigma_deg, nullptr, a, b, stream);
+}
+
+extern "C" int spb_gauss2beta_opt(spb_context *ctx, int B, const double *mu_deg,
+                                  const double *sigma_deg, const spb_moments_options *opt, double *a,
+                                  double *b, void *stream) {
   SPB_REQUIRE(ctx != nullptr && B > 0, "gauss2beta: bad arguments");
   SPB_CHECK_CUDA(cudaSetDevice(ctx->device));
-  gauss2beta_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(B, mu_deg, sigma_deg, a, b);
+  const double *Bp, *lambda;
+  double abmin, lam, lbm;
+  resolve_options(ctx, opt, &Bp, &lambda, &abmin, &lam, &lbm);
+  gauss2beta_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(B, mu_deg, sigma_deg, a, b, lam,
+                                                                     lbm);
   SPB_LAUNCH_CHECK(ctx);
   return 0;
 }
 
 // K1b -> K1c -> K2 -> SYRK for B samples whose (Sred, qs, mom1, scale, info) are in place.
 static int moments_tail(spb_context *ctx, int B, K1Params &p1, MomWs &ws, double *cov_ylm, bool has_dr,
-                        cudaStream_t stream) {
+                        const double *lambda, cudaStream_t stream) {
   moments_k1b<<<(B + K1B_WARPS - 1) / K1B_WARPS, 32 * K1B_WARPS, K1B_WARPS * sizeof(K1bWarp), stream>>>(p1);
   SPB_LAUNCH_CHECK(ctx);
   moments_k1c<<<B, NT1, 0, stream>>>(p1);
@@ -1226,7 +1260,7 @@ static int moments_tail(spb_context *ctx, int B, K1Params &p1, MomWs &ws, double
     d.scale = ws.scale + b0;
     d.vec = ws.mom1 + (size_t)b0 * 256;
     d.strideVec = 256;
-    d.diag = ctx->d_tables + SPB_TAB_LAMBDA;
+    d.diag = lambda;
     d.rkeep = ws.rkeep + b0;
     d.ldeg = has_dr ? ws.E2 + (size_t)b0 * 256 : nullptr;
     d.alpha = 1.0;
@@ -1245,14 +1279,15 @@ extern "C" int spb_ylm_moments(spb_context *ctx, int B, const double *r_deg, con
                                const double *b, const double *c, const double *n, double *mean_ylm,
                                double *cov_ylm, int32_t *info, void *workspace,
                                size_t workspace_bytes, void *stream_) {
-  return spb_ylm_moments_dr(ctx, B, r_deg, nullptr, a, b, c, n, mean_ylm, cov_ylm, info, workspace,
-                            workspace_bytes, stream_);
+  return spb_ylm_moments_dr(ctx, B, r_deg, nullptr, a, b, c, n, nullptr, mean_ylm, cov_ylm, info,
+                            workspace, workspace_bytes, stream_);
 }
 
 extern "C" int spb_ylm_moments_dr(spb_context *ctx, int B, const double *r_deg, const double *dr_deg,
                                   const double *a, const double *b, const double *c, const double *n,
-                                  double *mean_ylm, double *cov_ylm, int32_t *info, void *workspace,
-                                  size_t workspace_bytes, void *stream_) {
+                                  const spb_moments_options *opt, double *mean_ylm, double *cov_ylm,
+                                  int32_t *info, void *workspace, size_t workspace_bytes,
+                                  void *stream_) {
   SPB_REQUIRE(ctx != nullptr && B > 0, "ylm_moments: bad arguments");
   SPB_REQUIRE(ctx->tables_count == SPB_TAB_TOTAL, "ylm_moments: context has no constant tables");
   SPB_REQUIRE(workspace_bytes >= mom_ws_layout(B, nullptr, nullptr) && workspace != nullptr,
@@ -1275,7 +1310,14 @@ extern "C" int spb_ylm_moments_dr(spb_context *ctx, int B, const double *r_deg, 
     if (st) return st;
   }
   SPB_REQUIRE(k1_upload_perm(ctx->device) == 0, "ylm_moments: constant upload failed");
+  const double *Bp, *lambda;
+  double abmin, lam, lbm;
+  resolve_options(ctx, opt, &Bp, &lambda, &abmin, &lam, &lbm);
   K1Params p1;
+  p1.Bp = Bp;
+  p1.abmin = abmin;
+  p1.lam = lam;
+  p1.lbm = lbm;
   p1.r_deg = r_deg;
   p1.dr_deg = dr_deg;
   p1.E2 = ws.E2;
@@ -1295,7 +1337,7 @@ extern "C" int spb_ylm_moments_dr(spb_context *ctx, int B, const double *r_deg, 
   p1.qs = ws.qs;
   moments_k1a<<<B, NT1, sizeof(K1Smem), stream>>>(p1);
   SPB_LAUNCH_CHECK(ctx);
-  return moments_tail(ctx, B, p1, ws, cov_ylm, dr_deg != nullptr, stream);
+  return moments_tail(ctx, B, p1, ws, cov_ylm, dr_deg != nullptr, lambda, stream);
 }
 
 // Workspace of the gradient call: the moments workspace of 7 B samples plus the tangent arrays.
@@ -1324,9 +1366,10 @@ extern "C" size_t spb_ylm_moments_grad_workspace_bytes(const spb_context *ctx, i
 }
 
 extern "C" int spb_ylm_moments_grad(spb_context *ctx, int B, const double *r_deg, const double *a,
-                                    const double *b, const double *c, const double *n, double rel_step,
-                                    double *mean_ylm, double *cov_ylm, double *eps, int32_t *info,
-                                    void *workspace, size_t workspace_bytes, void *stream_) {
+                                    const double *b, const double *c, const double *n,
+                                    const spb_moments_options *opt, double rel_step, double *mean_ylm,
+                                    double *cov_ylm, double *eps, int32_t *info, void *workspace,
+                                    size_t workspace_bytes, void *stream_) {
   SPB_REQUIRE(ctx != nullptr && B > 0 && rel_step > 0.0, "ylm_moments_grad: bad arguments");
   SPB_REQUIRE(ctx->tables_count == SPB_TAB_TOTAL, "ylm_moments_grad: context has no constant tables");
   SPB_REQUIRE(workspace != nullptr && workspace_bytes >= spb_ylm_moments_grad_workspace_bytes(ctx, B),
@@ -1353,7 +1396,14 @@ extern "C" int spb_ylm_moments_grad(spb_context *ctx, int B, const double *r_deg
   }
   SPB_REQUIRE(k1_upload_perm(ctx->device) == 0, "ylm_moments_grad: constant upload failed");
   // base sample: K1a into the first B slots of the 7 B arrays
+  const double *Bp, *lambda;
+  double abmin, lam, lbm;
+  resolve_options(ctx, opt, &Bp, &lambda, &abmin, &lam, &lbm);
   K1Params p1;
+  p1.Bp = Bp;
+  p1.abmin = abmin;
+  p1.lam = lam;
+  p1.lbm = lbm;
   p1.r_deg = r_deg;
   p1.dr_deg = nullptr;
   p1.E2 = ws.E2;
@@ -1374,6 +1424,10 @@ extern "C" int spb_ylm_moments_grad(spb_context *ctx, int B, const double *r_deg
   moments_k1a<<<B, NT1, sizeof(K1Smem), stream>>>(p1);
   SPB_LAUNCH_CHECK(ctx);
   K1TanParams pt;
+  pt.Bp = Bp;
+  pt.abmin = abmin;
+  pt.lam = lam;
+  pt.lbm = lbm;
   pt.r_deg = r_deg;
   pt.a = a;
   pt.b = b;
@@ -1403,10 +1457,9 @@ extern "C" int spb_ylm_moments_grad(spb_context *ctx, int B, const double *r_deg
   SPB_LAUNCH_CHECK(ctx);
   // the unchanged pipeline on the 7 B variants
   p1.B = 7 * B;
-  int st = moments_tail(ctx, 7 * B, p1, ws, cov_ylm, false, stream);
+  int st = moments_tail(ctx, 7 * B, p1, ws, cov_ylm, false, lambda, stream);
   if (st) return st;
-  moments_scale_variants_kernel<<<dim3(B, 4), 256, 0, stream>>>(B, c, n, eps,
-                                                               ctx->d_tables + SPB_TAB_LAMBDA, mean_ylm,
+  moments_scale_variants_kernel<<<dim3(B, 4), 256, 0, stream>>>(B, c, n, eps, lambda, mean_ylm,
                                                                cov_ylm);
   SPB_LAUNCH_CHECK(ctx);
   // flags of the base sample (bounds, eigen-solve) are what the caller sees

@@ -188,15 +188,19 @@ class StarryProcess(object):
             self._temporal_kernel = tk
         self._ydeg = int(kwargs.pop("ydeg", defaults["ydeg"]))
         self._udeg = int(kwargs.pop("udeg", defaults["udeg"]))
-        if self._ydeg != 15:
-            raise NotImplementedError("libspb200 is specialised for ydeg = 15 (constants.h:14-34 bakes "
-                                      "the degree in at compile time in the reference as well)")
+        assert self._ydeg >= 5, "Degree of map must be >= 5."           # sp.py:236
+        if self._ydeg > 15:
+            raise NotImplementedError("libspb200 evaluates spherical-harmonic degrees up to 15 (the "
+                                      "reference is numerically unstable above: joss/paper.md:174-191)")
         if self._udeg not in (0, 2):
             raise NotImplementedError("udeg must be 0 or 2")
-        for key, val in (("epsy", 1e-12), ("epsy15", 1e-9), ("abmin", 1e-12), ("log_alpha_max", 10),
-                         ("log_beta_max", 10)):
-            if kwargs.pop(key, val) != val:
-                raise NotImplementedError("non-default `%s` is not supported" % key)
+        # keyword options the reference threads through its integrals (sp.py:241-262):
+        # contrast.py:26-32 (epsy, epsy15), latitude.py:171-200 (abmin, log_alpha_max, log_beta_max)
+        self._opt_kw = dict(epsy=float(kwargs.pop("epsy", defaults["epsy"])),
+                            epsy15=float(kwargs.pop("epsy15", defaults["epsy15"])),
+                            abmin=float(kwargs.pop("abmin", defaults["abmin"])),
+                            log_alpha_max=float(kwargs.pop("log_alpha_max", defaults["log_alpha_max"])),
+                            log_beta_max=float(kwargs.pop("log_beta_max", defaults["log_beta_max"])))
         self._normN = int(kwargs.pop("normalization_order", defaults["normalization_order"]))
         self._normzmax = float(kwargs.pop("normalization_zmax", defaults["normalization_zmax"]))
         self._max_chunk_bytes = int(kwargs.pop("max_chunk_bytes", 96 << 30))
@@ -210,6 +214,7 @@ class StarryProcess(object):
         self._ctx = get_context(device, kwargs.pop("longitude_basis", None))
         self.device = self._ctx.device
         self._lib = self._ctx.lib
+        self._opt, self._opt_keep = self._moments_options()
 
         params = dict(r=r, c=c, n=n)
         if dr is not None:     # uniform prior on the spot radius over [r - dr, r + dr], size.py:116-125
@@ -274,6 +279,64 @@ class StarryProcess(object):
         self._z = None
         self._rTA1_cache = {}
 
+    def _moments_options(self):
+        """spb_moments_options for non-default keywords / a degree below 15 (None: all defaults).
+        A lower degree is EMBEDDED in the degree-15 machinery: the spot operator ``Bp`` of that degree
+        (size.py:10-43, rows l > ydeg zero) and a jitter vector that vanishes for l > ydeg make every
+        Ylm moment with l > ydeg exactly zero, the rotations are block-diagonal in l, and the
+        leading ``(ydeg+1)^2`` block is the reference's degree-``ydeg`` result."""
+        kw, ydeg = self._opt_kw, self._ydeg
+        default = (ydeg == 15 and kw["epsy"] == defaults["epsy"] and kw["epsy15"] == defaults["epsy15"]
+                   and kw["abmin"] == defaults["abmin"]
+                   and kw["log_alpha_max"] == defaults["log_alpha_max"]
+                   and kw["log_beta_max"] == defaults["log_beta_max"])
+        if default:
+            return None, ()
+        opt = _lib.MomentsOptions()
+        keep = []
+        if ydeg < 15:
+            Bp = np.zeros((16, 1000))
+            Bp[: ydeg + 1] = _tables.spot_operator(ydeg)
+            bp_d = torch.tensor(Bp, dtype=torch.float64, device=self.device).contiguous()
+            keep.append(bp_d)
+            opt.Bp = bp_d.data_ptr()
+        lam = np.zeros(256)
+        lam[: self._nylm] = kw["epsy"]
+        lam[15 ** 2: self._nylm] = kw["epsy15"]        # contrast.py:28-31 (only l = 15 exists there)
+        lam_d = torch.tensor(lam, dtype=torch.float64, device=self.device)
+        keep.append(lam_d)
+        opt.lambda_ = lam_d.data_ptr()
+        opt.abmin, opt.log_alpha_max, opt.log_beta_max = kw["abmin"], kw["log_alpha_max"], kw["log_beta_max"]
+        return opt, tuple(keep)
+
+    def _optp(self):
+        return ctypes.byref(self._opt) if self._opt is not None else None
+
+    @property
+    def ydeg(self):
+        """sp.py:347-350."""
+        return self._ydeg
+
+    def _cut(self, x, dims):
+        """Leading (ydeg+1)^2 block along the given Ylm axes (no-op at degree 15)."""
+        if self._nylm == 256:
+            return x
+        for d in dims:
+            x = x.narrow(d, 0, self._nylm)
+        return x.contiguous()
+
+    def _pad_ylm(self, x, dim):
+        """Zero-pad a Ylm axis of length (ydeg+1)^2 to 256."""
+        if x.shape[dim] == 256:
+            return x
+        if x.shape[dim] != self._nylm:
+            raise ValueError("expected a spherical-harmonic axis of length %d" % self._nylm)
+        shape = list(x.shape)
+        shape[dim] = 256
+        out = torch.zeros(shape, dtype=x.dtype, device=x.device)
+        out.narrow(dim, 0, self._nylm).copy_(x)
+        return out
+
     # ------------------------------------------------------------------ hyperparameters
     @property
     def a(self):
@@ -322,8 +385,9 @@ class StarryProcess(object):
         ``(a, b) -> (mu, sigma)`` transform, ``-inf`` where ``sigma > sigma_max``."""
         out = torch.empty(self._B, dtype=torch.float64, device=self.device)
         with torch.cuda.device(self.device):
-            _lib.check(self._lib.spb_log_jac(self._ctx.handle, self._B, _ptr(self._a), _ptr(self._b),
-                                             self._sigma_max, _ptr(out), _stream()))
+            _lib.check(self._lib.spb_log_jac_opt(self._ctx.handle, self._B, _ptr(self._a),
+                                                 _ptr(self._b), self._sigma_max, self._optp(),
+                                                 _ptr(out), _stream()))
         return self._out(out)
 
     # ------------------------------------------------------------------ Ylm moments
@@ -339,8 +403,8 @@ class StarryProcess(object):
             ev = self._mark("moments")
             _lib.check(self._lib.spb_ylm_moments_dr(
                 self._ctx.handle, B, _ptr(self._r), _ptr(self._dr), _ptr(self._a), _ptr(self._b),
-                _ptr(self._c), _ptr(self._n), _ptr(mean), _ptr(cov), _ptr(self._info), _ptr(ws),
-                nbytes, _stream()))
+                _ptr(self._c), _ptr(self._n), self._optp(), _ptr(mean), _ptr(cov), _ptr(self._info),
+                _ptr(ws), nbytes, _stream()))
             self._mark_end(ev)
             del ws
         self._mean_ylm, self._cov_ylm = mean, cov
@@ -349,13 +413,13 @@ class StarryProcess(object):
     def mean_ylm(self):
         """sp.py:420-426."""
         self._compute_moments()
-        return self._out(self._mean_ylm)
+        return self._out(self._cut(self._mean_ylm, (1,)))
 
     @property
     def cov_ylm(self):
         """sp.py:428-434."""
         self._compute_moments()
-        return self._out(self._cov_ylm)
+        return self._out(self._cut(self._cov_ylm, (1, 2)))
 
     @property
     def cho_cov_ylm(self):
@@ -363,14 +427,19 @@ class StarryProcess(object):
         self._compute_moments()
         if self._cho_cov_ylm is None:
             with torch.cuda.device(self.device):
-                L = torch.empty_like(self._cov_ylm)
+                cov = self._cov_ylm
+                if self._nylm < 256:     # embedded lower degree: unit diagonal on the padded block
+                    cov = cov.clone()
+                    cov[:, self._nylm:, self._nylm:] += torch.eye(256 - self._nylm, dtype=torch.float64,
+                                                                  device=self.device)
+                L = torch.empty_like(cov)
                 info = torch.zeros(self._B, dtype=torch.int32, device=self.device)
-                _lib.check(self._lib.spb_cho_cov_ylm(self._ctx.handle, self._B, _ptr(self._cov_ylm),
+                _lib.check(self._lib.spb_cho_cov_ylm(self._ctx.handle, self._B, _ptr(cov),
                                                      _ptr(L), _ptr(info), _stream()))
                 bad = (info & 1) != 0
                 L = torch.where(bad[:, None, None], torch.full_like(L, float("nan")), L)
             self._cho_cov_ylm = L
-        return self._out(self._cho_cov_ylm)
+        return self._out(self._cut(self._cho_cov_ylm, (1, 2)))
 
     def sample_ylm(self, t=None, nsamples=1, u=None, generator=None):
         """sp.py:489-509 (``t`` must be None: static surfaces).  ``u`` optionally supplies the
@@ -378,23 +447,25 @@ class StarryProcess(object):
         ``random_normal(self.random, (nylm, nsamples))`` or ``(B, nylm, nsamples)``."""
         if t is not None:
             return self._sample_ylm_temporal(t, nsamples, u, generator)
-        L = self.cho_cov_ylm
-        L = L if self._batched else L[None]
-        B = self._B
+        self.cho_cov_ylm
+        L = self._cho_cov_ylm          # (B, 256, 256), padded at degrees below 15
+        B, ny = self._B, self._nylm
         with torch.cuda.device(self.device):
             if u is None:
-                un = torch.randn(B, nsamples, 256, dtype=torch.float64, device=self.device,
-                                 generator=generator)
+                un = torch.zeros(B, nsamples, 256, dtype=torch.float64, device=self.device)
+                un[:, :, :ny] = torch.randn(B, nsamples, ny, dtype=torch.float64, device=self.device,
+                                            generator=generator)
             else:
                 un = torch.as_tensor(u, dtype=torch.float64).to(self.device)
                 nsamples = un.shape[-1]
                 if un.ndim == 2:
-                    un = un[None].expand(B, 256, nsamples)
-                un = un.transpose(1, 2).contiguous()
+                    un = un[None].expand(B, un.shape[0], nsamples)
+                un = self._pad_ylm(un.transpose(1, 2).contiguous(), 2)
             y = torch.empty(B, nsamples, 256, dtype=torch.float64, device=self.device)
             _lib.check(self._lib.spb_sample_ylm(self._ctx.handle, B, nsamples, _ptr(self._mean_ylm),
-                                                _ptr(L.contiguous()), _ptr(un), _ptr(y), _stream()))
-        return self._out(y)
+                                                _ptr(L.contiguous()), _ptr(un.contiguous()), _ptr(y),
+                                                _stream()))
+        return self._out(self._cut(y, (2,)))
 
     # ------------------------------------------------------------------ flux operator / design
     def _u(self, u):
@@ -436,7 +507,12 @@ class StarryProcess(object):
         return it.contiguous()
 
     def design_matrix(self, t, i=defaults["i"], p=defaults["p"], u=None):
-        """flux.py:345-350: ``A (nt, 256)``, or ``(I, nt, 256)`` for a vector of inclinations."""
+        """flux.py:345-350: ``A (nt, nylm)``, or ``(I, nt, nylm)`` for a vector of inclinations."""
+        A = self._cut(self._design_full(t, i, p, u), (2,))
+        return A if _is_batched(i) else A[0]
+
+    def _design_full(self, t, i, p, u):
+        """The degree-15 design matrix ``(I, nt, 256)`` (a lower degree is its leading block)."""
         t = self._t(t)
         inc = self._inc(i)
         _check_bounds("p", p, 0, np.inf)
@@ -450,7 +526,7 @@ class StarryProcess(object):
             _lib.check(self._lib.spb_design_matrix(self._ctx.handle, I, nt, _ptr(t), _ptr(inc),
                                                    _ptr(per), _ptr(rta1), 0, _ptr(A), _ptr(ws),
                                                    nbytes, _stream()))
-        return A if _is_batched(i) else A[0]
+        return A
 
     # ------------------------------------------------------------------ flux mean / covariance
     def _noise_model(self, nt, data_cov, baseline_var, keep, lower_only=False, b0=0):
@@ -749,7 +825,8 @@ class StarryProcess(object):
             ws = torch.empty(nb, dtype=torch.uint8, device=dev)
             ev = self._mark("moments_grad")
             _lib.check(lib.spb_ylm_moments_grad(h, B, _ptr(self._r), _ptr(self._a), _ptr(self._b),
-                                                _ptr(self._c), _ptr(self._n), float(rel_step),
+                                                _ptr(self._c), _ptr(self._n), self._optp(),
+                                                float(rel_step),
                                                 _ptr(mean), _ptr(cov), _ptr(eps), _ptr(info), _ptr(ws),
                                                 nb, _stream()))
             self._mark_end(ev)
@@ -850,11 +927,55 @@ class StarryProcess(object):
                    alpha=1.0, beta=1.0)
         return out
 
+    # ---- batch chunking of the methods that materialise several (nt x nt) arrays per element
+    def _sub(self, b0, b1):
+        """A view of batch elements b0:b1 as a process of its own (moments already computed)."""
+        sub = object.__new__(type(self))
+        sub.__dict__.update(self.__dict__)
+        sub._B, sub._batched = b1 - b0, True
+        for k in ("_r", "_a", "_b", "_c", "_n", "_tau", "_dr", "_mean_ylm", "_cov_ylm", "_info"):
+            v = getattr(self, k, None)
+            setattr(sub, k, None if v is None else v[b0:b1])
+        sub._cho_cov_ylm = None if self._cho_cov_ylm is None else self._cho_cov_ylm[b0:b1]
+        if getattr(self, "_mu_sigma", None) is not None:
+            sub._mu_sigma = (self._mu_sigma[0][b0:b1], self._mu_sigma[1][b0:b1])
+        return sub
+
+    def _chunked(self, method, n1, n2, kwargs,
+                 per_element=("i", "unit_normals", "baseline_mean", "baseline_var")):
+        """Runs ``method`` over batch chunks when the whole batch would not fit ``max_chunk_bytes``
+        (about four (n1 x n2) arrays per element) or one launch (65535 elements: the assembly and
+        GEMM kernels carry the batch in grid.y).  Returns None when no chunking is needed."""
+        per = 4 * n1 * (n2 + (n2 & 1)) * 8 + 4 * 256 * 256 * 8
+        step = max(1, min(self._B, self._max_chunk_bytes // per, 65535))
+        if step >= self._B:
+            return None
+        self._compute_moments()
+        outs = []
+        for b0 in range(0, self._B, step):
+            b1 = min(self._B, b0 + step)
+            kw = dict(kwargs)
+            for k in per_element:
+                v = kw.get(k, None)
+                if isinstance(v, (torch.Tensor, np.ndarray)) and v.ndim >= 1 and v.shape[0] == self._B \
+                        and v.ndim == (3 if k == "unit_normals" else 1):
+                    kw[k] = v[b0:b1]
+            outs.append(getattr(self._sub(b0, b1), method)(**kw))
+        if isinstance(outs[0], tuple):
+            return tuple(torch.cat([o[k] for o in outs]) for k in range(len(outs[0])))
+        return torch.cat(outs)
+
     def sample(self, t, i=defaults["i"], p=defaults["p"], u=None, nsamples=1, eps=defaults["eps"],
                unit_normals=None, generator=None, marginalize_over_inclination=None):
         """sp.py:729-765: draws from the prior over light curves, ``(nsamples, nt)`` (or
         ``(B, nsamples, nt)``).  ``unit_normals`` optionally supplies the reference's
         ``random_normal(self.random, (nt, nsamples))``."""
+        nt_ = int(np.size(t)) if not isinstance(t, torch.Tensor) else t.numel()
+        out = self._chunked("sample", nt_, nt_, dict(
+            t=t, i=i, p=p, u=u, nsamples=nsamples, eps=eps, unit_normals=unit_normals,
+            generator=generator, marginalize_over_inclination=marginalize_over_inclination))
+        if out is not None:
+            return out
         marg, t, inc, rta1 = self._prep(t, i, p, u, marginalize_over_inclination)
         nt = t.numel()
         ldk = nt + (nt & 1)
@@ -887,6 +1008,15 @@ class StarryProcess(object):
         mean)``, and ``mu = mean + V w``, ``K = K(ts, ts) - V V^T`` are two tensor-core GEMMs."""
         if self._normalized:
             raise NotImplementedError("Method not implemented when the flux is normalized.")
+        nt_ = int(np.size(t)) if not isinstance(t, torch.Tensor) else t.numel()
+        ns_ = nt_ if t_sample is None else (
+            int(np.size(t_sample)) if not isinstance(t_sample, torch.Tensor) else t_sample.numel())
+        out = self._chunked("predict", max(nt_, ns_), max(nt_, ns_), dict(
+            t=t, flux=flux, data_cov=data_cov, t_sample=t_sample, i=i, p=p, u=u,
+            baseline_mean=baseline_mean, baseline_var=baseline_var,
+            marginalize_over_inclination=marginalize_over_inclination))
+        if out is not None:
+            return out
         marg, t, inc, rta1 = self._prep(t, i, p, u, marginalize_over_inclination)
         dev, B = self.device, self._B
         nt = t.numel()
@@ -972,6 +1102,16 @@ class StarryProcess(object):
         """sp.py:924-1002: draws ``(nsamples, nts)`` from the conditional light-curve distribution.
         (The reference body reads an undefined name ``ts``; the intended ``ts = t_sample or t`` is
         what is implemented.)"""
+        nt_ = int(np.size(t)) if not isinstance(t, torch.Tensor) else t.numel()
+        ns_ = nt_ if t_sample is None else (
+            int(np.size(t_sample)) if not isinstance(t_sample, torch.Tensor) else t_sample.numel())
+        out = self._chunked("sample_conditional", max(nt_, ns_), max(nt_, ns_), dict(
+            t=t, flux=flux, data_cov=data_cov, t_sample=t_sample, i=i, p=p, u=u,
+            baseline_mean=baseline_mean, baseline_var=baseline_var, nsamples=nsamples, eps=eps,
+            unit_normals=unit_normals, generator=generator,
+            marginalize_over_inclination=marginalize_over_inclination))
+        if out is not None:
+            return out
         mu, K = self.predict(t, flux, data_cov, t_sample=t_sample, i=i, p=p, u=u,
                              baseline_mean=baseline_mean, baseline_var=baseline_var,
                              marginalize_over_inclination=marginalize_over_inclination)
@@ -1005,6 +1145,15 @@ class StarryProcess(object):
             raise NotImplementedError("Method not implemented when the flux is normalized.")
         if self._time_variable:
             raise NotImplementedError("Method not implemented for time-variable maps.")
+        if self._nylm != 256:
+            raise NotImplementedError("sample_ylm_conditional is implemented at ydeg = 15")
+        nt_ = int(np.size(t)) if not isinstance(t, torch.Tensor) else t.numel()
+        out = self._chunked("sample_ylm_conditional", nt_, 256, dict(
+            t=t, flux=flux, data_cov=data_cov, i=i, p=p, u=u, baseline_mean=baseline_mean,
+            baseline_var=baseline_var, nsamples=nsamples, unit_normals=unit_normals,
+            generator=generator))
+        if out is not None:
+            return out
         self._compute_moments()
         dev, B = self.device, self._B
         t = self._t(t)
@@ -1016,8 +1165,7 @@ class StarryProcess(object):
         bm = torch.as_tensor(baseline_mean, dtype=torch.float64).to(dev)
         lib, h = self._lib, self._ctx.handle
         with torch.cuda.device(dev):
-            A = self.design_matrix(t, i, p, u)
-            A = A if A.ndim == 3 else A[None]
+            A = self._design_full(t, i, p, u)
             I = A.shape[0]
             if I not in (1, B):
                 raise ValueError("`i` must be a scalar or have one entry per batch element")
@@ -1088,6 +1236,8 @@ class StarryProcess(object):
         this branch.  ``u`` optionally supplies ``U`` of shape ``(nsamples, nt, nylm)``."""
         if not self._time_variable:
             raise ValueError("sample_ylm(t=...) needs a time-variable process (tau)")
+        if self._nylm != 256:
+            raise NotImplementedError("time-variable sample_ylm is implemented at ydeg = 15")
         t = self._t(t)
         nt = t.numel()
         ldt = nt + (nt & 1)
@@ -1139,9 +1289,10 @@ class StarryProcess(object):
         squeeze = yt.ndim == 1
         if squeeze:
             yt = yt[None]
-        A = self.design_matrix(t, i, p, u)
-        if A.ndim != 2:
+        if _is_batched(i):
             raise ValueError("flux() takes a scalar inclination")
+        A = self._design_full(t, i, p, u)[0]
+        yt = self._pad_ylm(yt, yt.ndim - 1)
         nt = A.shape[0]
         with torch.cuda.device(dev):
             if self._time_variable:
@@ -1192,7 +1343,7 @@ class StarryProcessSum(StarryProcess):
         assert first.device == second.device, "Mismatch in device."
         for k in ("_ydeg", "_udeg", "_nylm", "_normalized", "_marginalize_over_inclination",
                   "_covpts", "_normN", "_normzmax", "_max_chunk_bytes", "_sigma_max", "_ctx",
-                  "device", "_lib"):
+                  "device", "_lib", "_opt", "_opt_keep", "_opt_kw"):
             setattr(self, k, getattr(first, k))
         self._time_variable, self._tkind, self._tau = False, 0, None
         self._children = []

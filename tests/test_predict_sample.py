@@ -199,3 +199,43 @@ def test_gpu_predict_odd_sizes_vs_live_oracle(spb, oracle, golden, marg):
     assert tuple(s1.shape) == (4, nts) and bool(torch.isfinite(s1).all()) and torch.equal(s1, s2)
     s3 = gp.sample(t, nsamples=2, generator=torch.Generator(device="cuda").manual_seed(2), **KW)
     assert tuple(s3.shape) == (2, nt) and bool(torch.isfinite(s3).all())
+
+
+@pytest.mark.gpu
+def test_gpu_sample_predict_chunked_equals_unchunked():
+    """sample / predict / sample_conditional / sample_ylm_conditional split a large batch
+    into chunks (max_chunk_bytes, and at most 65535 elements per launch) like log_likelihood does;
+    chunked and unchunked evaluation agree bit for bit (same kernels per element)."""
+    import torch
+
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import starry_process_b200 as spb
+
+    rng = np.random.default_rng(2)
+    B, nt = 9, 60
+    hp = dict(r=rng.uniform(10, 30, B), mu=rng.uniform(0, 80, B), sigma=rng.uniform(5, 30, B),
+              c=rng.uniform(0.02, 0.12, B), n=rng.uniform(1, 10, B))
+    t = np.linspace(0, 2, nt)
+    ts = np.linspace(0.1, 2.3, 37)
+    f = 1e-3 * rng.standard_normal(nt)
+    un = rng.standard_normal((nt, 3))
+    un_s = rng.standard_normal((37, 2))
+    un_y = rng.standard_normal((256, 2))
+    inc = torch.tensor(rng.uniform(20, 80, B))
+    for marg in (True, False):
+        kw = dict(normalized=False, marginalize_over_inclination=marg, **hp)
+        big = spb.StarryProcess(**kw)
+        small = spb.StarryProcess(max_chunk_bytes=3 << 20, **kw)     # ~ 2 elements per chunk
+        ii = 60.0 if marg else inc
+        a = big.sample(t, i=ii, unit_normals=un)
+        b = small.sample(t, i=ii, unit_normals=un)
+        assert a.shape == (B, 3, nt) and torch.equal(a, b)
+        (m1, K1), (m2, K2) = big.predict(t, f, 1e-6, t_sample=ts, i=ii), small.predict(t, f, 1e-6, t_sample=ts, i=ii)
+        assert torch.equal(m1, m2) and torch.equal(K1, K2)
+        c1 = big.sample_conditional(t, f, 1e-6, t_sample=ts, i=ii, unit_normals=un_s)
+        c2 = small.sample_conditional(t, f, 1e-6, t_sample=ts, i=ii, unit_normals=un_s)
+        assert torch.equal(c1, c2)
+    y1 = big.sample_ylm_conditional(t, f, 1e-6, i=60.0, unit_normals=un_y)
+    y2 = small.sample_ylm_conditional(t, f, 1e-6, i=60.0, unit_normals=un_y)
+    assert y1.shape == (B, 2, 256) and torch.equal(y1, y2)
