@@ -13,6 +13,11 @@ graph-build time, re-organised for the GPU kernels ("constant tab
     ``Rx(pi/2)`` into the 16 quadratic forms ``Omega_m`` used by the marginal-kernel GEMM
   * Gauss-Legendre nodes for the limb-darkened flux operator.
 
+``wigner_poly`` and ``rx_numeric`` are a PORT of the reference's table construction (the same
+recurrences in the same order, wigner.py:192-372 / ops/include/wigner.h:37-284, so that the constant
+tensors come out bit-compatible with the ones the reference builds); every other table is this
+package's own re-organisation.  They run once per process on the host and are not on the hot path.
+
 Only NumPy/SciPy; nothing here touches the GPU.  The packed blob layout is shared with
 ``csrc/spb_tables.h``.
 """
