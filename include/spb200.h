@@ -41,6 +41,7 @@ typedef struct spb_context spb_context;
 #define SPB_INFO_Z_RANGE 2      /* normalised process: z > normalization_zmax (sp.py:1178-1183) */
 #define SPB_INFO_BOUNDS 4       /* hyperparameter outside CheckBoundsOp range (ops/exceptions.py:30-48) */
 #define SPB_INFO_EIG_NOCONV 8   /* latitude eigen-solve did not converge (eigh.py:12-16 -> NaN) */
+#define SPB_INFO_I8_RANGE 16    /* transient: spb_cholesky_lnlike_i8 re-ran this matrix on the DMMA kernel */
 
 const char *spb_last_error(void);
 int spb_version(void);
@@ -272,6 +273,24 @@ int spb_cholesky_lnlike_affine(spb_context *ctx, int B, int nt, double *K, int l
                                long long K_stride, const spb_affine *affine, int M, double *resid,
                                int ldr, long long resid_stride, double *lnlike, double *quad,
                                double *logdet, int32_t *info, void *stream);
+
+/* The same log-likelihood with the panel updates of the factorisation evaluated on the INT8 tensor
+ * cores (tcgen05.mma.kind::i8, accumulators in TMEM) from 7-bit digit planes of L -- an error-free
+ * (Ozaki-style) emulation of the FP64 products: `planes` = 8 carries 56 bits relative to each row's
+ * maximum, i.e. results at the rounding-noise level of the FP64 kernel (7: 49 bits).  Replaces the same
+ * reference lines as spb_cholesky_lnlike_affine (math.py:75-100, sp.py:1154-1188).  Differences:
+ *   K is only READ (the factor is not returned);  `affine` must be given with affine->diag != NULL
+ *   (the data covariance bounds the scale of the right-hand-side rows);  workspace of
+ *   spb_cholesky_i8_workspace_bytes(B, nt, M, planes) bytes (digit planes + row scales);
+ *   matrices whose digits overflow (SPB_INFO_I8_RANGE, never observed) are re-run through the FP64
+ *   kernel, which overwrites THEIR K with L.
+ * resid / lnlike / quad / logdet / info as spb_cholesky_lnlike.                                    */
+size_t spb_cholesky_i8_workspace_bytes(int B, int nt, int M, int planes);
+int spb_cholesky_lnlike_i8(spb_context *ctx, int B, int nt, double *K, int ldk, long long K_stride,
+                           const spb_affine *affine, int M, double *resid, int ldr,
+                           long long resid_stride, double *lnlike, double *quad, double *logdet,
+                           int32_t *info, int planes, void *workspace, size_t workspace_bytes,
+                           void *stream);
 
 /* Forward solve y = L^{-1} r for many right-hand sides against ONE factor, the RHS rows split
  * across the whole GPU (config "1 factorisation + 1024 RHS").  quad: (M) out.               */

@@ -85,7 +85,10 @@ def _compile(nvcc, LIB, objdir, verbose, extra):
 
 
 if __name__ == "__main__":
-    if "--prof" in sys.argv:
+    if "--prof-nomma" in sys.argv:
+        print(build(defines=["SPB_POTRF_PROF", "SPB_I8_NOMMA"], lib=os.path.join(HERE, "libspb200_prof.so"),
+                    verbose="-v" in sys.argv))
+    elif "--prof" in sys.argv:
         print(build(defines=["SPB_POTRF_PROF"], lib=os.path.join(HERE, "libspb200_prof.so"),
                     verbose="-v" in sys.argv))
     else:

@@ -57,6 +57,8 @@ inline int spb_once_per_device(spb_once_flag &f, int device, F &&fn) {
 int spb_encode_tmap_3d_f64(CUtensorMap *out, void *base, unsigned long long d0,
                            unsigned long long d1, unsigned long long d2, unsigned long long s1,
                            unsigned long long s2, unsigned b0, unsigned b1, unsigned b2);
+int spb_encode_tmap_u8_4d(CUtensorMap *out, void *base, const unsigned long long dims[4],
+                          const unsigned long long strides[3], const unsigned box[4]);
 
 #define SPB_CHECK_CUDA(expr)                                                          \
   do {                                                                                \

@@ -141,3 +141,30 @@ int spb_encode_tmap_3d_f64(CUtensorMap *out, void *base, unsigned long long d0,
   SPB_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (alignment / stride constraints)");
   return 0;
 }
+
+// 4-D tensor map of bytes (digit planes of the INT8 Cholesky path), 32-byte swizzle.
+int spb_encode_tmap_u8_4d(CUtensorMap *out, void *base, const unsigned long long dims_[4],
+                          const unsigned long long strides_[3], const unsigned box_[4]) {
+  static spb_encode_fn fn = nullptr;
+  static std::mutex mu;
+  {
+    std::lock_guard<std::mutex> lock(mu);
+    if (!fn) {
+      void *ptr = nullptr;
+      cudaDriverEntryPointQueryResult qres;
+      SPB_CHECK_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres));
+      SPB_REQUIRE(ptr != nullptr && qres == cudaDriverEntryPointSuccess,
+                  "cuTensorMapEncodeTiled is not available in this driver");
+      fn = reinterpret_cast<spb_encode_fn>(ptr);
+    }
+  }
+  cuuint64_t dims[4] = {dims_[0], dims_[1], dims_[2], dims_[3]};
+  cuuint64_t strides[3] = {strides_[0], strides_[1], strides_[2]};
+  cuuint32_t box[4] = {box_[0], box_[1], box_[2], box_[3]};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, base, dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B,
+                  CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  SPB_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (digit planes)");
+  return 0;
+}

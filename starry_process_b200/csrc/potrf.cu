@@ -85,6 +85,7 @@ struct PotrfParams {
   unsigned int *counter;  // zeroed before the launch: work items beyond the first wave are claimed here
   double *scratch;        // cluster kernel: (B, CLUSTER) per-CTA partial sums of |y|^2
   int use_tma;            // operand tiles that lie wholly inside K come through TMA (tensor map of K)
+  int only_flag;          // != 0: only matrices whose info has this bit are processed (the bit is cleared)
   spb_affine aff;    // fused last assembly step (scal == q == diag == offset == NULL: none)
   int aff_on;
 };
@@ -239,8 +240,8 @@ __device__ __forceinline__ double aff_apply(const SM &sm, const AffRow &af, doub
   return k;
 }
 
-template <class SM>
-__device__ __forceinline__ void init_acc(const SM &sm, const RowMap &rm, const AffRow &af, bool aff_on,
+template <class SM, class RM>
+__device__ __forceinline__ void init_acc(const SM &sm, const RM &rm, const AffRow &af, bool aff_on,
                                          int v, int c0, int tg, bool full, double (&accrow)[8][2]) {
   int kind;
   const double *p = rm.row(v, kind);
@@ -870,6 +871,13 @@ __global__ void __launch_bounds__(Geo<TM>::NTHREADS, MIN_CTAS)
   // an SM drift in and out of phase (tensor-pipe phases overlapping or not), so CTA run times for
   // the same number of matrices differ by +-15 %; a static split would wait for the slowest.
   for (int item = blockIdx.x; item < nitems;) {
+    if (p.only_flag && !(p.info[item] & p.only_flag)) {   // block-uniform: skip, claim the next matrix
+      if (tid == 0) sm.next_item = (int)gridDim.x + (int)atomicAdd(p.counter, 1u);
+      __syncthreads();
+      item = sm.next_item;
+      __syncthreads();
+      continue;
+    }
     RowMap rm;
     rm.n = p.n;
     rm.ld = p.ld;
@@ -994,7 +1002,7 @@ __global__ void __launch_bounds__(Geo<TM>::NTHREADS, MIN_CTAS)
       double ll = -0.5 * quad - (double)rm.M * logdet -
                   0.5 * (double)p.n * (double)rm.M * 1.8378770664093453;  // log(2 pi)
       // flags raised by earlier stages (bounds, normalisation range) also map to -inf
-      const int prev = p.info ? (p.info[item] & ~SPB_INFO_NOT_PD) : 0;
+      const int prev = p.info ? (p.info[item] & ~(SPB_INFO_NOT_PD | p.only_flag)) : 0;
       if (bad || (prev & (SPB_INFO_Z_RANGE | SPB_INFO_BOUNDS)) || ll != ll) ll = -INFINITY;
       if (p.lnlike) p.lnlike[item] = ll;
       if (p.logdet) p.logdet[item] = bad ? NAN : logdet;
@@ -1017,6 +1025,8 @@ __global__ void __launch_bounds__(Geo<TM>::NTHREADS, MIN_CTAS)
   }
 #endif
 }
+
+#include "potrf_i8.cuh"
 
 // ------------------------------------------------------------------------------------------
 // Warp-specialised batch kernel: 4 COMPUTE warps (one 64-row tile at a time, 16 rows x 64 columns
@@ -1699,6 +1709,7 @@ extern "C" int spb_cholesky_lnlike(spb_context *ctx, int B, int nt, double *K, i
                                    double *logdet, int32_t *info, void *stream) {
   SPB_REQUIRE(ctx != nullptr, "null context");
   PotrfParams p;
+  p.only_flag = 0;
   p.K = K;
   p.n = nt;
   p.ld = ldk;
@@ -1728,6 +1739,7 @@ extern "C" int spb_cholesky_lnlike_affine(spb_context *ctx, int B, int nt, doubl
   SPB_REQUIRE((affine->scal == nullptr) == (affine->q == nullptr),
               "cholesky_lnlike_affine: scal and q must be given together");
   PotrfParams p;
+  p.only_flag = 0;
   p.K = K;
   p.n = nt;
   p.ld = ldk;
@@ -1748,11 +1760,132 @@ extern "C" int spb_cholesky_lnlike_affine(spb_context *ctx, int B, int nt, doubl
   return potrf_launch(ctx, p, stream);
 }
 
+// ---- INT8-tensor-core path (potrf_i8.cuh) ----------------------------------------------------------
+static inline int i8_n64(int nt) { return (nt + NB - 1) & ~(NB - 1); }
+
+extern "C" size_t spb_cholesky_i8_workspace_bytes(int B, int nt, int M, int planes) {
+  if (B <= 0 || nt <= 0 || M < 0 || planes < 7 || planes > 8) return 0;
+  const size_t NR = (size_t)i8_n64(nt) + (size_t)M, LDQ = (size_t)i8_n64(nt);
+  return (size_t)B * ((size_t)planes * NR * LDQ + NR * sizeof(double)) + 1024;
+}
+
+extern "C" int spb_cholesky_lnlike_i8(spb_context *ctx, int B, int nt, double *K, int ldk,
+                                      long long K_stride, const spb_affine *affine, int M,
+                                      double *resid, int ldr, long long resid_stride, double *lnlike,
+                                      double *quad, double *logdet, int32_t *info, int planes,
+                                      void *workspace, size_t workspace_bytes, void *stream) {
+  SPB_REQUIRE(ctx != nullptr && affine != nullptr, "cholesky_lnlike_i8: null argument");
+  SPB_REQUIRE(affine->diag != nullptr, "cholesky_lnlike_i8: affine->diag (data covariance) is required");
+  SPB_REQUIRE((affine->scal == nullptr) == (affine->q == nullptr),
+              "cholesky_lnlike_i8: scal and q must be given together");
+  SPB_REQUIRE(planes == 7 || planes == 8, "cholesky_lnlike_i8: planes must be 7 or 8");
+  SPB_REQUIRE(info != nullptr, "cholesky_lnlike_i8: info is required");
+  SPB_REQUIRE(nt > NB && nt <= NB * I8_MAXP, "cholesky_lnlike_i8: nt out of range (64 < nt <= 16384)");
+  SPB_REQUIRE(workspace != nullptr && workspace_bytes >= spb_cholesky_i8_workspace_bytes(B, nt, M, planes),
+              "cholesky_lnlike_i8: workspace too small");
+  PotrfParams p;
+  p.only_flag = 0;
+  p.K = K;
+  p.n = nt;
+  p.ld = ldk;
+  p.strideK = K_stride;
+  p.R = (M > 0) ? resid : nullptr;
+  p.M = M;
+  p.ldr = ldr;
+  p.strideR = resid_stride;
+  p.lnlike = lnlike;
+  p.quad = quad;
+  p.logdet = logdet;
+  p.info = info;
+  p.B = B;
+  p.mode = MODE_FACTOR;
+  p.rows_per_cta = 0;
+  p.aff = *affine;
+  p.aff_on = 1;
+  p.scratch = nullptr;
+  p.use_tma = 0;
+  SPB_REQUIRE(p.n > 0 && p.B > 0, "cholesky: empty problem");
+  SPB_REQUIRE(p.ld >= p.n && (p.ld % 2) == 0, "cholesky: ldk must be even and >= nt");
+  SPB_REQUIRE(((uintptr_t)p.K % 16) == 0 && (p.strideK % 2) == 0,
+              "cholesky: K must be 16-byte aligned with an even batch stride");
+  if (p.R) {
+    SPB_REQUIRE(p.ldr >= p.n && (p.ldr % 2) == 0, "cholesky: ldr must be even and >= nt");
+    SPB_REQUIRE(((uintptr_t)p.R % 16) == 0 && (p.strideR % 2) == 0,
+                "cholesky: resid must be 16-byte aligned with an even batch stride");
+  }
+  SPB_CHECK_CUDA(cudaSetDevice(ctx->device));
+  I8Params ip;
+  const int n64 = i8_n64(nt);
+  ip.NR = n64 + M;
+  ip.LDQ = n64;
+  ip.store_factor = 0;
+  uintptr_t w = ((uintptr_t)workspace + 255) & ~(uintptr_t)255;
+  ip.Q = reinterpret_cast<uint8_t *>(w);
+  ip.strideQ = (long long)planes * ip.NR * ip.LDQ;
+  ip.E = reinterpret_cast<double *>((w + (size_t)B * ip.strideQ + 255) & ~(uintptr_t)255);
+  SPB_REQUIRE((uintptr_t)(ip.E + (size_t)B * ip.NR) <= (uintptr_t)workspace + workspace_bytes,
+              "cholesky_lnlike_i8: workspace too small");
+  CUtensorMap tmA, tmB;
+  memset(&tmA, 0, sizeof(tmA));
+  memset(&tmB, 0, sizeof(tmB));
+  {
+    const unsigned long long dims[4] = {(unsigned long long)ip.LDQ, (unsigned long long)ip.NR,
+                                        (unsigned long long)planes, (unsigned long long)B};
+    const unsigned long long strides[3] = {(unsigned long long)ip.LDQ,
+                                           (unsigned long long)ip.LDQ * ip.NR,
+                                           (unsigned long long)ip.strideQ};
+    const unsigned boxA[4] = {I8_KCH, I8_TM, (unsigned)planes, 1};
+    const unsigned boxB[4] = {I8_KCH, NB, (unsigned)planes, 1};
+    int st = spb_encode_tmap_u8_4d(&tmA, ip.Q, dims, strides, boxA);
+    if (st) return st;
+    st = spb_encode_tmap_u8_4d(&tmB, ip.Q, dims, strides, boxB);
+    if (st) return st;
+  }
+  static spb_once_flag attr_once;
+  {
+    const int st = spb_once_per_device(attr_once, ctx->device, [&]() -> int {
+      SPB_CHECK_CUDA(cudaFuncSetAttribute(potrf_i8_kernel<8, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)sizeof(SmemI8<8, 3>)));
+      SPB_CHECK_CUDA(cudaFuncSetAttribute(potrf_i8_kernel<7, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)sizeof(SmemI8<7, 3>)));
+      SPB_CHECK_CUDA(cudaFuncSetAttribute(potrf_lnlike_kernel<128, 3, 2>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)sizeof(Smem<128, 3>)));
+      return 0;
+    });
+    if (st) return st;
+  }
+  const int grid = B < ctx->num_sms ? B : ctx->num_sms;
+  p.counter = ctx->d_counters +
+      (__atomic_fetch_add(&ctx->counter_next, 1u, __ATOMIC_RELAXED) % SPB_NUM_COUNTERS);
+  SPB_CHECK_CUDA(cudaMemsetAsync(p.counter, 0, sizeof(unsigned int), (cudaStream_t)stream));
+  if (planes == 8)
+    potrf_i8_kernel<8, 3><<<grid, I8_NTHREADS, sizeof(SmemI8<8, 3>), (cudaStream_t)stream>>>(p, ip, tmA, tmB);
+  else
+    potrf_i8_kernel<7, 3><<<grid, I8_NTHREADS, sizeof(SmemI8<7, 3>), (cudaStream_t)stream>>>(p, ip, tmA, tmB);
+  SPB_LAUNCH_CHECK(ctx);
+  // safety net: matrices flagged SPB_INFO_I8_RANGE go through the FP64 kernel (their K is intact)
+  {
+    PotrfParams f = p;
+    f.only_flag = SPB_INFO_I8_RANGE;
+    f.counter = ctx->d_counters +
+        (__atomic_fetch_add(&ctx->counter_next, 1u, __ATOMIC_RELAXED) % SPB_NUM_COUNTERS);
+    SPB_CHECK_CUDA(cudaMemsetAsync(f.counter, 0, sizeof(unsigned int), (cudaStream_t)stream));
+    CUtensorMap tmK;
+    memset(&tmK, 0, sizeof(tmK));
+    const int g2 = B < 2 * ctx->num_sms ? B : 2 * ctx->num_sms;
+    potrf_lnlike_kernel<128, 3, 2><<<g2, Geo<128>::NTHREADS, sizeof(Smem<128, 3>), (cudaStream_t)stream>>>(f, tmK);
+    SPB_LAUNCH_CHECK(ctx);
+  }
+  return 0;
+}
+
 extern "C" int spb_cholesky_solve_rows(spb_context *ctx, int nt, const double *L, int ldk, int M,
                                        double *resid, int ldr, double *quad, void *stream) {
   SPB_REQUIRE(ctx != nullptr, "null context");
   SPB_REQUIRE(M > 0 && resid != nullptr, "solve_rows: no right-hand sides");
   PotrfParams p;
+  p.only_flag = 0;
   p.K = const_cast<double *>(L);
   p.n = nt;
   p.ld = ldk;

@@ -64,9 +64,18 @@ class _Context(object):
             _lib.check(self.lib.spb_create(device, blob.ctypes.data_as(ctypes.c_void_p), blob.size,
                                            ctypes.byref(h)))
         self.handle = h
+        # digit planes of the INT8-tensor-core Cholesky (spb_cholesky_lnlike_i8): 0 = FP64 (DMMA) kernel
+        self.cholesky_i8 = int(os.environ.get("SPB200_CHOLESKY_I8", "0"))
 
     def set_option(self, name, value):
-        """Run-time switches of the library (include/spb200.h: spb_set_option)."""
+        """Run-time switches of the library (include/spb200.h: spb_set_option), plus
+        ``"cholesky_i8"`` (0 | 7 | 8): batched ``log_likelihood`` factorises on the INT8 tensor cores
+        with that many 7-bit digit planes (``spb_cholesky_lnlike_i8``)."""
+        if name == "cholesky_i8":
+            if int(value) not in (0, 7, 8):
+                raise ValueError("cholesky_i8 must be 0, 7 or 8")
+            self.cholesky_i8 = int(value)
+            return
         _lib.check(self.lib.spb_set_option(self.handle, name.encode(), int(value)))
 
     def launches(self):
@@ -656,6 +665,8 @@ class StarryProcess(object):
         # B200 has 180 GB), of equal size: the Cholesky kernel claims matrices dynamically, so one
         # long launch has a shorter tail than several short ones
         per = nt * ldk * 8 + 4 * 256 * 256 * 8
+        if self._ctx.cholesky_i8:   # digit planes of the INT8 path live next to K
+            per += self._ctx.cholesky_i8 * (nt + 64) * (nt + 64)
         # (the assembly / GEMM kernels carry the batch in grid.y: at most 65535 elements a launch)
         step = max(1, min(self._B, self._max_chunk_bytes // per, 65535))
         nchunks = -(-self._B // step)
@@ -777,6 +788,15 @@ class StarryProcess(object):
                     ll = -0.5 * quad.sum() - M * logdet[0] - 0.5 * nt * M * math.log(2 * math.pi)
                     flagged = (self._info[b0:b1] != 0) | torch.isnan(ll)
                     lnlike[b0:b1] = torch.where(flagged, torch.full_like(ll, -float("inf")), ll)
+                elif affine is not None and self._ctx.cholesky_i8 and affine.diag and nt > 64:
+                    planes = self._ctx.cholesky_i8
+                    nb_i8 = lib.spb_cholesky_i8_workspace_bytes(Bc, nt, M, planes)
+                    ws_i8 = torch.empty(nb_i8, dtype=torch.uint8, device=dev)
+                    _lib.check(lib.spb_cholesky_lnlike_i8(
+                        h, Bc, nt, _ptr(K), ldk, nt * ldk, ctypes.byref(affine), M, _ptr(resid), ldk,
+                        M * ldk, _ptr(lnlike[b0:b1]), None, None, _ptr(self._info[b0:b1]), planes,
+                        _ptr(ws_i8), nb_i8, _stream()))
+                    del ws_i8
                 elif affine is not None:
                     _lib.check(lib.spb_cholesky_lnlike_affine(
                         h, Bc, nt, _ptr(K), ldk, nt * ldk, ctypes.byref(affine), M, _ptr(resid), ldk,
