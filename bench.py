@@ -482,41 +482,115 @@ def long_baseline_phase(spb, dev, torch, dmma_peak, B=512, reps=2):
     td, fd = torch.tensor(lb["t"], device=dev), torch.tensor(lb["flux"], device=dev)
     bvar = torch.zeros(B, dtype=torch.float64, device=dev)
     bvar[:ns] = torch.tensor(r2["baseline_var"], device=dev)
-    stage = {}
-    times = []
-    ll = None
-    for r in range(reps + 1):
-        gp = spb.StarryProcess(marginalize_over_inclination=False, normalized=False, **hd)
-        if r >= 1:
-            gp._stage_ms = stage
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        ll = gp.log_likelihood(td, fd, 1e-6, i=60.0, p=1.0, u=U_LD, baseline_var=bvar)
-        e1.record()
-        torch.cuda.synchronize()
-        if r >= 1:
-            times.append(e0.elapsed_time(e1))
-        del gp
-    ms = float(np.mean(times))
-    chol_ms = _event_ms(stage.get("cholesky", [])) / reps
-    flops = B * (nt ** 3 / 3.0 + nt ** 2 * 1.0)
-    flops_all = flops + B * (2.0 * nt * 256 * 256 + 1.0 * nt * nt * 256)
-    got = ll[:ns].cpu().numpy()
+    ctx = spb.get_context()
     ref = r2["lnlike_n0"]
     fin = np.isfinite(ref)
-    return {"workload": "configs[3]: 512 hyperparameter samples x 1 light curve of nt = 4096, "
-                        "u=[0.4,0.26], conditional on i = 60 deg, unnormalised (one element non-PD by "
-                        "construction); K = 134 MB per sample (68.7 GB for the batch, one chunk)",
-            "value": B / (ms * 1e-3), "unit": "evals/s", "ms_per_call": ms,
-            "algorithmic_tflops_whole_call": flops_all / (ms * 1e-3) / 1e12,
-            "roofline": {"bound": "tensor", "kernel": "potrf_lnlike_kernel (nt = 4096)",
-                         "achieved": flops / (chol_ms * 1e-3) / 1e12, "peak": dmma_peak,
-                         "unit": "TFLOP/s", "frac": flops / (chol_ms * 1e-3) / 1e12 / dmma_peak,
-                         "ms_per_launch": chol_ms, "algorithmic_flops_per_launch": flops},
-            "parity_vs_reference_golden": {
-                "max_rel": float(np.max(np.abs(got[fin] - ref[fin]) / np.abs(ref[fin]))), "n": int(ns),
-                "neg_inf_pattern_equal": bool(np.array_equal(np.isneginf(got), np.isneginf(ref))),
-                "tolerance": 1e-8}}
+    flops = B * (nt ** 3 / 3.0 + nt ** 2 * 1.0)
+    flops_all = flops + B * (2.0 * nt * 256 * 256 + 1.0 * nt * nt * 256)
+
+    def run(planes):
+        """planes: -1 = the library's automatic choice (INT8 tensor cores, 8 digit planes, at this size),
+        0 = the FP64 (DMMA) kernel."""
+        saved = ctx.cholesky_i8
+        ctx.set_option("cholesky_i8", planes)
+        try:
+            stage, times, ll = {}, [], None
+            for r in range(reps + 1):
+                gp = spb.StarryProcess(marginalize_over_inclination=False, normalized=False, **hd)
+                if r >= 1:
+                    gp._stage_ms = stage
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                ll = gp.log_likelihood(td, fd, 1e-6, i=60.0, p=1.0, u=U_LD, baseline_var=bvar)
+                e1.record()
+                torch.cuda.synchronize()
+                if r >= 1:
+                    times.append(e0.elapsed_time(e1))
+                del gp
+            used = ctx.i8_planes(nt, B)
+        finally:
+            ctx.set_option("cholesky_i8", saved)
+        ms = float(np.mean(times))
+        chol_ms = _event_ms(stage.get("cholesky", [])) / reps
+        got = ll[:ns].cpu().numpy()
+        return {"value": B / (ms * 1e-3), "unit": "evals/s", "ms_per_call": ms,
+                "algorithmic_tflops_whole_call": flops_all / (ms * 1e-3) / 1e12,
+                "cholesky_kernel": ("potrf_i8_kernel: INT8 tensor cores (tcgen05 + TMEM), %d digit planes" % used)
+                if used else "potrf_lnlike_kernel: FP64 tensor cores (DMMA)",
+                "roofline": {"bound": "tensor", "kernel": "potrf_i8_kernel (nt = 4096)" if used
+                             else "potrf_lnlike_kernel (nt = 4096)",
+                             "achieved": flops / (chol_ms * 1e-3) / 1e12, "peak": dmma_peak,
+                             "peak_is": "measured FP64 DMMA peak (the INT8 path emulates the FP64 products "
+                                        "exactly, so FP64-equivalent throughput can exceed it)",
+                             "unit": "TFLOP/s (FP64-equivalent)",
+                             "frac": flops / (chol_ms * 1e-3) / 1e12 / dmma_peak,
+                             "ms_per_launch": chol_ms, "algorithmic_flops_per_launch": flops},
+                "parity_vs_reference_golden": {
+                    "max_rel": float(np.max(np.abs(got[fin] - ref[fin]) / np.abs(ref[fin]))), "n": int(ns),
+                    "neg_inf_pattern_equal": bool(np.array_equal(np.isneginf(got), np.isneginf(ref))),
+                    "tolerance": 1e-8}}
+
+    out = run(-1)
+    out["workload"] = ("configs[3]: 512 hyperparameter samples x 1 light curve of nt = 4096, "
+                       "u=[0.4,0.26], conditional on i = 60 deg, unnormalised (one element non-PD by "
+                       "construction); K = 134 MB per sample (68.7 GB for the batch)")
+    fp64 = run(0)
+    out["fp64_kernel"] = {k: fp64[k] for k in ("value", "ms_per_call", "cholesky_kernel", "roofline",
+                                               "parity_vs_reference_golden")}
+    return out
+
+
+def int8_cholesky_phase(spb, dev, torch, dmma_peak, B=4096, reps=3):
+    """The headline workload (configs[2], nt = 1000) with the factorisation on the INT8 tensor cores
+    (opt-in at this size: the automatic choice starts at nt = 1200): stage time, FP64-equivalent rate and
+    agreement with the FP64 kernel / the reference golden for 8 and 7 digit planes."""
+    hp, t, flux, _ = synthetic_inputs(B, seed=1234, prior="narrow")
+    hd = {k: torch.tensor(v, device=dev) for k, v in hp.items()}
+    td, fd = torch.tensor(t, device=dev), torch.tensor(flux, device=dev)
+    ctx = spb.get_context()
+    saved = ctx.cholesky_i8
+    gpath = os.path.join(ROOT, "tests", "golden", "bench_sweep_seed1234.npz")
+    ref = np.load(gpath)["lnlike_m1_n1"] if os.path.exists(gpath) else None
+    flops = B * (NT ** 3 / 3.0 + NT ** 2 * 1.0)
+    out, base = {}, None
+    try:
+        for planes in (0, 8, 7):
+            ctx.set_option("cholesky_i8", planes)
+            stage, times, ll = {}, [], None
+            for r in range(reps + 1):
+                gp = spb.StarryProcess(**hd)
+                if r >= 1:
+                    gp._stage_ms = stage
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                ll = gp.log_likelihood(td, fd, 1e-6, p=1.0, u=U_LD)
+                e1.record()
+                torch.cuda.synchronize()
+                if r >= 1:
+                    times.append(e0.elapsed_time(e1))
+            got = ll.cpu().numpy()
+            chol_ms = _event_ms(stage.get("cholesky", [])) / reps
+            ent = {"ms_per_step": float(np.mean(times)), "evals_per_s": B / (float(np.mean(times)) * 1e-3),
+                   "cholesky_ms": chol_ms,
+                   "cholesky_fp64_equivalent_tflops": flops / (chol_ms * 1e-3) / 1e12,
+                   "frac_of_dmma_peak": flops / (chol_ms * 1e-3) / 1e12 / dmma_peak}
+            if planes == 0:
+                base = got
+            else:
+                fin = np.isfinite(base)
+                ent["max_rel_lnlike_diff_vs_fp64_kernel"] = float(
+                    np.max(np.abs(got[fin] - base[fin]) / np.abs(base[fin])))
+                ent["neg_inf_pattern_equal"] = bool(np.array_equal(np.isfinite(got), fin))
+            if ref is not None:
+                k = len(ref)
+                f2 = np.isfinite(ref)
+                ent["max_rel_vs_reference_golden"] = float(
+                    np.max(np.abs(got[:k][f2] - ref[f2]) / np.abs(ref[f2])))
+            out["fp64_dmma" if planes == 0 else "int8_%d_planes" % planes] = ent
+    finally:
+        ctx.set_option("cholesky_i8", saved)
+    out["workload"] = "configs[2] (the headline workload), Cholesky kernel switched with cholesky_i8 = 0 | 8 | 7"
+    return out
 
 
 def full_prior_phase(spb, dev, torch, B=4096, reps=3):
@@ -772,6 +846,7 @@ def run_b200(args):
             guarded("ensemble_1024", lambda: ensemble_phase(spb, dev, torch, dmma_peak))
             guarded("full_prior", lambda: full_prior_phase(spb, dev, torch))
             guarded("long_baseline_nt4096", lambda: long_baseline_phase(spb, dev, torch, dmma_peak))
+            guarded("int8_cholesky_nt1000", lambda: int8_cholesky_phase(spb, dev, torch, dmma_peak))
     if args.workload == "sweep":
         llall = ll.cpu().numpy()
         # the first samples evaluated by the UNMODIFIED reference in the build container

@@ -279,8 +279,9 @@ int spb_cholesky_lnlike_affine(spb_context *ctx, int B, int nt, double *K, int l
  * (Ozaki-style) emulation of the FP64 products: `planes` = 8 carries 56 bits relative to each row's
  * maximum, i.e. results at the rounding-noise level of the FP64 kernel (7: 49 bits).  Replaces the same
  * reference lines as spb_cholesky_lnlike_affine (math.py:75-100, sp.py:1154-1188).  Differences:
- *   K is only READ (the factor is not returned);  `affine` must be given with affine->diag != NULL
- *   (the data covariance bounds the scale of the right-hand-side rows);  workspace of
+ *   K is only READ (the factor is not returned);  a lower bound of the smallest eigenvalue of K' is
+ *   needed to scale the right-hand-side rows: `lambda_min` > 0 (e.g. the white-noise variance already
+ *   added to K), or, when lambda_min <= 0, min(affine->diag) (`affine` may be NULL otherwise);  workspace of
  *   spb_cholesky_i8_workspace_bytes(B, nt, M, planes) bytes (digit planes + row scales);
  *   matrices whose digits overflow (SPB_INFO_I8_RANGE, never observed) are re-run through the FP64
  *   kernel, which overwrites THEIR K with L.
@@ -289,8 +290,8 @@ size_t spb_cholesky_i8_workspace_bytes(int B, int nt, int M, int planes);
 int spb_cholesky_lnlike_i8(spb_context *ctx, int B, int nt, double *K, int ldk, long long K_stride,
                            const spb_affine *affine, int M, double *resid, int ldr,
                            long long resid_stride, double *lnlike, double *quad, double *logdet,
-                           int32_t *info, int planes, void *workspace, size_t workspace_bytes,
-                           void *stream);
+                           int32_t *info, int planes, double lambda_min, void *workspace,
+                           size_t workspace_bytes, void *stream);
 
 /* Forward solve y = L^{-1} r for many right-hand sides against ONE factor, the RHS rows split
  * across the whole GPU (config "1 factorisation + 1024 RHS").  quad: (M) out.               */

@@ -1,0 +1,37 @@
+"""configs[3] shape (nt = 4096, conditional, limb-darkened) with the Cholesky on the FP64 (DMMA) kernel and on
+the INT8 tensor cores: lnlike agreement and stage times."""
+import os, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np, torch
+import starry_process_b200 as spb
+import bench
+ctx = spb.get_context()
+dev = torch.device("cuda")
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 148
+nt = int(sys.argv[2]) if len(sys.argv) > 2 else 4096
+hp, _, _, _ = bench.synthetic_inputs(B, 1234, "narrow")
+hd = {k: torch.as_tensor(v, dtype=torch.float64, device=dev) for k, v in hp.items()}
+rng = np.random.default_rng(5)
+t = np.linspace(0, 16.0, nt)
+flux = 1e-3 * rng.standard_normal(nt) + 2e-3 * np.sin(2 * np.pi * t)
+td = torch.as_tensor(t, device=dev); fd = torch.as_tensor(flux, device=dev)
+res = {}
+for planes in (0, 8, 7):
+    ctx.set_option("cholesky_i8", planes)
+    best = None
+    for rep in range(3):
+        gp = spb.StarryProcess(marginalize_over_inclination=False, normalized=True, **hd)
+        gp._stage_ms = {}
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        ll = gp.log_likelihood(td, fd, 1e-6, i=60.0, p=1.0, u=bench.U_LD)
+        torch.cuda.synchronize(); ms = (time.perf_counter() - t0) * 1e3
+        st = {k: sum(a.elapsed_time(b) for a, b in v) for k, v in gp._stage_ms.items()}
+        if best is None or ms < best[0]: best = (ms, st)
+    res[planes] = ll.cpu().numpy()
+    print("B %d nt %d planes %d: %.1f ms, stages %s" % (B, nt, planes, best[0], {k: round(v, 1) for k, v in best[1].items()}), flush=True)
+fin = np.isfinite(res[0])
+for planes in (8, 7):
+    print("  planes %d: max rel lnlike diff vs FP64 kernel %.2e, -inf pattern equal %s" % (
+        planes, np.max(np.abs(res[planes][fin] - res[0][fin]) / np.abs(res[0][fin])), np.array_equal(np.isfinite(res[planes]), fin)))
+ctx.set_option("cholesky_i8", -1)

@@ -46,7 +46,7 @@ def capi_case(ctx, B, n, M, planes, seed=0, dg=1e-4):
             ws = torch.empty(nb, dtype=torch.uint8, device=dev)
             _lib.check(lib.spb_cholesky_lnlike_i8(h, B, n, _ptr(Kc), ld, n * ld, ctypes.byref(af), M,
                                                   _ptr(rc), ld, max(M, 1) * ld, _ptr(ll), _ptr(quad),
-                                                  _ptr(logdet), _ptr(info), planes, _ptr(ws), nb, _stream()))
+                                                  _ptr(logdet), _ptr(info), planes, 0.0, _ptr(ws), nb, _stream()))
         torch.cuda.synchronize()
         out[name] = (ll.cpu(), quad.cpu(), logdet.cpu(), info.cpu(), rc.cpu())
     a, b = out["f64"], out["i8"]
@@ -105,7 +105,7 @@ def main():
                 ts.append((time.perf_counter() - t0) * 1e3)
                 st = {k: sum(a.elapsed_time(b) for a, b in v) for k, v in gp._stage_ms.items()}
             print("  B %d planes %d: step %.2f ms (best of 4), stages %s" % (B, planes, min(ts), {k: round(v, 2) for k, v in st.items()}), flush=True)
-    ctx.set_option("cholesky_i8", 0)
+    ctx.set_option("cholesky_i8", -1)
 
 
 if __name__ == "__main__":

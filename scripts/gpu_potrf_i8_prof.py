@@ -34,7 +34,7 @@ def run(B, n, M=1, planes=8):
         e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
         e0.record()
         _lib.check(lib.spb_cholesky_lnlike_i8(ctx, B, n, P(K), ld, n * ld, ctypes.byref(af), M, P(Rc), ld, max(M, 1) * ld,
-                                              P(ll), None, None, P(info), planes, P(ws), nb, None))
+                                              P(ll), None, None, P(info), planes, 0.0, P(ws), nb, None))
         e1.record(); torch.cuda.synchronize()
         ms = e0.elapsed_time(e1)
         lib.spb_potrf_prof(out)

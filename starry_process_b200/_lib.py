@@ -81,7 +81,7 @@ PROTOTYPES = {
     "spb_assemble_workspace_layout": (None, [_I, _I, _P, _c.POINTER(_P), _c.POINTER(_P)]),
     "spb_cholesky_i8_workspace_bytes": (_SZ, [_I, _I, _I, _I]),
     "spb_cholesky_lnlike_i8": (_I, [_P, _I, _I, _P, _I, _LL, _c.POINTER(Affine), _I, _P, _I, _LL,
-                                    _P, _P, _P, _P, _I, _P, _SZ, _P]),
+                                    _P, _P, _P, _P, _I, _D, _P, _SZ, _P]),
     "spb_cholesky_solve_rows": (_I, [_P, _I, _P, _I, _I, _P, _I, _P, _P]),
     "spb_temporal_scale": (_I, [_P, _I, _I, _I, _P, _P, _I, _P, _LL, _P, _LL, _P, _I, _LL, _P]),
     "spb_gemm_nt": (_I, [_P, _I, _I, _I, _I, _D, _P, _I, _LL, _P, _I, _LL, _D, _P, _I, _LL, _P]),

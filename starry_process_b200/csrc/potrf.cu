@@ -1773,10 +1773,12 @@ extern "C" int spb_cholesky_lnlike_i8(spb_context *ctx, int B, int nt, double *K
                                       long long K_stride, const spb_affine *affine, int M,
                                       double *resid, int ldr, long long resid_stride, double *lnlike,
                                       double *quad, double *logdet, int32_t *info, int planes,
-                                      void *workspace, size_t workspace_bytes, void *stream) {
-  SPB_REQUIRE(ctx != nullptr && affine != nullptr, "cholesky_lnlike_i8: null argument");
-  SPB_REQUIRE(affine->diag != nullptr, "cholesky_lnlike_i8: affine->diag (data covariance) is required");
-  SPB_REQUIRE((affine->scal == nullptr) == (affine->q == nullptr),
+                                      double lambda_min, void *workspace, size_t workspace_bytes,
+                                      void *stream) {
+  SPB_REQUIRE(ctx != nullptr, "cholesky_lnlike_i8: null context");
+  SPB_REQUIRE(lambda_min > 0.0 || (affine != nullptr && affine->diag != nullptr),
+              "cholesky_lnlike_i8: lambda_min > 0 or affine->diag (data covariance) is required");
+  SPB_REQUIRE(affine == nullptr || (affine->scal == nullptr) == (affine->q == nullptr),
               "cholesky_lnlike_i8: scal and q must be given together");
   SPB_REQUIRE(planes == 7 || planes == 8, "cholesky_lnlike_i8: planes must be 7 or 8");
   SPB_REQUIRE(info != nullptr, "cholesky_lnlike_i8: info is required");
@@ -1800,8 +1802,8 @@ extern "C" int spb_cholesky_lnlike_i8(spb_context *ctx, int B, int nt, double *K
   p.B = B;
   p.mode = MODE_FACTOR;
   p.rows_per_cta = 0;
-  p.aff = *affine;
-  p.aff_on = 1;
+  p.aff = affine ? *affine : spb_affine{};
+  p.aff_on = affine ? 1 : 0;
   p.scratch = nullptr;
   p.use_tma = 0;
   SPB_REQUIRE(p.n > 0 && p.B > 0, "cholesky: empty problem");
@@ -1819,6 +1821,11 @@ extern "C" int spb_cholesky_lnlike_i8(spb_context *ctx, int B, int nt, double *K
   ip.NR = n64 + M;
   ip.LDQ = n64;
   ip.store_factor = 0;
+  ip.lambda_min = lambda_min;
+  {
+    const char *e = getenv("SPB_I8_GATE");
+    ip.gate = e ? atoi(e) : 0;   // experiments only (bit 0: hold the MMA stream back during potf2 / TRSM)
+  }
   uintptr_t w = ((uintptr_t)workspace + 255) & ~(uintptr_t)255;
   ip.Q = reinterpret_cast<uint8_t *>(w);
   ip.strideQ = (long long)planes * ip.NR * ip.LDQ;

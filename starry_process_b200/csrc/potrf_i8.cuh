@@ -55,16 +55,22 @@ struct I8Params {
   long long strideQ;     // bytes per matrix
   int NR, LDQ;
   int store_factor;      // also write L (fp64) over K like the DMMA kernel
+  double lambda_min;     // > 0: lower bound of the smallest eigenvalue of K' (else min(aff.diag))
+  int gate;              // pause the MMA stream while warps are in the shuffle / shared-memory bound phases
 };
 
-// Virtual rows of a panel for this kernel: the matrix is treated as n64 = round_up(nt, 64) rows (the
-// rows nt .. n64 - 1 do not exist: KIND_NONE, and KIND_PAD inside the last diagonal block), the
-// right-hand sides follow at virtual row NB + nb64 + m.  With the digit planes laid out as
-// [nt matrix rows | n64 - nt unused rows | M right-hand-side rows], virtual row v of the panel at column
-// c0 is plane row c0 + v for every panel, so a tile's A operand is ONE box of 128 consecutive plane rows.
+// Virtual rows of a panel for this kernel.  A tile's A operand must be ONE box of 128 consecutive plane
+// rows, i.e. virtual row v of the panel at column c0 has to be plane row c0 + v; the last panel of a
+// matrix whose size is not a multiple of 64 (identity-padded diagonal block, right-hand sides at virtual
+// row 64 + m) fixes the plane rows of the right-hand sides at n64 + m, n64 = round_up(nt, 64).  Two layouts:
+//   * "gap" (M <= n64 - nt, the bench case): the right-hand-side planes are kept TWICE, at rows nt + m
+//     (inside the unused gap nt .. n64 - 1, read by the full panels, where they follow the last matrix row
+//     exactly as in the FP64 kernel: no extra tile) and at rows n64 + m (read by the last panel);
+//   * otherwise: once, at n64 + m, and every panel carries the n64 - nt unused rows as KIND_NONE rows
+//     between the matrix rows and the right-hand sides (nbel counts them).
 struct RowMapI8 {
   double *Kb, *Rb;
-  int n, M, ld, ldr, c0, nb64;
+  int n, M, ld, ldr, c0, nbel;   // nbel: virtual rows between the diagonal block and the right-hand sides
   __device__ __forceinline__ double *row(int v, int &kind) const {
     if (v < NB) {
       const int r = c0 + v;
@@ -76,7 +82,7 @@ struct RowMapI8 {
       return nullptr;
     }
     int w = v - NB;
-    if (w < nb64) {
+    if (w < nbel) {
       const int r = c0 + NB + w;
       if (r < n) {
         kind = KIND_BELOW;
@@ -85,7 +91,7 @@ struct RowMapI8 {
       kind = KIND_NONE;
       return nullptr;
     }
-    w -= nb64;
+    w -= nbel;
     if (w < M) {
       kind = KIND_RHS;
       return Rb + (size_t)w * ldr;
@@ -113,6 +119,7 @@ struct SmemI8 {
   unsigned first[I8_MAXP + 1];   // sequence number of the first tile of every panel of this matrix
   uint32_t tmem_base;
   volatile unsigned stored;      // tiles whose planes are in global memory (monotone over the launch)
+  int quiet;                     // number of warps inside potf2 / TRSM (the issuer holds back while > 0)
   int bad;
   int bad_range;
   int next_item;
@@ -178,6 +185,15 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 __device__ __forceinline__ void mbar_wait_sleep(uint64_t *bar, unsigned parity, unsigned ns) {
   while (!mbar_test(bar, parity)) __nanosleep(ns);
 }
+// The tensor core reads its operands through the same shared-memory datapath the warps' SHFL / LDS use:
+// while the MMA stream runs, the shuffle-bound pivot chain of potf2 and the in-register TRSM run 2.5x
+// slower (measured with phase timers).  Warps announce those phases; the issuer holds back meanwhile.
+__device__ __forceinline__ void quiet_enter(int *q, int lane, bool on) {
+  if (on && lane == 0) atomicAdd(q, 1);
+}
+__device__ __forceinline__ void quiet_leave(int *q, int lane, bool on) {
+  if (on && lane == 0) atomicSub(q, 1);
+}
 __device__ __forceinline__ void cbar256() { asm volatile("bar.sync 2, 256;\n" ::: "memory"); }
 
 // smallest power of two 2^e with 1.0101 x < 2^e  (x / 2^e <= 0.99: the leading digit fits int8)
@@ -224,7 +240,13 @@ __host__ __device__ constexpr long long i8_bias(int S) {
 }
 
 // number of 128-row tiles of the panel starting at column c0 (NR = nt + M virtual rows in total)
-__device__ __forceinline__ int i8_ntiles(int NR, int c0) { return (NR - c0 + I8_TM - 1) / I8_TM; }
+__device__ __forceinline__ int i8_nbel(int n, int n64, bool gap, int c0) {
+  return gap ? ((c0 + NB <= n) ? n - c0 - NB : 0) : n64 - c0 - NB;
+}
+__device__ __forceinline__ int i8_nvirt(int n, int n64, int M, bool gap, int c0) {
+  return NB + i8_nbel(n, n64, gap, c0) + M;
+}
+__device__ __forceinline__ int i8_ntiles(int nvirt) { return (nvirt + I8_TM - 1) / I8_TM; }
 
 template <int S, int STAGES>
 __global__ void __launch_bounds__(I8_NTHREADS, 1)
@@ -250,6 +272,7 @@ __global__ void __launch_bounds__(I8_NTHREADS, 1)
     mbar_init(&sm.tmem_full, 1);
     mbar_init(&sm.tmem_empty, I8_NCT / 32);
     sm.stored = 0;
+    sm.quiet = 0;
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
 #ifdef SPB_POTRF_PROF
@@ -280,6 +303,8 @@ __global__ void __launch_bounds__(I8_NTHREADS, 1)
     rm.Rb = p.R ? p.R + (size_t)item * p.strideR : nullptr;
     rm.M = p.R ? p.M : 0;
     const int n64 = (p.n + NB - 1) & ~(NB - 1);
+    const int M_ = p.R ? p.M : 0;
+    const bool gap = (M_ <= n64 - p.n);   // also true when M = 0; false when nt is a multiple of 64 and M > 0
     double *quad_out = p.quad ? p.quad + (size_t)item * p.M : nullptr;
     AffRow af;
     af.q = nullptr;
@@ -307,7 +332,7 @@ __global__ void __launch_bounds__(I8_NTHREADS, 1)
       int j = 0;
       for (int c0 = 0; c0 < p.n; c0 += NB, ++j) {
         sm.first[j] = f;
-        f += (unsigned)i8_ntiles(NR, c0);
+        f += (unsigned)i8_ntiles(i8_nvirt(p.n, n64, M_, gap, c0));
       }
       sm.first[j] = f;
     }
@@ -323,7 +348,9 @@ __global__ void __launch_bounds__(I8_NTHREADS, 1)
       // row scales: 2^e_i > 1.0101 sqrt(K'_ii) for the rows of L;  for the right-hand-side rows
       // |y_k| <= |y| <= |r| / sqrt(lambda_min(K')) <= sqrt(nt) max|r| / sqrt(min diag) (x 4 of margin)
       double dgm = 1e300;
-      if (af.dg) {
+      if (ip.lambda_min > 0.0) {
+        dgm = ip.lambda_min;
+      } else if (af.dg) {
         if (af.dg_vec) {
           for (int r = tid; r < p.n; r += I8_NCT) dgm = fmin(dgm, af.dg[r]);
         } else {
@@ -364,8 +391,8 @@ __global__ void __launch_bounds__(I8_NTHREADS, 1)
       unsigned seq = seq_base;
       for (int c0 = 0; c0 < p.n; c0 += NB) {
         rm.c0 = c0;
-        rm.nb64 = n64 - c0 - NB;
-        const int nvirt = NR - c0;     // NB + nb64 + M
+        rm.nbel = i8_nbel(p.n, n64, gap, c0);
+        const int nvirt = NB + rm.nbel + rm.M;
         const bool full_panel = (c0 + NB <= p.n);
         const bool need_planes = (c0 + NB < p.n);   // a later panel will read these columns
         const int nchunks = c0 / I8_KCH;
@@ -375,15 +402,38 @@ __global__ void __launch_bounds__(I8_NTHREADS, 1)
 #pragma unroll
           for (int mt = 0; mt < 2; ++mt)
             init_acc(sm, rm, af, p.aff_on != 0, vr + mt * 8 + g, c0, tg, full_panel, acc[mt]);
+          {
+            // the K rows of the NEXT tile are read exactly once, from HBM, at the top of that tile: ask
+            // for them now (one 128-byte line per lane and row) so that they wait in L2
+            RowMapI8 rn = rm;
+            int v0n = v0 + I8_TM;
+            if (v0n >= nvirt) {
+              v0n = 0;
+              rn.c0 = c0 + NB;
+              rn.nbel = i8_nbel(p.n, n64, gap, rn.c0);
+            }
+            if (rn.c0 < p.n && !(ip.gate & 4)) {
+#pragma unroll
+              for (int mt = 0; mt < 2; ++mt) {
+                int kind;
+                const double *pn = rn.row(v0n + warp * 16 + mt * 8 + g, kind);
+                if (pn != nullptr && rn.c0 + 16 * tg < p.n)
+                  asm volatile("prefetch.global.L2 [%0];\n" ::"l"(pn + rn.c0 + 16 * tg));
+              }
+            }
+          }
           I8_PROF(sm, 0);
           if (nchunks > 0) {
             // scales of this thread's rows (plane row = c0 + virtual row for matrix and RHS rows alike)
             double si[2];
 #pragma unroll
             for (int mt = 0; mt < 2; ++mt) {
-              const int pr = c0 + vr + mt * 8 + g;
-              const bool valid = pr < p.n || (pr >= n64 && pr < NR);   // not a padding row
-              si[mt] = valid ? -ldexp(Eb[pr], -2 * I8_BITS) : 0.0;
+              const int v = vr + mt * 8 + g;
+              int kind;
+              (void)rm.row(v, kind);
+              const int er = (kind == KIND_RHS) ? n64 + (v - NB - rm.nbel) : c0 + v;   // row of the scale table
+              const bool valid = (kind == KIND_DIAG || kind == KIND_BELOW || kind == KIND_RHS);
+              si[mt] = valid ? -ldexp(Eb[er], -2 * I8_BITS) : 0.0;
             }
             mbar_wait_sleep(&sm.tmem_full, tq & 1u, 50);
             tc_fence_after();
@@ -420,8 +470,13 @@ __global__ void __launch_bounds__(I8_NTHREADS, 1)
             ++tq;
             I8_PROF(sm, 2);
           }
+          const int lw = warp;
           if (diag_tile) {
-            if (warp < 4) potf2_regs(sm, acc, warp, lane);
+            if (lw < 4) {
+              quiet_enter(&sm.quiet, lane, (ip.gate & 1) != 0);
+              potf2_regs(sm, acc, lw, lane);
+              quiet_leave(&sm.quiet, lane, (ip.gate & 1) != 0);
+            }
             cbar256();   // L_jj and the inverses of its diagonal tiles are in shared memory
             if (tid < min(NB, p.n - c0)) logdet_part += 0.5 * log(sm.dpiv[tid]);
             if (ip.store_factor) {
@@ -432,12 +487,15 @@ __global__ void __launch_bounds__(I8_NTHREADS, 1)
             }
           }
           I8_PROF(sm, 3);
-          if (!(diag_tile && warp < 4) && vr < nvirt) {
+          const int vr2 = v0 + lw * 16;             // first tile row of this warp from here on
+          if (!(diag_tile && lw < 4) && vr2 < nvirt) {
+            quiet_enter(&sm.quiet, lane, (ip.gate & 1) != 0);
             trsm_warp(sm, acc, lane);
+            quiet_leave(&sm.quiet, lane, (ip.gate & 1) != 0);
             I8_PROF(sm, 4);
 #pragma unroll
             for (int mt = 0; mt < 2; ++mt) {
-              const int v = vr + mt * 8 + g;
+              const int v = vr2 + mt * 8 + g;
               int kind;
               double *prow = rm.row(v, kind);
               const bool live = (kind == KIND_BELOW || kind == KIND_RHS);
@@ -466,7 +524,7 @@ __global__ void __launch_bounds__(I8_NTHREADS, 1)
               if (quad_out) {
                 q += __shfl_xor_sync(0xffffffffu, q, 1);
                 q += __shfl_xor_sync(0xffffffffu, q, 2);
-                if (kind == KIND_RHS && tg == 0) atomicAdd(quad_out + (v - NB - rm.nb64), q);
+                if (kind == KIND_RHS && tg == 0) atomicAdd(quad_out + (v - NB - rm.nbel), q);
               }
               // ---- digit planes of the new rows (read by the MMA stream of later panels).
               // Inside a 64-column panel block the bytes are stored in the order 16 tg + 2 nt + e
@@ -476,7 +534,8 @@ __global__ void __launch_bounds__(I8_NTHREADS, 1)
               // Digits: X = rint(x 2^(7S - e)), Xb = X + sum_j 64 128^j has base-128 digits u_j in
               // [0, 127] (plain bit fields, no carry chain), d_j = u_j - 64; the top digit keeps the sign.
               if (need_planes && live) {
-                const int pr = c0 + v;
+                const int mrhs = v - NB - rm.nbel;                      // right-hand-side index (KIND_RHS)
+                const int pr = (kind == KIND_RHS) ? n64 + mrhs : c0 + v;   // plane row == row of the scale table
                 const double sinv = ldexp(1.0 / Eb[pr], I8_BITS * S);   // 2^(7 S - e): exact
                 uint8_t *qrow = Qb + (size_t)pr * ip.LDQ + c0 + 16 * tg;
                 const size_t pstride = (size_t)NR * ip.LDQ;
@@ -508,6 +567,10 @@ __global__ void __launch_bounds__(I8_NTHREADS, 1)
                   o.z = (s == 0) ? W[s][2] : __vsub4(W[s][2], 0x40404040u);
                   o.w = (s == 0) ? W[s][3] : __vsub4(W[s][3], 0x40404040u);
                   *reinterpret_cast<uint4 *>(qrow + (size_t)s * pstride) = o;
+                  // "gap" layout: second copy of a right-hand-side row, read by the full panels
+                  if (gap && kind == KIND_RHS && n64 != p.n)
+                    *reinterpret_cast<uint4 *>(qrow + (size_t)s * pstride -
+                                               (size_t)(n64 - p.n) * ip.LDQ) = o;
                 }
               }
             }
@@ -515,7 +578,7 @@ __global__ void __launch_bounds__(I8_NTHREADS, 1)
           // the planes (generic-proxy stores) must be visible to the TMA engine before the producer is
           // told about them; the barrier also protects Ld / Dv against the next panel's potf2
           I8_PROF(sm, 5);
-          fence_proxy_async_global();
+          if (!(ip.gate & 2)) fence_proxy_async_global();   // (bit 1: timing experiment only)
           __threadfence_block();
           cbar256();
           if (tid == 0) sm.stored = seq + 1;
@@ -548,15 +611,25 @@ __global__ void __launch_bounds__(I8_NTHREADS, 1)
         I8_PROF_DECL(1);
         unsigned known = sm.stored;
         for (int c0 = NB; c0 < p.n; c0 += NB) {
-          const int nvirt = NR - c0;
+          const int nvirt = i8_nvirt(p.n, n64, M_, gap, c0);
           const int nchunks = c0 / I8_KCH;
+          const bool last_partial = (c0 + NB > p.n);
           for (int v0 = 0; v0 < nvirt; v0 += I8_TM) {
-            const int rlast = min(c0 + v0 + I8_TM - 1, NR - 1);   // last plane row the tile reads
+            const int vlast = min(v0 + I8_TM, nvirt) - 1;   // last live virtual row of the tile
             for (int ch = 0; ch < nchunks; ++ch, ++xchunk) {
-              // the k-columns of this chunk were written during panel P by the tile holding row rlast
+              // the k-columns of this chunk were written during panel P (a full panel), by the tile that
+              // held the tile's last live row there.  Virtual row of that row in panel P: matrix rows and,
+              // in full panels, right-hand sides simply shift by c0 - P; in the last (partial) panel the
+              // right-hand side m = vlast - 64 sat at NB + nbel(P) + m.
               const int P = (ch * I8_KCH) & ~(NB - 1);
-              const unsigned need = sm.first[P / NB] +
-                                    (unsigned)min(i8_ntiles(NR, P) - 1, (rlast - P) / I8_TM) + 1u;
+              int vP;
+              if (last_partial) {
+                const int m = vlast - NB;
+                vP = (m >= 0) ? NB + i8_nbel(p.n, n64, gap, P) + m : (p.n - 1 - P);
+              } else {
+                vP = vlast + (c0 - P);
+              }
+              const unsigned need = sm.first[P / NB] + (unsigned)(vP / I8_TM) + 1u;
               I8_PROF(sm, 10);
               if ((int)(known - need) < 0) {
                 while ((int)((known = sm.stored) - need) < 0) __nanosleep(100);
@@ -579,7 +652,7 @@ __global__ void __launch_bounds__(I8_NTHREADS, 1)
       if (lane == 0) {
         I8_PROF_DECL(1);
         for (int c0 = NB; c0 < p.n; c0 += NB) {
-          const int nvirt = NR - c0;
+          const int nvirt = i8_nvirt(p.n, n64, M_, gap, c0);
           const int nchunks = c0 / I8_KCH;
           for (int v0 = 0; v0 < nvirt; v0 += I8_TM, ++tq) {
             I8_PROF(sm, 2);
@@ -590,6 +663,8 @@ __global__ void __launch_bounds__(I8_NTHREADS, 1)
               const unsigned st = xchunk % STAGES;
               I8_PROF(sm, 2);
               mbar_wait_sleep(&sm.full[st], (xchunk / STAGES) & 1u, 50);
+              if (ip.gate & 1)
+                while (*(volatile int *)&sm.quiet > 0) __nanosleep(40);
               tc_fence_after();
               I8_PROF(sm, 1);
 #pragma unroll

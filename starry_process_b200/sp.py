@@ -65,15 +65,27 @@ class _Context(object):
                                            ctypes.byref(h)))
         self.handle = h
         # digit planes of the INT8-tensor-core Cholesky (spb_cholesky_lnlike_i8): 0 = FP64 (DMMA) kernel
-        self.cholesky_i8 = int(os.environ.get("SPB200_CHOLESKY_I8", "0"))
+        # always, 7 | 8 = INT8 path whenever it applies, -1 (default) = automatic: 8 planes (56 bits per
+        # row: FP64 rounding-noise level) where that kernel is the faster one on B200 -- nt >= 1200 and
+        # more matrices than the cluster kernel takes (measured: -22 % at nt = 1280, -41 % at 1536,
+        # -44 % at 4096; +3 % at nt = 1000)
+        self.cholesky_i8 = int(os.environ.get("SPB200_CHOLESKY_I8", "-1"))
+        self.num_sms = torch.cuda.get_device_properties(self.device).multi_processor_count
+
+    def i8_planes(self, nt, batch):
+        """Digit planes the batched ``log_likelihood`` uses for ``batch`` matrices of size ``nt`` (0: the
+        FP64 kernel)."""
+        if self.cholesky_i8 >= 0:
+            return self.cholesky_i8
+        return 8 if (nt >= 1200 and 2 * batch > self.num_sms) else 0
 
     def set_option(self, name, value):
         """Run-time switches of the library (include/spb200.h: spb_set_option), plus
-        ``"cholesky_i8"`` (0 | 7 | 8): batched ``log_likelihood`` factorises on the INT8 tensor cores
-        with that many 7-bit digit planes (``spb_cholesky_lnlike_i8``)."""
+        ``"cholesky_i8"`` (-1 | 0 | 7 | 8): batched ``log_likelihood`` factorises on the INT8 tensor cores
+        with that many 7-bit digit planes (``spb_cholesky_lnlike_i8``); -1 = automatic, 0 = never."""
         if name == "cholesky_i8":
-            if int(value) not in (0, 7, 8):
-                raise ValueError("cholesky_i8 must be 0, 7 or 8")
+            if int(value) not in (-1, 0, 7, 8):
+                raise ValueError("cholesky_i8 must be -1, 0, 7 or 8")
             self.cholesky_i8 = int(value)
             return
         _lib.check(self.lib.spb_set_option(self.handle, name.encode(), int(value)))
@@ -665,8 +677,8 @@ class StarryProcess(object):
         # B200 has 180 GB), of equal size: the Cholesky kernel claims matrices dynamically, so one
         # long launch has a shorter tail than several short ones
         per = nt * ldk * 8 + 4 * 256 * 256 * 8
-        if self._ctx.cholesky_i8:   # digit planes of the INT8 path live next to K
-            per += self._ctx.cholesky_i8 * (nt + 64) * (nt + 64)
+        if self._ctx.i8_planes(nt, self._B):   # digit planes of the INT8 path live next to K
+            per += self._ctx.i8_planes(nt, self._B) * (nt + 64) * (nt + 64)
         # (the assembly / GEMM kernels carry the batch in grid.y: at most 65535 elements a launch)
         step = max(1, min(self._B, self._max_chunk_bytes // per, 65535))
         nchunks = -(-self._B // step)
@@ -753,6 +765,13 @@ class StarryProcess(object):
         lnlike = torch.empty(self._B, dtype=torch.float64, device=dev)
         zs = []
         lib, h = self._lib, self._ctx.handle
+        # white-noise floor of K (a lower bound of its smallest eigenvalue): scales the right-hand-side
+        # digit planes of the INT8 path when the noise was already added by the assembly kernels
+        lam_min = 0.0
+        if isinstance(data_cov, (int, float)):
+            lam_min = float(data_cov)
+        elif isinstance(data_cov, (torch.Tensor, np.ndarray)) and data_cov.ndim == 0:
+            lam_min = float(data_cov)
         with torch.cuda.device(dev):
             for b0, b1 in self._chunks(nt, ldk):
                 Bc = b1 - b0
@@ -788,14 +807,18 @@ class StarryProcess(object):
                     ll = -0.5 * quad.sum() - M * logdet[0] - 0.5 * nt * M * math.log(2 * math.pi)
                     flagged = (self._info[b0:b1] != 0) | torch.isnan(ll)
                     lnlike[b0:b1] = torch.where(flagged, torch.full_like(ll, -float("inf")), ll)
-                elif affine is not None and self._ctx.cholesky_i8 and affine.diag and nt > 64:
-                    planes = self._ctx.cholesky_i8
+                elif self._ctx.i8_planes(nt, Bc) and nt > 64 and (
+                        (affine is not None and affine.diag) or lam_min > 0.0):
+                    # factorisation on the INT8 tensor cores (K is only read; potrf_i8.cuh)
+                    planes = self._ctx.i8_planes(nt, Bc)
                     nb_i8 = lib.spb_cholesky_i8_workspace_bytes(Bc, nt, M, planes)
                     ws_i8 = torch.empty(nb_i8, dtype=torch.uint8, device=dev)
                     _lib.check(lib.spb_cholesky_lnlike_i8(
-                        h, Bc, nt, _ptr(K), ldk, nt * ldk, ctypes.byref(affine), M, _ptr(resid), ldk,
+                        h, Bc, nt, _ptr(K), ldk, nt * ldk,
+                        ctypes.byref(affine) if affine is not None else None, M, _ptr(resid), ldk,
                         M * ldk, _ptr(lnlike[b0:b1]), None, None, _ptr(self._info[b0:b1]), planes,
-                        _ptr(ws_i8), nb_i8, _stream()))
+                        0.0 if affine is not None and affine.diag else lam_min, _ptr(ws_i8), nb_i8,
+                        _stream()))
                     del ws_i8
                 elif affine is not None:
                     _lib.check(lib.spb_cholesky_lnlike_affine(

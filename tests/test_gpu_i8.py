@@ -1,0 +1,140 @@
+"""GPU (-m gpu): the INT8-tensor-core Cholesky path (csrc/potrf_i8.cuh, spb_cholesky_lnlike_i8).
+
+The digit-plane emulation of the FP64 panel updates is error-free up to the 56 (planes = 8) or 49
+(planes = 7) bits kept per row, so it must reproduce the FP64 (DMMA) kernel to rounding noise and keep
+the 1e-8 parity with the unmodified reference's golden values:
+* C ABI: random SPD matrices, sizes that exercise the partial last panel, the "gap" and padded layouts of
+  the right-hand-side planes, many right-hand sides, more matrices than SMs;
+* the safety net (SPB_INFO_I8_RANGE -> FP64 kernel) on a right-hand side that cannot be scaled;
+* StarryProcess.log_likelihood with ``cholesky_i8`` on against the reference golden of the bench draws.
+"""
+import ctypes
+
+import numpy as np
+import pytest
+
+from conftest import U_LD
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def spb():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import starry_process_b200 as m
+
+    return m
+
+
+def P(t):
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def _both_kernels(spb, B, n, M, planes, seed, dg=1e-4, poison=None):
+    from starry_process_b200 import _lib
+
+    ctx = spb.get_context()
+    lib, h = ctx.lib, ctx.handle
+    dev = torch.device("cuda")
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    ld = n + (n & 1)
+    A = torch.randn(B, n, 24, dtype=torch.float64, generator=g)
+    K = torch.zeros(B, n, ld, dtype=torch.float64)
+    K[:, :, :n] = A @ A.transpose(1, 2) / 24.0
+    Mr = max(M, 1)
+    r = torch.zeros(B, Mr, ld, dtype=torch.float64)
+    r[:, :, :n] = 0.01 * torch.randn(B, Mr, n, dtype=torch.float64, generator=g)
+    if poison is not None:
+        r[poison[0], 0, poison[1]] = poison[2]
+    K, r = K.to(dev), r.to(dev)
+    dgt = torch.full((1,), dg, dtype=torch.float64, device=dev)
+    af = _lib.Affine()
+    af.diag, af.diag_kind, af.diag_stride = dgt.data_ptr(), 0, 0
+    out = {}
+    for name in ("f64", "i8"):
+        Kc, rc = K.clone(), r.clone()
+        ll = torch.zeros(B, dtype=torch.float64, device=dev)
+        quad = torch.zeros(B, Mr, dtype=torch.float64, device=dev)
+        logdet = torch.zeros(B, dtype=torch.float64, device=dev)
+        info = torch.zeros(B, dtype=torch.int32, device=dev)
+        if name == "f64":
+            _lib.check(lib.spb_cholesky_lnlike_affine(h, B, n, P(Kc), ld, n * ld, ctypes.byref(af), M, P(rc), ld,
+                                                      Mr * ld, P(ll), P(quad), P(logdet), P(info), None))
+        else:
+            nb = lib.spb_cholesky_i8_workspace_bytes(B, n, M, planes)
+            assert nb > 0
+            ws = torch.empty(nb, dtype=torch.uint8, device=dev)
+            _lib.check(lib.spb_cholesky_lnlike_i8(h, B, n, P(Kc), ld, n * ld, ctypes.byref(af), M, P(rc), ld,
+                                                  Mr * ld, P(ll), P(quad), P(logdet), P(info), planes, 0.0, P(ws), nb,
+                                                  None))
+            torch.cuda.synchronize()
+            if poison is None:
+                assert torch.equal(Kc, K), "the INT8 path must leave K untouched"
+        torch.cuda.synchronize()
+        out[name] = dict(ll=ll.cpu().numpy(), quad=quad.cpu().numpy(), logdet=logdet.cpu().numpy(),
+                         info=info.cpu().numpy(), y=rc.cpu().numpy()[:, :M, :n])
+    return out
+
+
+@pytest.mark.parametrize("B,n,M", [(2, 65, 1), (2, 128, 1), (2, 200, 1), (3, 257, 2), (2, 1000, 1), (2, 1000, 3),
+                                   (1, 1024, 0), (2, 1000, 24), (2, 1000, 25), (2, 1000, 130), (2, 1024, 2),
+                                   (1, 2049, 1), (300, 320, 1)])
+@pytest.mark.parametrize("planes", [8, 7])
+def test_i8_kernel_matches_fp64_kernel(spb, B, n, M, planes):
+    """math.py:75-100 / sp.py:1154-1188 through both kernels: same lnlike, |y|^2, log-determinant and
+    solved rows.  planes = 8: 56 bits per row -> FP64 rounding-noise level; planes = 7: 49 bits."""
+    o = _both_kernels(spb, B, n, M, planes, seed=1000 * B + n + M)
+    a, b = o["f64"], o["i8"]
+    tol = 2e-11 if planes == 8 else 3e-9
+    assert np.all(a["info"] == 0) and np.all(b["info"] == 0)
+    assert np.max(np.abs(a["logdet"] - b["logdet"]) / np.abs(a["logdet"])) < tol
+    if M:
+        assert np.max(np.abs(a["ll"] - b["ll"]) / np.abs(a["ll"])) < tol
+        assert np.max(np.abs(a["quad"] - b["quad"]) / np.abs(a["quad"])) < 50 * tol
+        assert np.max(np.abs(a["y"] - b["y"])) < 1e3 * tol * np.max(np.abs(a["y"]))
+
+
+def test_i8_safety_net_reruns_unscalable_matrices_on_the_fp64_kernel(spb):
+    """A right-hand side whose scale bound overflows (an entry of 1e300) cannot be cut into digits: the
+    matrix is flagged SPB_INFO_I8_RANGE inside the kernel and re-run through the FP64 kernel by the
+    launcher, so both paths return the same numbers; the other matrices of the batch are unaffected."""
+    o = _both_kernels(spb, 3, 500, 1, 8, seed=77, poison=(1, 10, 1e300))
+    a, b = o["f64"], o["i8"]
+    assert np.array_equal(np.isfinite(a["ll"]), np.isfinite(b["ll"]))
+    assert np.array_equal(a["ll"][1:2], b["ll"][1:2]) or (np.isneginf(a["ll"][1]) and np.isneginf(b["ll"][1]))
+    ok = [0, 2]
+    assert np.max(np.abs(a["ll"][ok] - b["ll"][ok]) / np.abs(a["ll"][ok])) < 2e-11
+    assert np.all(b["info"][ok] == 0)
+
+
+@pytest.mark.parametrize("planes", [8, 7])
+def test_log_likelihood_with_i8_cholesky_against_reference_golden(spb, golden, planes):
+    """The bench draws (tests/golden/bench_sweep_seed1234.npz, produced by the unmodified reference) with
+    the factorisation on the INT8 tensor cores: 1e-8 relative, identical -inf pattern, and rounding-noise
+    agreement with the FP64 kernel."""
+    import bench
+
+    hp, t, flux, _ = bench.synthetic_inputs(4096, 1234)
+    sw = golden("bench_sweep_seed1234.npz")
+    ns = len(sw["r"])
+    ctx = spb.get_context()
+    res = {}
+    try:
+        for pl in (0, planes):
+            ctx.set_option("cholesky_i8", pl)
+            gp = spb.StarryProcess(marginalize_over_inclination=True, normalized=True,
+                                   **{k: hp[k][:ns] for k in hp})
+            res[pl] = gp.log_likelihood(t, flux, 1e-6, i=60.0, p=1.0, u=U_LD).cpu().numpy()
+    finally:
+        ctx.set_option("cholesky_i8", -1)
+    ref = sw["lnlike_m1_n1"]
+    ll = res[planes]
+    assert np.array_equal(np.isneginf(ll), np.isneginf(ref))
+    fin = np.isfinite(ref)
+    err = np.abs(ll[fin] - ref[fin]) / np.abs(ref[fin])
+    d = np.abs(ll[fin] - res[0][fin]) / np.abs(res[0][fin])
+    print("i8 planes=%d: max rel err vs reference %.2e, vs FP64 kernel %.2e" % (planes, err.max(), d.max()))
+    assert err.max() <= 1e-8
+    assert d.max() <= (1e-11 if planes == 8 else 1e-9)
