@@ -487,6 +487,9 @@ __global__ void __launch_bounds__(I8_NTHREADS, 1)
             }
           }
           I8_PROF(sm, 3);
+          // a matrix already found not positive definite turns into NaNs from here on: its digits
+          // overflow, but there is nothing to rescue by re-running it on the FP64 kernel
+          const bool already_bad = (*(volatile int *)&sm.bad) != 0;
           const int vr2 = v0 + lw * 16;             // first tile row of this warp from here on
           if (!(diag_tile && lw < 4) && vr2 < nvirt) {
             quiet_enter(&sm.quiet, lane, (ip.gate & 1) != 0);
@@ -555,7 +558,7 @@ __global__ void __launch_bounds__(I8_NTHREADS, 1)
                     for (int jd = 0; jd < S - 1; ++jd)
                       W[S - 1 - jd][nt >> 1] += ((uint32_t)(Xb >> (I8_BITS * jd)) & 127u) * mul;
                     const int top = (int)(Xb >> (I8_BITS * (S - 1))) - 64;
-                    bad_range = bad_range || top < -128 || top > 127;
+                    bad_range = bad_range || ((top < -128 || top > 127) && !already_bad);
                     W[0][nt >> 1] += ((uint32_t)top & 255u) * mul;
                   }
                 }

@@ -32,7 +32,7 @@ def P(t):
     return ctypes.c_void_p(t.data_ptr())
 
 
-def _both_kernels(spb, B, n, M, planes, seed, dg=1e-4, poison=None):
+def _both_kernels(spb, B, n, M, planes, seed, dg=1e-4, poison=None, not_pd=None):
     from starry_process_b200 import _lib
 
     ctx = spb.get_context()
@@ -43,6 +43,8 @@ def _both_kernels(spb, B, n, M, planes, seed, dg=1e-4, poison=None):
     A = torch.randn(B, n, 24, dtype=torch.float64, generator=g)
     K = torch.zeros(B, n, ld, dtype=torch.float64)
     K[:, :, :n] = A @ A.transpose(1, 2) / 24.0
+    if not_pd is not None:   # an indefinite element: the pivots turn negative half way through
+        K[not_pd, n // 2:, n // 2:n] -= 3.0 * torch.eye(n - n // 2, dtype=torch.float64)
     Mr = max(M, 1)
     r = torch.zeros(B, Mr, ld, dtype=torch.float64)
     r[:, :, :n] = 0.01 * torch.randn(B, Mr, n, dtype=torch.float64, generator=g)
@@ -70,7 +72,7 @@ def _both_kernels(spb, B, n, M, planes, seed, dg=1e-4, poison=None):
                                                   Mr * ld, P(ll), P(quad), P(logdet), P(info), planes, 0.0, P(ws), nb,
                                                   None))
             torch.cuda.synchronize()
-            if poison is None:
+            if poison is None and not_pd is None:
                 assert torch.equal(Kc, K), "the INT8 path must leave K untouched"
         torch.cuda.synchronize()
         out[name] = dict(ll=ll.cpu().numpy(), quad=quad.cpu().numpy(), logdet=logdet.cpu().numpy(),
@@ -138,3 +140,17 @@ def test_log_likelihood_with_i8_cholesky_against_reference_golden(spb, golden, p
     print("i8 planes=%d: max rel err vs reference %.2e, vs FP64 kernel %.2e" % (planes, err.max(), d.max()))
     assert err.max() <= 1e-8
     assert d.max() <= (1e-11 if planes == 8 else 1e-9)
+
+
+def test_i8_not_positive_definite_element(spb):
+    """math.py:82-91: a matrix that is not positive definite gives -inf and SPB_INFO_NOT_PD on both kernels,
+    is NOT re-run through the FP64 kernel (its digit overflow is a consequence, not a cause), and leaves the
+    other matrices of the batch alone."""
+    o = _both_kernels(spb, 4, 700, 1, 8, seed=5, not_pd=2)
+    a, b = o["f64"], o["i8"]
+    assert a["info"][2] & 1 and b["info"][2] & 1
+    assert not (b["info"][2] & 16)
+    assert np.isneginf(a["ll"][2]) and np.isneginf(b["ll"][2])
+    ok = [0, 1, 3]
+    assert np.all(b["info"][ok] == 0)
+    assert np.max(np.abs(a["ll"][ok] - b["ll"][ok]) / np.abs(a["ll"][ok])) < 2e-11
