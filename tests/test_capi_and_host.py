@@ -250,3 +250,15 @@ def test_longitude_basis_tables():
         assert diff.min() >= off["LON_T"] and diff.max() < off["LON_T"] + 31 * T.NWIG
     with pytest.raises(ValueError):
         T.build_tables("nonsense")
+
+
+def test_sass_int8_cholesky_uses_tcgen05_tmem_and_tma(built_lib):
+    """potrf_i8.cuh: the panel updates of the INT8 path must be tcgen05.mma.kind::i8 (SASS UTCIMMA) with
+    accumulators read back from tensor memory (LDTM), operands fetched by 4-D TMA loads (UTMALDG.4D),
+    tcgen05.commit (UTCBAR) hand-offs and the generic -> async proxy fence before the planes are re-read."""
+    sass = subprocess.run(["cuobjdump", "-sass", built_lib], capture_output=True, text=True).stdout
+    beg = sass.index("potrf_i8_kernel")
+    end = sass.find("Function :", beg)
+    body = sass[beg:end if end > 0 else None]
+    for mnemonic in ("UTCIMMA", "LDTM", "UTMALDG.4D", "UTCBAR", "FENCE.VIEW.ASYNC.G", "DMMA.8x8x4"):
+        assert mnemonic in body, mnemonic
