@@ -45,7 +45,12 @@
 constexpr int I8_KCH = 32;           // bytes of k per ring stage = K of one tcgen05.mma.kind::i8
 constexpr int I8_BITS = 7;
 constexpr int I8_NCT = 256;          // compute threads (warps 0-7)
-constexpr int I8_NTHREADS = 320;     // + warp 8 (TMA producer) + warp 9 (MMA issuer)
+#ifndef I8_ROLE_WARP0
+#define I8_ROLE_WARP0 8
+#endif
+constexpr int I8_PRODUCER_WARP = I8_ROLE_WARP0;        // TMA producer (one thread)
+constexpr int I8_ISSUER_WARP = I8_ROLE_WARP0 + 1;      // MMA issuer (one thread)
+constexpr int I8_NTHREADS = 32 * (I8_ROLE_WARP0 + 2);
 constexpr int I8_MAXP = 256;         // panels per matrix (nt <= 16384)
 constexpr int I8_TM = 128;
 
@@ -278,7 +283,7 @@ __global__ void __launch_bounds__(I8_NTHREADS, 1)
 #ifdef SPB_POTRF_PROF
   if (tid < 32) sm.prof[tid / 16][tid % 16] = 0;
 #endif
-  if (pw == 9) {
+  if (pw == I8_ISSUER_WARP) {
     const uint32_t a = (uint32_t)__cvta_generic_to_shared(&sm.tmem_base);
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(a), "r"(512u)
                  : "memory");
@@ -412,7 +417,7 @@ __global__ void __launch_bounds__(I8_NTHREADS, 1)
               rn.c0 = c0 + NB;
               rn.nbel = i8_nbel(p.n, n64, gap, rn.c0);
             }
-            if (rn.c0 < p.n && !(ip.gate & 4)) {
+            if (rn.c0 < p.n) {
 #pragma unroll
               for (int mt = 0; mt < 2; ++mt) {
                 int kind;
@@ -581,7 +586,7 @@ __global__ void __launch_bounds__(I8_NTHREADS, 1)
           // the planes (generic-proxy stores) must be visible to the TMA engine before the producer is
           // told about them; the barrier also protects Ld / Dv against the next panel's potf2
           I8_PROF(sm, 5);
-          if (!(ip.gate & 2)) fence_proxy_async_global();   // (bit 1: timing experiment only)
+          fence_proxy_async_global();
           __threadfence_block();
           cbar256();
           if (tid == 0) sm.stored = seq + 1;
@@ -608,7 +613,7 @@ __global__ void __launch_bounds__(I8_NTHREADS, 1)
           p.info[item] = prev | (bad ? SPB_INFO_NOT_PD : 0) | (sm.bad_range ? SPB_INFO_I8_RANGE : 0);
         sm.next_item = (int)gridDim.x + (int)atomicAdd(p.counter, 1u);
       }
-    } else if (pw == 8) {
+    } else if (pw == I8_PRODUCER_WARP) {
       // ============================================================== TMA PRODUCER (one thread)
       if (lane == 0) {
         I8_PROF_DECL(1);
@@ -650,7 +655,7 @@ __global__ void __launch_bounds__(I8_NTHREADS, 1)
           }
         }
       }
-    } else {
+    } else if (pw == I8_ISSUER_WARP) {
       // ============================================================== MMA ISSUER (one thread)
       if (lane == 0) {
         I8_PROF_DECL(1);
@@ -700,7 +705,7 @@ __global__ void __launch_bounds__(I8_NTHREADS, 1)
 #ifdef SPB_POTRF_PROF
   if (tid < 32) atomicAdd(&g_potrf_prof[tid / 16][tid % 16], sm.prof[tid / 16][tid % 16]);
 #endif
-  if (pw == 9) {
+  if (pw == I8_ISSUER_WARP) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "r"(512u) : "memory");
   }
 }
