@@ -1,4 +1,5 @@
-"""One launch of spb_cholesky_lnlike_i8 (B = 148, nt = 1000, M = 1) for ncu."""
+"""One launch of spb_cholesky_lnlike_i8 (default B = 148, 8 planes, nt = 1000, M = 1) for ncu:
+   python scripts/gpu_i8_one.py [B [planes [nt]]]"""
 import ctypes, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -8,7 +9,10 @@ from starry_process_b200 import _lib
 dev = torch.device("cuda:0")
 c = spb.get_context(0); lib, ctx = c.lib, c.handle
 P = lambda x: ctypes.c_void_p(x.data_ptr())
-B, n, M, planes = int(sys.argv[1]) if len(sys.argv) > 1 else 148, 1000, 1, int(sys.argv[2]) if len(sys.argv) > 2 else 8
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 148
+planes = int(sys.argv[2]) if len(sys.argv) > 2 else 8
+n = int(sys.argv[3]) if len(sys.argv) > 3 else 1000
+M = 1
 A = torch.randn(B, n, 32, dtype=torch.float64, device=dev)
 K = torch.bmm(A, A.transpose(1, 2)) / 32
 R = 0.01 * torch.randn(B, 1, n, dtype=torch.float64, device=dev)
