@@ -767,11 +767,11 @@ class StarryProcess(object):
         lib, h = self._lib, self._ctx.handle
         # white-noise floor of K (a lower bound of its smallest eigenvalue): scales the right-hand-side
         # digit planes of the INT8 path when the noise was already added by the assembly kernels
-        lam_min = 0.0
-        if isinstance(data_cov, (int, float)):
+        lam_min, noise_free = 0.0, False
+        if isinstance(data_cov, (int, float)) or (
+                isinstance(data_cov, (torch.Tensor, np.ndarray)) and data_cov.ndim == 0):
             lam_min = float(data_cov)
-        elif isinstance(data_cov, (torch.Tensor, np.ndarray)) and data_cov.ndim == 0:
-            lam_min = float(data_cov)
+            noise_free = not (lam_min > 0.0)   # no white-noise floor: nothing bounds the solved rows
         with torch.cuda.device(dev):
             for b0, b1 in self._chunks(nt, ldk):
                 Bc = b1 - b0
@@ -807,7 +807,7 @@ class StarryProcess(object):
                     ll = -0.5 * quad.sum() - M * logdet[0] - 0.5 * nt * M * math.log(2 * math.pi)
                     flagged = (self._info[b0:b1] != 0) | torch.isnan(ll)
                     lnlike[b0:b1] = torch.where(flagged, torch.full_like(ll, -float("inf")), ll)
-                elif self._ctx.i8_planes(nt, Bc) and nt > 64 and (
+                elif self._ctx.i8_planes(nt, Bc) and nt > 64 and not noise_free and (
                         (affine is not None and affine.diag) or lam_min > 0.0):
                     # factorisation on the INT8 tensor cores (K is only read; potrf_i8.cuh)
                     planes = self._ctx.i8_planes(nt, Bc)
