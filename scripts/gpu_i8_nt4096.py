@@ -17,7 +17,7 @@ t = np.linspace(0, 16.0, nt)
 flux = 1e-3 * rng.standard_normal(nt) + 2e-3 * np.sin(2 * np.pi * t)
 td = torch.as_tensor(t, device=dev); fd = torch.as_tensor(flux, device=dev)
 res = {}
-for planes in (0, 8, 7):
+for planes in (0, 78):
     ctx.set_option("cholesky_i8", planes)
     best = None
     for rep in range(3):
@@ -31,7 +31,7 @@ for planes in (0, 8, 7):
     res[planes] = ll.cpu().numpy()
     print("B %d nt %d planes %d: %.1f ms, stages %s" % (B, nt, planes, best[0], {k: round(v, 1) for k, v in best[1].items()}), flush=True)
 fin = np.isfinite(res[0])
-for planes in (8, 7):
+for planes in (78,):
     print("  planes %d: max rel lnlike diff vs FP64 kernel %.2e, -inf pattern equal %s" % (
         planes, np.max(np.abs(res[planes][fin] - res[0][fin]) / np.abs(res[0][fin])), np.array_equal(np.isfinite(res[planes]), fin)))
 ctx.set_option("cholesky_i8", -1)

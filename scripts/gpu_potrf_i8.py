@@ -62,7 +62,7 @@ def main():
     print("== C ABI, random SPD + 1e-4 I")
     for (B, n, M) in [(2, 128, 1), (2, 200, 1), (3, 257, 2), (2, 1000, 1), (2, 1000, 3), (1, 1024, 0),
                       (2, 1000, 130), (1, 2049, 1), (300, 320, 1)]:
-        for planes in (8, 7):
+        for planes in (8, 78, 7):
             capi_case(ctx, B, n, M, planes, seed=B * 1000 + n)
     print("== through StarryProcess (bench draws, marginalised + normalised)")
     import bench
@@ -74,13 +74,13 @@ def main():
         td = torch.as_tensor(t, dtype=torch.float64, device=dev)
         fd = torch.as_tensor(flux, dtype=torch.float64, device=dev)
         res = {}
-        for planes in (0, 8, 7):
+        for planes in (0, 8, 78, 7):
             ctx.set_option("cholesky_i8", planes)
             ll = spb.StarryProcess(**hd).log_likelihood(td, fd, 1e-6, p=1.0, u=bench.U_LD)
             torch.cuda.synchronize()
             res[planes] = ll.cpu()
         fin = torch.isfinite(res[0])
-        for planes in (8, 7):
+        for planes in (8, 78, 7):
             same_inf = bool((torch.isfinite(res[planes]) == fin).all())
             rel = ((res[planes][fin] - res[0][fin]).abs() / res[0][fin].abs()).max()
             print("  prior %-6s planes %d: max rel lnlike diff vs FP64 kernel %.2e (finite %d / %d, -inf pattern equal: %s)"
@@ -92,7 +92,7 @@ def main():
         hd = {k: torch.as_tensor(v, dtype=torch.float64, device=dev) for k, v in hp.items()}
         td = torch.as_tensor(t, dtype=torch.float64, device=dev)
         fd = torch.as_tensor(flux, dtype=torch.float64, device=dev)
-        for planes in (0, 8, 7):
+        for planes in (0, 8, 78, 7):
             ctx.set_option("cholesky_i8", planes)
             ts = []
             for rep in range(4):

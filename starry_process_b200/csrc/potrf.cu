@@ -1763,8 +1763,20 @@ extern "C" int spb_cholesky_lnlike_affine(spb_context *ctx, int B, int nt, doubl
 // ---- INT8-tensor-core path (potrf_i8.cuh) ----------------------------------------------------------
 static inline int i8_n64(int nt) { return (nt + NB - 1) & ~(NB - 1); }
 
+// `planes` of the C ABI: 8 (= 87) eight planes of 7-bit digits, 7 (= 77) seven planes of 7-bit digits,
+// 78 seven planes of 8-bit digits
+static inline int i8_decode(int planes, int *rb) {
+  if (planes == 8 || planes == 87) { *rb = 7; return 8; }
+  if (planes == 7 || planes == 77) { *rb = 7; return 7; }
+  if (planes == 78) { *rb = 8; return 7; }
+  *rb = 0;
+  return 0;
+}
+
 extern "C" size_t spb_cholesky_i8_workspace_bytes(int B, int nt, int M, int planes) {
-  if (B <= 0 || nt <= 0 || M < 0 || planes < 7 || planes > 8) return 0;
+  int rb0;
+  planes = i8_decode(planes, &rb0);
+  if (B <= 0 || nt <= 0 || M < 0 || planes == 0) return 0;
   const size_t NR = (size_t)i8_n64(nt) + (size_t)M, LDQ = (size_t)i8_n64(nt);
   return (size_t)B * ((size_t)planes * NR * LDQ + NR * sizeof(double)) + 1024;
 }
@@ -1780,7 +1792,10 @@ extern "C" int spb_cholesky_lnlike_i8(spb_context *ctx, int B, int nt, double *K
               "cholesky_lnlike_i8: lambda_min > 0 or affine->diag (data covariance) is required");
   SPB_REQUIRE(affine == nullptr || (affine->scal == nullptr) == (affine->q == nullptr),
               "cholesky_lnlike_i8: scal and q must be given together");
-  SPB_REQUIRE(planes == 7 || planes == 8, "cholesky_lnlike_i8: planes must be 7 or 8");
+  int rb = 0;
+  const int planes_arg = planes;
+  planes = i8_decode(planes, &rb);
+  SPB_REQUIRE(planes != 0, "cholesky_lnlike_i8: planes must be 7, 8, 77, 78 or 87");
   SPB_REQUIRE(info != nullptr, "cholesky_lnlike_i8: info is required");
   SPB_REQUIRE(nt > NB && nt <= NB * I8_MAXP, "cholesky_lnlike_i8: nt out of range (64 < nt <= 16384)");
   SPB_REQUIRE(workspace != nullptr && workspace_bytes >= spb_cholesky_i8_workspace_bytes(B, nt, M, planes),
@@ -1851,9 +1866,11 @@ extern "C" int spb_cholesky_lnlike_i8(spb_context *ctx, int B, int nt, double *K
   static spb_once_flag attr_once;
   {
     const int st = spb_once_per_device(attr_once, ctx->device, [&]() -> int {
-      SPB_CHECK_CUDA(cudaFuncSetAttribute(potrf_i8_kernel<8, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+      SPB_CHECK_CUDA(cudaFuncSetAttribute(potrf_i8_kernel<8, 3, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           (int)sizeof(SmemI8<8, 3>)));
-      SPB_CHECK_CUDA(cudaFuncSetAttribute(potrf_i8_kernel<7, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+      SPB_CHECK_CUDA(cudaFuncSetAttribute(potrf_i8_kernel<7, 3, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)sizeof(SmemI8<7, 3>)));
+      SPB_CHECK_CUDA(cudaFuncSetAttribute(potrf_i8_kernel<7, 3, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           (int)sizeof(SmemI8<7, 3>)));
       SPB_CHECK_CUDA(cudaFuncSetAttribute(potrf_lnlike_kernel<128, 3, 2>,
                                           cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1867,9 +1884,11 @@ extern "C" int spb_cholesky_lnlike_i8(spb_context *ctx, int B, int nt, double *K
       (__atomic_fetch_add(&ctx->counter_next, 1u, __ATOMIC_RELAXED) % SPB_NUM_COUNTERS);
   SPB_CHECK_CUDA(cudaMemsetAsync(p.counter, 0, sizeof(unsigned int), (cudaStream_t)stream));
   if (planes == 8)
-    potrf_i8_kernel<8, 3><<<grid, I8_NTHREADS, sizeof(SmemI8<8, 3>), (cudaStream_t)stream>>>(p, ip, tmA, tmB);
+    potrf_i8_kernel<8, 3, 7><<<grid, I8_NTHREADS, sizeof(SmemI8<8, 3>), (cudaStream_t)stream>>>(p, ip, tmA, tmB);
+  else if (rb == 7)
+    potrf_i8_kernel<7, 3, 7><<<grid, I8_NTHREADS, sizeof(SmemI8<7, 3>), (cudaStream_t)stream>>>(p, ip, tmA, tmB);
   else
-    potrf_i8_kernel<7, 3><<<grid, I8_NTHREADS, sizeof(SmemI8<7, 3>), (cudaStream_t)stream>>>(p, ip, tmA, tmB);
+    potrf_i8_kernel<7, 3, 8><<<grid, I8_NTHREADS, sizeof(SmemI8<7, 3>), (cudaStream_t)stream>>>(p, ip, tmA, tmB);
   SPB_LAUNCH_CHECK(ctx);
   // safety net: matrices flagged SPB_INFO_I8_RANGE go through the FP64 kernel (their K is intact)
   {

@@ -43,7 +43,10 @@
 #endif
 
 constexpr int I8_KCH = 32;           // bytes of k per ring stage = K of one tcgen05.mma.kind::i8
-constexpr int I8_BITS = 7;
+// digit width RB (template parameter): 7 -> digits in [-64, 63] except the leading one, which uses the whole
+// int8 range (|x| <= 0.99); 8 -> balanced base-256 digits in [-128, 127], all planes use the whole range, the
+// rows are scaled to |x| <= 1/2: 7 planes then carry 55 bits -- one bit less than 8 planes of 7 bits with 28
+// instead of 36 plane products and 7/8 of the operand traffic
 constexpr int I8_NCT = 256;          // compute threads (warps 0-7)
 #ifndef I8_ROLE_WARP0
 #define I8_ROLE_WARP0 8
@@ -238,9 +241,9 @@ __device__ __forceinline__ double block_min_i8(SM &sm, double v) {
 }
 
 // sum_{j < S} 64 128^j: makes every base-128 digit of a signed S-digit number non-negative
-__host__ __device__ constexpr long long i8_bias(int S) {
+__host__ __device__ constexpr long long i8_bias(int S, int RB) {
   long long b = 0;
-  for (int j = 0; j < S; ++j) b = b * 128 + 64;
+  for (int j = 0; j < S; ++j) b = (b << RB) + (1ll << (RB - 1));
   return b;
 }
 
@@ -253,7 +256,7 @@ __device__ __forceinline__ int i8_nvirt(int n, int n64, int M, bool gap, int c0)
 }
 __device__ __forceinline__ int i8_ntiles(int nvirt) { return (nvirt + I8_TM - 1) / I8_TM; }
 
-template <int S, int STAGES>
+template <int S, int STAGES, int RB>
 __global__ void __launch_bounds__(I8_NTHREADS, 1)
     potrf_i8_kernel(PotrfParams p, I8Params ip, const __grid_constant__ CUtensorMap tmA,
                     const __grid_constant__ CUtensorMap tmB) {
@@ -375,7 +378,7 @@ __global__ void __launch_bounds__(I8_NTHREADS, 1)
           }
           kd = aff_apply(sm, af, kd, Ci, Di, true, r, r);
         }
-        Eb[r] = pow2_above(sqrt(kd));
+        Eb[r] = pow2_above(sqrt(kd)) * (RB == 8 ? 2.0 : 1.0);
       }
       for (int m = pw; m < rm.M; m += I8_NCT / 32) {
         const double *rr = rm.Rb + (size_t)m * p.ldr;
@@ -383,7 +386,8 @@ __global__ void __launch_bounds__(I8_NTHREADS, 1)
         for (int k = lane; k < p.n; k += 32) mx = fmax(mx, fabs(rr[k]));
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-        if (lane == 0) Eb[n64 + m] = pow2_above(4.0 * sqrt((double)p.n) * mx * rsqrt(dgm));
+        if (lane == 0)
+          Eb[n64 + m] = pow2_above(4.0 * sqrt((double)p.n) * mx * rsqrt(dgm)) * (RB == 8 ? 2.0 : 1.0);
       }
       for (int r = p.n + tid; r < n64; r += I8_NCT) Eb[r] = 1.0;
       __threadfence_block();
@@ -438,7 +442,7 @@ __global__ void __launch_bounds__(I8_NTHREADS, 1)
               (void)rm.row(v, kind);
               const int er = (kind == KIND_RHS) ? n64 + (v - NB - rm.nbel) : c0 + v;   // row of the scale table
               const bool valid = (kind == KIND_DIAG || kind == KIND_BELOW || kind == KIND_RHS);
-              si[mt] = valid ? -ldexp(Eb[er], -2 * I8_BITS) : 0.0;
+              si[mt] = valid ? -ldexp(Eb[er], -2 * RB) : 0.0;
             }
             mbar_wait_sleep(&sm.tmem_full, tq & 1u, 50);
             tc_fence_after();
@@ -463,7 +467,7 @@ __global__ void __launch_bounds__(I8_NTHREADS, 1)
                     double t = (double)(int)v[D][4 * b + 2 * mt + e];
 #pragma unroll
                     for (int d = D - 1; d >= 0; --d)
-                      t = fma(t, 0.0078125, (double)(int)v[d][4 * b + 2 * mt + e]);
+                      t = fma(t, RB == 8 ? 0.00390625 : 0.0078125, (double)(int)v[d][4 * b + 2 * mt + e]);
                     acc[mt][nt][e] = fma(si[mt] * (e ? sj1 : sj0), t, acc[mt][nt][e]);
                   }
                 }
@@ -544,10 +548,12 @@ __global__ void __launch_bounds__(I8_NTHREADS, 1)
               if (need_planes && live) {
                 const int mrhs = v - NB - rm.nbel;                      // right-hand-side index (KIND_RHS)
                 const int pr = (kind == KIND_RHS) ? n64 + mrhs : c0 + v;   // plane row == row of the scale table
-                const double sinv = ldexp(1.0 / Eb[pr], I8_BITS * S);   // 2^(7 S - e): exact
+                const double sinv = ldexp(1.0 / Eb[pr], RB * S);   // 2^(RB S - e): exact
                 uint8_t *qrow = Qb + (size_t)pr * ip.LDQ + c0 + 16 * tg;
                 const size_t pstride = (size_t)NR * ip.LDQ;
-                constexpr long long BIAS = i8_bias(S);
+                constexpr long long BIAS = i8_bias(S, RB);
+                constexpr unsigned FMASK = (1u << RB) - 1u;
+                constexpr unsigned HALF4 = (RB == 8) ? 0x80808080u : 0x40404040u;
                 uint32_t W[S][4];
 #pragma unroll
                 for (int s = 0; s < S; ++s)
@@ -561,8 +567,8 @@ __global__ void __launch_bounds__(I8_NTHREADS, 1)
                     const unsigned mul = 1u << (8 * ((nt & 1) * 2 + e));   // byte position in the word
 #pragma unroll
                     for (int jd = 0; jd < S - 1; ++jd)
-                      W[S - 1 - jd][nt >> 1] += ((uint32_t)(Xb >> (I8_BITS * jd)) & 127u) * mul;
-                    const int top = (int)(Xb >> (I8_BITS * (S - 1))) - 64;
+                      W[S - 1 - jd][nt >> 1] += ((uint32_t)(Xb >> (RB * jd)) & FMASK) * mul;
+                    const int top = (int)(Xb >> (RB * (S - 1))) - (1 << (RB - 1));
                     bad_range = bad_range || ((top < -128 || top > 127) && !already_bad);
                     W[0][nt >> 1] += ((uint32_t)top & 255u) * mul;
                   }
@@ -570,10 +576,10 @@ __global__ void __launch_bounds__(I8_NTHREADS, 1)
 #pragma unroll
                 for (int s = 0; s < S; ++s) {
                   uint4 o;
-                  o.x = (s == 0) ? W[s][0] : __vsub4(W[s][0], 0x40404040u);
-                  o.y = (s == 0) ? W[s][1] : __vsub4(W[s][1], 0x40404040u);
-                  o.z = (s == 0) ? W[s][2] : __vsub4(W[s][2], 0x40404040u);
-                  o.w = (s == 0) ? W[s][3] : __vsub4(W[s][3], 0x40404040u);
+                  o.x = (s == 0) ? W[s][0] : __vsub4(W[s][0], HALF4);
+                  o.y = (s == 0) ? W[s][1] : __vsub4(W[s][1], HALF4);
+                  o.z = (s == 0) ? W[s][2] : __vsub4(W[s][2], HALF4);
+                  o.w = (s == 0) ? W[s][3] : __vsub4(W[s][3], HALF4);
                   *reinterpret_cast<uint4 *>(qrow + (size_t)s * pstride) = o;
                   // "gap" layout: second copy of a right-hand-side row, read by the full panels
                   if (gap && kind == KIND_RHS && n64 != p.n)

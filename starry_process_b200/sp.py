@@ -64,11 +64,12 @@ class _Context(object):
             _lib.check(self.lib.spb_create(device, blob.ctypes.data_as(ctypes.c_void_p), blob.size,
                                            ctypes.byref(h)))
         self.handle = h
-        # digit planes of the INT8-tensor-core Cholesky (spb_cholesky_lnlike_i8): 0 = FP64 (DMMA) kernel
-        # always, 7 | 8 = INT8 path whenever it applies, -1 (default) = automatic: 8 planes (56 bits per
-        # row: FP64 rounding-noise level) where that kernel is the faster one on B200 -- nt >= 1200 and
-        # more matrices than the cluster kernel takes (measured: -22 % at nt = 1280, -41 % at 1536,
-        # -44 % at 4096; +3 % at nt = 1000)
+        # INT8-tensor-core Cholesky (spb_cholesky_lnlike_i8): 0 = always the FP64 (DMMA) kernel; 78 = seven
+        # planes of 8-bit digits (55 bits per row: FP64 rounding-noise level), 8 / 87 = eight planes of 7-bit
+        # digits (56 bits), 7 / 77 = seven planes of 7-bit digits (49 bits) whenever the path applies;
+        # -1 (default) = automatic: 78 where that kernel is the faster one on B200 -- nt >= 704 and more
+        # matrices than the cluster kernel takes (measured Cholesky stage, INT8 vs DMMA: nt = 512 +14 %,
+        # 768 -10 %, 1000 -13 % (-25 % conditional), 1536 -45 %, 4096 -55 %)
         self.cholesky_i8 = int(os.environ.get("SPB200_CHOLESKY_I8", "-1"))
         self.num_sms = torch.cuda.get_device_properties(self.device).multi_processor_count
 
@@ -77,15 +78,15 @@ class _Context(object):
         FP64 kernel)."""
         if self.cholesky_i8 >= 0:
             return self.cholesky_i8
-        return 8 if (nt >= 1200 and 2 * batch > self.num_sms) else 0
+        return 78 if (nt >= 704 and 2 * batch > self.num_sms) else 0
 
     def set_option(self, name, value):
         """Run-time switches of the library (include/spb200.h: spb_set_option), plus
         ``"cholesky_i8"`` (-1 | 0 | 7 | 8): batched ``log_likelihood`` factorises on the INT8 tensor cores
         with that many 7-bit digit planes (``spb_cholesky_lnlike_i8``); -1 = automatic, 0 = never."""
         if name == "cholesky_i8":
-            if int(value) not in (-1, 0, 7, 8):
-                raise ValueError("cholesky_i8 must be -1, 0, 7 or 8")
+            if int(value) not in (-1, 0, 7, 8, 77, 78, 87):
+                raise ValueError("cholesky_i8 must be -1, 0, 7 (= 77), 8 (= 87) or 78")
             self.cholesky_i8 = int(value)
             return
         _lib.check(self.lib.spb_set_option(self.handle, name.encode(), int(value)))
@@ -678,7 +679,8 @@ class StarryProcess(object):
         # long launch has a shorter tail than several short ones
         per = nt * ldk * 8 + 4 * 256 * 256 * 8
         if self._ctx.i8_planes(nt, self._B):   # digit planes of the INT8 path live next to K
-            per += self._ctx.i8_planes(nt, self._B) * (nt + 64) * (nt + 64)
+            code = self._ctx.i8_planes(nt, self._B)   # 7 | 8 | 77 | 78 | 87: the first digit is the plane count
+            per += (code // 10 if code > 10 else code) * (nt + 64) * (nt + 64)
         # (the assembly / GEMM kernels carry the batch in grid.y: at most 65535 elements a launch)
         step = max(1, min(self._B, self._max_chunk_bytes // per, 65535))
         nchunks = -(-self._B // step)
