@@ -276,8 +276,10 @@ int spb_cholesky_lnlike_affine(spb_context *ctx, int B, int nt, double *K, int l
 
 /* The same log-likelihood with the panel updates of the factorisation evaluated on the INT8 tensor
  * cores (tcgen05.mma.kind::i8, accumulators in TMEM) from 7-bit digit planes of L -- an error-free
- * (Ozaki-style) emulation of the FP64 products: `planes` = 8 carries 56 bits relative to each row's
- * maximum, i.e. results at the rounding-noise level of the FP64 kernel (7: 49 bits).  Replaces the same
+ * (Ozaki-style) emulation of the FP64 products.  `planes`: 78 = seven planes of balanced 8-bit digits
+ * (55 bits relative to each row's maximum: results at the rounding-noise level of the FP64 kernel, 28
+ * plane products -- the fastest), 8 or 87 = eight planes of 7-bit digits (56 bits, 36 products), 7 or 77 =
+ * seven planes of 7-bit digits (49 bits).  Replaces the same
  * reference lines as spb_cholesky_lnlike_affine (math.py:75-100, sp.py:1154-1188).  Differences:
  *   K is only READ (the factor is not returned);  a lower bound of the smallest eigenvalue of K' is
  *   needed to scale the right-hand-side rows: `lambda_min` > 0 (e.g. the white-noise variance already
