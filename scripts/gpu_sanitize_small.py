@@ -37,3 +37,16 @@ ctx.set_option("cholesky_tile", 0)
 ctx.set_option("cholesky_cluster", 1)
 torch.cuda.synchronize()
 print("done round 2")
+# round 2: Cholesky on the INT8 tensor cores (tcgen05 / TMEM / 4-D TMA), all three digit formats, both branches,
+# sizes with a partial last panel, the "gap" and the padded layouts of the right-hand-side planes
+for code in (78, 87, 77):
+    ctx.set_option("cholesky_i8", code)
+    for marg in (True, False):
+        gi = spb.StarryProcess(r=[12.0, 20.0, 15.0], mu=[30.0, 50.0, 10.0], sigma=[5.0, 10.0, 20.0],
+                               c=[0.1, 0.05, 0.2], n=[10.0, 3.0, 5.0], marginalize_over_inclination=marg)
+        print("i8", code, marg, gi.log_likelihood(t, f, 1e-6, i=60.0, p=1.0, u=[0.4, 0.26]).cpu().numpy())
+    fm = np.stack([f + 1e-4 * k for k in range(30)])       # 30 light curves: more rows than the gap holds
+    print("i8 M=30", code, gi.log_likelihood(t, fm, 1e-6, i=60.0, p=1.0, u=[0.4, 0.26]).cpu().numpy())
+ctx.set_option("cholesky_i8", -1)
+torch.cuda.synchronize()
+print("done int8")

@@ -1761,6 +1761,9 @@ extern "C" int spb_cholesky_lnlike_affine(spb_context *ctx, int B, int nt, doubl
 }
 
 // ---- INT8-tensor-core path (potrf_i8.cuh) ----------------------------------------------------------
+#ifndef I8_ST7
+#define I8_ST7 3   // ring stages of the 7-plane kernels
+#endif
 static inline int i8_n64(int nt) { return (nt + NB - 1) & ~(NB - 1); }
 
 // `planes` of the C ABI: 8 (= 87) eight planes of 7-bit digits, 7 (= 77) seven planes of 7-bit digits,
@@ -1868,10 +1871,10 @@ extern "C" int spb_cholesky_lnlike_i8(spb_context *ctx, int B, int nt, double *K
     const int st = spb_once_per_device(attr_once, ctx->device, [&]() -> int {
       SPB_CHECK_CUDA(cudaFuncSetAttribute(potrf_i8_kernel<8, 3, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           (int)sizeof(SmemI8<8, 3>)));
-      SPB_CHECK_CUDA(cudaFuncSetAttribute(potrf_i8_kernel<7, 3, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          (int)sizeof(SmemI8<7, 3>)));
-      SPB_CHECK_CUDA(cudaFuncSetAttribute(potrf_i8_kernel<7, 3, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          (int)sizeof(SmemI8<7, 3>)));
+      SPB_CHECK_CUDA(cudaFuncSetAttribute(potrf_i8_kernel<7, I8_ST7, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)sizeof(SmemI8<7, I8_ST7>)));
+      SPB_CHECK_CUDA(cudaFuncSetAttribute(potrf_i8_kernel<7, I8_ST7, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)sizeof(SmemI8<7, I8_ST7>)));
       SPB_CHECK_CUDA(cudaFuncSetAttribute(potrf_lnlike_kernel<128, 3, 2>,
                                           cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           (int)sizeof(Smem<128, 3>)));
@@ -1886,9 +1889,9 @@ extern "C" int spb_cholesky_lnlike_i8(spb_context *ctx, int B, int nt, double *K
   if (planes == 8)
     potrf_i8_kernel<8, 3, 7><<<grid, I8_NTHREADS, sizeof(SmemI8<8, 3>), (cudaStream_t)stream>>>(p, ip, tmA, tmB);
   else if (rb == 7)
-    potrf_i8_kernel<7, 3, 7><<<grid, I8_NTHREADS, sizeof(SmemI8<7, 3>), (cudaStream_t)stream>>>(p, ip, tmA, tmB);
+    potrf_i8_kernel<7, I8_ST7, 7><<<grid, I8_NTHREADS, sizeof(SmemI8<7, I8_ST7>), (cudaStream_t)stream>>>(p, ip, tmA, tmB);
   else
-    potrf_i8_kernel<7, 3, 8><<<grid, I8_NTHREADS, sizeof(SmemI8<7, 3>), (cudaStream_t)stream>>>(p, ip, tmA, tmB);
+    potrf_i8_kernel<7, I8_ST7, 8><<<grid, I8_NTHREADS, sizeof(SmemI8<7, I8_ST7>), (cudaStream_t)stream>>>(p, ip, tmA, tmB);
   SPB_LAUNCH_CHECK(ctx);
   // safety net: matrices flagged SPB_INFO_I8_RANGE go through the FP64 kernel (their K is intact)
   {
