@@ -595,7 +595,10 @@ __global__ void __launch_bounds__(I8_NTHREADS, 1)
           fence_proxy_async_global();
           __threadfence_block();
           cbar256();
-          if (tid == 0) sm.stored = seq + 1;
+          if (tid == 0) {
+            __threadfence_block();   // the barrier's view of the other warps' stores before the counter moves
+            sm.stored = seq + 1;
+          }
           I8_PROF(sm, 6);
         }
       }

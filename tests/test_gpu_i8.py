@@ -155,3 +155,39 @@ def test_i8_not_positive_definite_element(spb):
     ok = [0, 1, 3]
     assert np.all(b["info"][ok] == 0)
     assert np.max(np.abs(a["ll"][ok] - b["ll"][ok]) / np.abs(a["ll"][ok])) < 2e-11
+
+
+def test_i8_kernel_is_deterministic_under_load(spb):
+    """The producer thread reads digit planes that the compute warps of the same CTA stored a tile earlier
+    (stored-tile counter + generic -> async proxy fence): 12 launches over 600 matrices (4 per SM, dynamic
+    work claiming) must return bit-identical lnlike vectors -- a lost ordering would show up as a stale
+    plane in some matrix of some launch."""
+    from starry_process_b200 import _lib
+
+    ctx = spb.get_context()
+    lib, h = ctx.lib, ctx.handle
+    dev = torch.device("cuda")
+    B, n, M = 600, 1000, 1
+    g = torch.Generator(device="cuda").manual_seed(3)
+    A = torch.randn(B, n, 16, dtype=torch.float64, device=dev, generator=g)
+    K = torch.bmm(A, A.transpose(1, 2)) / 16.0
+    r0 = 0.01 * torch.randn(B, 1, n, dtype=torch.float64, device=dev, generator=g)
+    dgt = torch.full((1,), 1e-4, dtype=torch.float64, device=dev)
+    af = _lib.Affine()
+    af.diag, af.diag_kind, af.diag_stride = dgt.data_ptr(), 0, 0
+    nb = lib.spb_cholesky_i8_workspace_bytes(B, n, M, 78)
+    ws = torch.empty(nb, dtype=torch.uint8, device=dev)
+    first = None
+    for rep in range(12):
+        ws.random_(0, 255)            # stale planes from the previous launch must never be read
+        ll = torch.zeros(B, dtype=torch.float64, device=dev)
+        info = torch.zeros(B, dtype=torch.int32, device=dev)
+        r = r0.clone()
+        _lib.check(lib.spb_cholesky_lnlike_i8(h, B, n, P(K), n, n * n, ctypes.byref(af), M, P(r), n, n, P(ll),
+                                              None, None, P(info), 78, 0.0, P(ws), nb, None))
+        torch.cuda.synchronize()
+        assert int(info.abs().sum()) == 0
+        if first is None:
+            first = ll.clone()
+        else:
+            assert torch.equal(first, ll), "launch %d differs" % rep
