@@ -483,7 +483,13 @@ __global__ void __launch_bounds__(I8_NTHREADS, 1)
           if (diag_tile) {
             if (lw < 4) {
               quiet_enter(&sm.quiet, lane, (ip.gate & 1) != 0);
+#ifdef SPB_POTRF_PROF
+              const unsigned long long t8_before = sm.prof[0][11];
+#endif
               potf2_regs(sm, acc, lw, lane);
+#ifdef SPB_POTRF_PROF
+              if (tid == 0 && c0 == 0) sm.prof[0][15] += sm.prof[0][11] - t8_before;   // pivot chains of panel 0
+#endif
               quiet_leave(&sm.quiet, lane, (ip.gate & 1) != 0);
             }
             cbar256();   // L_jj and the inverses of its diagonal tiles are in shared memory
