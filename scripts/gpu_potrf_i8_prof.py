@@ -46,7 +46,8 @@ def run(B, n, M=1, planes=8):
     for k, name in CN.items():
         print("     %-26s %9.1f kclk/matrix  %5.1f%%" % (name, v[0, k] / nm / 1e3, 100 * v[0, k] / tot))
     for k, name in {11: "d:tile8", 12: "d:defer+bar1", 13: "d:trsm+bar2", 14: "d:crit_upd",
-                    15: "d:tile8 of panel 0 only (no MMA / TMA in flight)"}.items():
+                    15: "d:tile8 of panel 0 only (no MMA / TMA in flight)",
+                    9: "init_acc of panel 0 only (8 of the 68 tiles)"}.items():
         print("       %-24s %9.1f kclk/matrix" % (name, v[0, k] / nm / 1e3))
     for k, name in IN.items():
         print("     %-26s %9.1f kclk/matrix" % (name, v[1, k] / nm / 1e3))

@@ -240,35 +240,12 @@ __device__ __forceinline__ double aff_apply(const SM &sm, const AffRow &af, doub
   return k;
 }
 
-template <class SM, class RM>
-__device__ __forceinline__ void init_acc(const SM &sm, const RM &rm, const AffRow &af, bool aff_on,
-                                         int v, int c0, int tg, bool full, double (&accrow)[8][2]) {
-  int kind;
-  const double *p = rm.row(v, kind);
-  const bool cov_row = aff_on && (kind == KIND_DIAG || kind == KIND_BELOW);
-  const int gi = c0 + v;  // global row of a covariance row (diagonal-block and below rows alike)
-  double Ci = 0.0, Di = 0.0;
-  if (cov_row) {
-    Ci = sm.af[3];
-    if (af.norm) {
-      const double qi = af.q[gi];
-      const double a = sm.af[1] * (1.0 - qi);
-      Ci += a;
-      Di = a + sm.af[2] * qi;
-    }
-  }
-  const bool diag_row = (kind == KIND_DIAG);
-  if (full) {
-    if (p == nullptr) p = rm.Kb;
-    // all global loads first (no dependent instruction or branch in between: one batch of
-    // outstanding requests per tile), then the branch-free affine arithmetic
-#pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
-      const double2 kv = *reinterpret_cast<const double2 *>(p + c0 + nt * 8 + 2 * tg);
-      accrow[nt][0] = kv.x;
-      accrow[nt][1] = kv.y;
-    }
-    if (cov_row) {
+// The affine arithmetic of a full-panel covariance row (rows of the diagonal block and below it), applied
+// to accumulators that hold the raw K values: see aff_apply.
+template <class SM>
+__device__ __forceinline__ void aff_full_row(const SM &sm, const AffRow &af, bool diag_row, int gi, int v,
+                                             int c0, int tg, double Ci, double Di, double (&accrow)[8][2]) {
+  {
       if (af.norm) {
         const double s1 = sm.af[0];
         const double *qp = af.q + c0 + 2 * tg;
@@ -307,6 +284,37 @@ __device__ __forceinline__ void init_acc(const SM &sm, const RM &rm, const AffRo
         }
       }
     }
+}
+
+template <class SM, class RM>
+__device__ __forceinline__ void init_acc(const SM &sm, const RM &rm, const AffRow &af, bool aff_on,
+                                         int v, int c0, int tg, bool full, double (&accrow)[8][2]) {
+  int kind;
+  const double *p = rm.row(v, kind);
+  const bool cov_row = aff_on && (kind == KIND_DIAG || kind == KIND_BELOW);
+  const int gi = c0 + v;  // global row of a covariance row (diagonal-block and below rows alike)
+  double Ci = 0.0, Di = 0.0;
+  if (cov_row) {
+    Ci = sm.af[3];
+    if (af.norm) {
+      const double qi = af.q[gi];
+      const double a = sm.af[1] * (1.0 - qi);
+      Ci += a;
+      Di = a + sm.af[2] * qi;
+    }
+  }
+  const bool diag_row = (kind == KIND_DIAG);
+  if (full) {
+    if (p == nullptr) p = rm.Kb;
+    // all global loads first (no dependent instruction or branch in between: one batch of
+    // outstanding requests per tile), then the branch-free affine arithmetic
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      const double2 kv = *reinterpret_cast<const double2 *>(p + c0 + nt * 8 + 2 * tg);
+      accrow[nt][0] = kv.x;
+      accrow[nt][1] = kv.y;
+    }
+    if (cov_row) aff_full_row(sm, af, diag_row, gi, v, c0, tg, Ci, Di, accrow);
     return;
   }
 #pragma unroll
@@ -1761,9 +1769,6 @@ extern "C" int spb_cholesky_lnlike_affine(spb_context *ctx, int B, int nt, doubl
 }
 
 // ---- INT8-tensor-core path (potrf_i8.cuh) ----------------------------------------------------------
-#ifndef I8_ST7
-#define I8_ST7 3   // ring stages of the 7-plane kernels
-#endif
 static inline int i8_n64(int nt) { return (nt + NB - 1) & ~(NB - 1); }
 
 // `planes` of the C ABI: 8 (= 87) eight planes of 7-bit digits, 7 (= 77) seven planes of 7-bit digits,
@@ -1869,12 +1874,16 @@ extern "C" int spb_cholesky_lnlike_i8(spb_context *ctx, int B, int nt, double *K
   static spb_once_flag attr_once;
   {
     const int st = spb_once_per_device(attr_once, ctx->device, [&]() -> int {
-      SPB_CHECK_CUDA(cudaFuncSetAttribute(potrf_i8_kernel<8, 3, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          (int)sizeof(SmemI8<8, 3>)));
-      SPB_CHECK_CUDA(cudaFuncSetAttribute(potrf_i8_kernel<7, I8_ST7, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          (int)sizeof(SmemI8<7, I8_ST7>)));
-      SPB_CHECK_CUDA(cudaFuncSetAttribute(potrf_i8_kernel<7, I8_ST7, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          (int)sizeof(SmemI8<7, I8_ST7>)));
+#define SPB_I8_ATTR(S_, ST_, RB_, KP_)                                                                  \
+  SPB_CHECK_CUDA(cudaFuncSetAttribute(potrf_i8_kernel<S_, ST_, RB_, KP_>,                               \
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize,                      \
+                                      (int)sizeof(SmemI8<S_, ST_, KP_>)))
+      SPB_I8_ATTR(8, 3, 7, false);
+      SPB_I8_ATTR(7, 3, 7, false);
+      SPB_I8_ATTR(7, 3, 8, false);
+      SPB_I8_ATTR(7, 2, 7, true);
+      SPB_I8_ATTR(7, 2, 8, true);
+#undef SPB_I8_ATTR
       SPB_CHECK_CUDA(cudaFuncSetAttribute(potrf_lnlike_kernel<128, 3, 2>,
                                           cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           (int)sizeof(Smem<128, 3>)));
@@ -1886,12 +1895,17 @@ extern "C" int spb_cholesky_lnlike_i8(spb_context *ctx, int B, int nt, double *K
   p.counter = ctx->d_counters +
       (__atomic_fetch_add(&ctx->counter_next, 1u, __ATOMIC_RELAXED) % SPB_NUM_COUNTERS);
   SPB_CHECK_CUDA(cudaMemsetAsync(p.counter, 0, sizeof(unsigned int), (cudaStream_t)stream));
-  if (planes == 8)
-    potrf_i8_kernel<8, 3, 7><<<grid, I8_NTHREADS, sizeof(SmemI8<8, 3>), (cudaStream_t)stream>>>(p, ip, tmA, tmB);
-  else if (rb == 7)
-    potrf_i8_kernel<7, I8_ST7, 7><<<grid, I8_NTHREADS, sizeof(SmemI8<7, I8_ST7>), (cudaStream_t)stream>>>(p, ip, tmA, tmB);
-  else
-    potrf_i8_kernel<7, I8_ST7, 8><<<grid, I8_NTHREADS, sizeof(SmemI8<7, I8_ST7>), (cudaStream_t)stream>>>(p, ip, tmA, tmB);
+  // 7-plane kernels, nt <= 1536: two ring stages + the cp.async prefetch of the next K tile (the per-tile
+  // chain dominates there); larger nt: three ring stages (the MMA stream dominates, -8 % with two)
+  const bool kpre = (planes == 7) && nt <= 1536 && !getenv("SPB_I8_NO_KPRE");
+#define SPB_I8_GO(S_, ST_, RB_, KP_)                                                                    \
+  potrf_i8_kernel<S_, ST_, RB_, KP_><<<grid, I8_NTHREADS, sizeof(SmemI8<S_, ST_, KP_>), (cudaStream_t)stream>>>(p, ip, tmA, tmB)
+  if (planes == 8) SPB_I8_GO(8, 3, 7, false);
+  else if (rb == 7 && kpre) SPB_I8_GO(7, 2, 7, true);
+  else if (rb == 7) SPB_I8_GO(7, 3, 7, false);
+  else if (kpre) SPB_I8_GO(7, 2, 8, true);
+  else SPB_I8_GO(7, 3, 8, false);
+#undef SPB_I8_GO
   SPB_LAUNCH_CHECK(ctx);
   // safety net: matrices flagged SPB_INFO_I8_RANGE go through the FP64 kernel (their K is intact)
   {

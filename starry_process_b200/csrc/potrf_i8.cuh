@@ -109,7 +109,7 @@ struct RowMapI8 {
   }
 };
 
-template <int S_, int STAGES_>
+template <int S_, int STAGES_, bool KPRE_ = false>
 struct SmemI8 {
   using G = Geo<128>;
   static constexpr int S = S_;
@@ -117,6 +117,9 @@ struct SmemI8 {
   static constexpr int NTHREADS = I8_NCT;
   uint8_t A[STAGES_][S_][I8_TM][I8_KCH];   // 4 KB per plane
   uint8_t B[STAGES_][S_][NB][I8_KCH];      // 2 KB per plane; planes t0..t1 form one N = 64 (t1 - t0 + 1) operand
+  // KPRE: the 128 x 64 K tile of the NEXT tile, copied by cp.async while the current one is processed; chunk c
+  // (of 16) of thread t at [(c * 256 + t)]: every thread reads back what it copied, conflict-free both ways
+  double2 Kpre[KPRE_ ? 16 * I8_NCT : 1];
   LdStore<false> Ld;
   double Dv[NB][DS];
   double red[I8_NCT / 32];
@@ -212,6 +215,25 @@ __device__ __forceinline__ double pow2_above(double x) {
   return ldexp(1.0, ex);
 }
 
+// The fused affine map (spb_affine) of one accumulator row that holds RAW values of a full panel (the
+// arithmetic half of init_acc; used when the values come from the cp.async prefetch buffer).
+template <class SM>
+__device__ __forceinline__ void i8_apply_aff(const SM &sm, const RowMapI8 &rm, const AffRow &af, int v, int c0,
+                                             int tg, double (&accrow)[8][2]) {
+  int kind;
+  (void)rm.row(v, kind);
+  if (kind != KIND_DIAG && kind != KIND_BELOW) return;
+  const int gi = c0 + v;
+  double Ci = sm.af[3], Di = 0.0;
+  if (af.norm) {
+    const double qi = af.q[gi];
+    const double a = sm.af[1] * (1.0 - qi);
+    Ci += a;
+    Di = a + sm.af[2] * qi;
+  }
+  aff_full_row(sm, af, kind == KIND_DIAG, gi, v, c0, tg, Ci, Di, accrow);
+}
+
 template <class SM>
 __device__ __forceinline__ double block_sum_i8(SM &sm, double v) {
   const int tid = threadIdx.x, pw = tid >> 5, lane = tid & 31;
@@ -256,13 +278,13 @@ __device__ __forceinline__ int i8_nvirt(int n, int n64, int M, bool gap, int c0)
 }
 __device__ __forceinline__ int i8_ntiles(int nvirt) { return (nvirt + I8_TM - 1) / I8_TM; }
 
-template <int S, int STAGES, int RB>
+template <int S, int STAGES, int RB, bool KPRE>
 __global__ void __launch_bounds__(I8_NTHREADS, 1)
     potrf_i8_kernel(PotrfParams p, I8Params ip, const __grid_constant__ CUtensorMap tmA,
                     const __grid_constant__ CUtensorMap tmB) {
   constexpr int D = S - 1;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
-  using SM = SmemI8<S, STAGES>;
+  using SM = SmemI8<S, STAGES, KPRE>;
   SM &sm = *reinterpret_cast<SM *>(smem_raw);
   const int tid = threadIdx.x, pw = tid >> 5, lane = tid & 31, g = lane >> 2, tg = lane & 3;
   // TMEM lanes a warp may read: 32 (pw % 4) .. + 31; the fragment-shaped loads take 16 of them, so compute
@@ -397,6 +419,7 @@ __global__ void __launch_bounds__(I8_NTHREADS, 1)
       double logdet_part = 0.0, quad_part = 0.0;
       double acc[2][8][2];
       bool bad_range = false;
+      bool have_pre = false;   // KPRE: the prefetch buffer holds this tile's raw values (block-uniform)
       unsigned seq = seq_base;
       for (int c0 = 0; c0 < p.n; c0 += NB) {
         rm.c0 = c0;
@@ -408,12 +431,30 @@ __global__ void __launch_bounds__(I8_NTHREADS, 1)
         for (int v0 = 0; v0 < nvirt; v0 += I8_TM, ++seq) {
           const bool diag_tile = (v0 == 0);
           const int vr = v0 + warp * 16;            // first tile row of this warp
+          if (KPRE && have_pre) {
+            // the raw K (or right-hand-side) values of this tile were copied to shared memory during the
+            // previous tile: pick them up and apply the affine map
+            cp_async_wait<0>();
 #pragma unroll
-          for (int mt = 0; mt < 2; ++mt)
-            init_acc(sm, rm, af, p.aff_on != 0, vr + mt * 8 + g, c0, tg, full_panel, acc[mt]);
+            for (int mt = 0; mt < 2; ++mt) {
+#pragma unroll
+              for (int nt = 0; nt < 8; ++nt) {
+                const double2 kv = sm.Kpre[(mt * 8 + nt) * I8_NCT + tid];
+                acc[mt][nt][0] = kv.x;
+                acc[mt][nt][1] = kv.y;
+              }
+              if (p.aff_on) i8_apply_aff(sm, rm, af, vr + mt * 8 + g, c0, tg, acc[mt]);
+            }
+          } else {
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt)
+              init_acc(sm, rm, af, p.aff_on != 0, vr + mt * 8 + g, c0, tg, full_panel, acc[mt]);
+          }
           {
-            // the K rows of the NEXT tile are read exactly once, from HBM, at the top of that tile: ask
-            // for them now (one 128-byte line per lane and row) so that they wait in L2
+            // the K rows of the NEXT tile are read exactly once, from HBM, and their latency (3 us per tile
+            // when loaded at the top of the tile) is the largest single item of the per-tile chain: with
+            // KPRE they are copied now by cp.async (per thread: its own 16 x 16 bytes) and waited for at the
+            // top of the next tile; without, at least requested into L2
             RowMapI8 rn = rm;
             int v0n = v0 + I8_TM;
             if (v0n >= nvirt) {
@@ -421,16 +462,37 @@ __global__ void __launch_bounds__(I8_NTHREADS, 1)
               rn.c0 = c0 + NB;
               rn.nbel = i8_nbel(p.n, n64, gap, rn.c0);
             }
+            have_pre = false;
             if (rn.c0 < p.n) {
+              if (KPRE) {
+                if (rn.c0 + NB <= p.n) {      // full panels only (block-uniform)
 #pragma unroll
-              for (int mt = 0; mt < 2; ++mt) {
-                int kind;
-                const double *pn = rn.row(v0n + warp * 16 + mt * 8 + g, kind);
-                if (pn != nullptr && rn.c0 + 16 * tg < p.n)
-                  asm volatile("prefetch.global.L2 [%0];\n" ::"l"(pn + rn.c0 + 16 * tg));
+                  for (int mt = 0; mt < 2; ++mt) {
+                    int kind;
+                    const double *pn = rn.row(v0n + warp * 16 + mt * 8 + g, kind);
+                    const int bytes = pn ? 16 : 0;
+                    const double *src = (pn ? pn : rn.Kb) + rn.c0 + 2 * tg;
+#pragma unroll
+                    for (int nt = 0; nt < 8; ++nt)
+                      cp_async16(&sm.Kpre[(mt * 8 + nt) * I8_NCT + tid], src + nt * 8, bytes);
+                  }
+                  cp_async_commit();
+                  have_pre = true;
+                }
+              } else {
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt) {
+                  int kind;
+                  const double *pn = rn.row(v0n + warp * 16 + mt * 8 + g, kind);
+                  if (pn != nullptr && rn.c0 + 16 * tg < p.n)
+                    asm volatile("prefetch.global.L2 [%0];\n" ::"l"(pn + rn.c0 + 16 * tg));
+                }
               }
             }
           }
+#ifdef SPB_POTRF_PROF
+          if (tid == 0 && c0 == 0) sm.prof[0][9] += clock64() - _it;   // K loads of panel 0 (no MMA / TMA in flight)
+#endif
           I8_PROF(sm, 0);
           if (nchunks > 0) {
             // scales of this thread's rows (plane row = c0 + virtual row for matrix and RHS rows alike)
