@@ -7,9 +7,10 @@
 // micro-benchmark: scripts/micro/i8_emul_micro.cu):
 //
 //   * every stored row of L (and of the appended right-hand sides y = L^-1 r) is scaled by a power of
-//     two 2^-e_i fixed before the factorisation starts, rounded to S x 7 bits and cut into S signed
-//     7-bit digits  L_ik 2^-e_i = sum_s d_s(i,k) 2^{-7 (s+1)};  the digits are stored as S int8 PLANES
-//     next to K (same footprint: 8 planes = 8 bytes per entry);
+//     two 2^-e_i fixed before the factorisation starts, rounded to S x RB bits and cut into S signed
+//     RB-bit digits  L_ik 2^-e_i = sum_s d_s(i,k) 2^{-RB (s+1)};  the digits are stored as S int8 PLANES
+//     next to K.  Default: S = 7 planes of balanced RB = 8-bit digits (55 bits per row, 28 plane
+//     products); S = 8 x RB = 7 (56 bits, 36 products) and S = 7 x RB = 7 (49 bits) are kept;
 //   * for a 128 x 64 tile of the panel, one thread issues  tcgen05.mma.kind::i8  products of digit plane
 //     A_s (128 x 32 bytes of k) with the concatenated planes B_0 .. B_{D-s} (N up to 256) into TMEM:
 //     pairs with s + t = d accumulate EXACTLY (int32) in the 64-column block d, all 512 columns of an SM
@@ -17,7 +18,8 @@
 //     memory ring; the tensor core runs from smem descriptors, so no warp touches the operands;
 //   * the 8 compute warps read the S blocks back with fragment-shaped tcgen05.ld (16x256b: the same
 //     (row g, columns 2 tg) layout as the DMMA accumulators), combine them in fp64
-//     (Horner in 2^-7), apply the row scales and subtract from the K values they loaded meanwhile;
+//     (Horner in 2^-RB), apply the row scales and subtract from the K values of the tile (copied to
+//     shared memory by cp.async during the previous tile when nt <= 1536, loaded directly otherwise);
 //     from there on the tile is the round-1 kernel's: in-register potf2 of the diagonal block, in-register
 //     TRSM on DMMA, |y|^2 and log-determinant reductions;
 //   * the new rows of L are cut into digit planes straight from the accumulator registers and stored;
@@ -25,9 +27,9 @@
 //     tiles), so the MMA stream of the next tile -- and of the next PANEL, up to its last two k-chunks --
 //     runs while the warps are still in the TRSM / stores of the current one (look-ahead for free).
 //
-// With S = 8, D = 7 the update carries 56 bits relative to the row maximum: the lnlike differences to
-// the DMMA kernel are at the level of fp64 rounding noise (1e-13 .. 4e-12 relative on the bench
-// covariances, cond 1e4 .. 2e7).  K itself is only READ.
+// With 55 / 56 bits relative to the row maximum the lnlike differences to the DMMA kernel are at the level of
+// fp64 rounding noise (<= 3.8e-12 / 1.2e-12 relative on the bench covariances, cond 1e3 .. 2e7).  K itself is
+// only READ.
 //
 // Safety net: a digit that does not fit (a row bound violated: cannot happen for rows of L, and for
 // the right-hand-side rows only if K' - diag were indefinite by more than 15/16 of diag) sets
