@@ -186,6 +186,11 @@ size_t spb_flux_conditional_workspace_bytes(const spb_context *ctx, int B, int n
 int spb_flux_conditional(spb_context *ctx, int B, int nt, const double *A, long long A_stride,
                          const double *mean_ylm, const double *cov_ylm, double *gp_mean, double *K,
                          int ldk, void *workspace, size_t workspace_bytes, void *stream);
+/* Same, but only the lower triangle (and the diagonal) of K is written: for callers that factorise K
+ * next (flux.py:335-343 feeding sp.py:1135-1176); the strict upper triangle is left untouched. */
+int spb_flux_conditional_lower(spb_context *ctx, int B, int nt, const double *A, long long A_stride,
+                         const double *mean_ylm, const double *cov_ylm, double *gp_mean, double *K,
+                         int ldk, void *workspace, size_t workspace_bytes, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
  * (a17, a19, a21) assemble the GP covariance that is factorised:

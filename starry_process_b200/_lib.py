@@ -70,6 +70,7 @@ PROTOTYPES = {
     "spb_flux_marginal": (_I, [_P, _I, _P, _P, _P, _I, _P, _P, _P, _P, _SZ, _P]),
     "spb_flux_conditional_workspace_bytes": (_SZ, [_P, _I, _I]),
     "spb_flux_conditional": (_I, [_P, _I, _I, _P, _LL, _P, _P, _P, _P, _I, _P, _SZ, _P]),
+    "spb_flux_conditional_lower": (_I, [_P, _I, _I, _P, _LL, _P, _P, _P, _P, _I, _P, _SZ, _P]),
     "spb_assemble_workspace_bytes": (_SZ, [_P, _I, _I]),
     "spb_assemble_marginal": (_I, [_P, _I, _I, _P, _D, _I, _P, _P, _P, _c.POINTER(NoiseModel),
                                    _P, _I, _P, _P, _P, _SZ, _P]),

@@ -326,10 +326,10 @@ extern "C" size_t spb_flux_conditional_workspace_bytes(const spb_context *ctx, i
   return (size_t)Bc * nt * 256 * 8 + 1024;
 }
 
-extern "C" int spb_flux_conditional(spb_context *ctx, int B, int nt, const double *A,
-                                    long long A_stride, const double *mean_ylm,
-                                    const double *cov_ylm, double *gp_mean, double *K, int ldk,
-                                    void *workspace, size_t workspace_bytes, void *stream_) {
+static int flux_conditional_impl(spb_context *ctx, int B, int nt, const double *A, long long A_stride,
+                                 const double *mean_ylm, const double *cov_ylm, double *gp_mean, double *K,
+                                 int ldk, void *workspace, size_t workspace_bytes, void *stream_,
+                                 bool lower_only) {
   SPB_REQUIRE(ctx != nullptr && B > 0 && nt > 0, "flux_conditional: bad arguments");
   SPB_REQUIRE(workspace != nullptr &&
                   workspace_bytes >= spb_flux_conditional_workspace_bytes(ctx, B, nt),
@@ -361,7 +361,9 @@ extern "C" int spb_flux_conditional(spb_context *ctx, int B, int nt, const doubl
     d1.alpha = 1.0;
     int st = gnt::launch<gnt::EPI_STORE>(ctx, d1, stream);
     if (st) return st;
-    // K[b] = T[b] A^T, lower tiles mirrored
+    // K[b] = T[b] A^T: lower tiles, mirrored into the upper triangle unless the caller only needs the
+    // lower one (the log-likelihood path: the Cholesky kernels never read above the diagonal, and the
+    // mirror is 134 MB of strided 8-byte stores per nt = 4096 sample)
     gnt::Desc d2 = {};
     d2.A = T;
     d2.strideA = (long long)nt * 256;
@@ -379,8 +381,25 @@ extern "C" int spb_flux_conditional(spb_context *ctx, int B, int nt, const doubl
     d2.ksplit = 1;
     d2.lower_only = 1;
     d2.alpha = 1.0;
-    st = gnt::launch<gnt::EPI_MIRROR>(ctx, d2, stream);
+    st = lower_only ? gnt::launch<gnt::EPI_STORE>(ctx, d2, stream)
+                    : gnt::launch<gnt::EPI_MIRROR>(ctx, d2, stream);
     if (st) return st;
   }
   return 0;
+}
+
+extern "C" int spb_flux_conditional(spb_context *ctx, int B, int nt, const double *A,
+                                    long long A_stride, const double *mean_ylm,
+                                    const double *cov_ylm, double *gp_mean, double *K, int ldk,
+                                    void *workspace, size_t workspace_bytes, void *stream_) {
+  return flux_conditional_impl(ctx, B, nt, A, A_stride, mean_ylm, cov_ylm, gp_mean, K, ldk, workspace,
+                               workspace_bytes, stream_, false);
+}
+
+extern "C" int spb_flux_conditional_lower(spb_context *ctx, int B, int nt, const double *A,
+                                          long long A_stride, const double *mean_ylm,
+                                          const double *cov_ylm, double *gp_mean, double *K, int ldk,
+                                          void *workspace, size_t workspace_bytes, void *stream_) {
+  return flux_conditional_impl(ctx, B, nt, A, A_stride, mean_ylm, cov_ylm, gp_mean, K, ldk, workspace,
+                               workspace_bytes, stream_, true);
 }

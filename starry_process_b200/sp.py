@@ -609,6 +609,7 @@ class StarryProcess(object):
         dev = self.device
         keep = []
         nm = self._noise_model(nt, data_cov, baseline_var, keep, lower_only and marg, b0=b0)
+        defer_req = bool(defer)
         defer = bool(defer and marg and lower_only and nm.data_kind != 2 and nm.base_kind != 2)
         nm.defer = 1 if defer else 0
         mean_ylm = self._mean_ylm[b0:b1]
@@ -648,16 +649,23 @@ class StarryProcess(object):
                                              0, _ptr(A), _ptr(wsd), nbd, _stream()))
             nb = lib.spb_flux_conditional_workspace_bytes(h, Bc, nt)
             ws = torch.empty(nb, dtype=torch.uint8, device=dev)
-            _lib.check(lib.spb_flux_conditional(h, Bc, nt, _ptr(A), 0 if Ic == 1 else nt * 256,
-                                                _ptr(mean_ylm), _ptr(cov_ylm), _ptr(gp_mean),
-                                                _ptr(K), ldk, _ptr(ws), nb, _stream()))
-            if self._tkind:   # sp.py:697-698
+            # log-likelihood path of an unnormalised, static process: only the lower triangle is needed and
+            # the noise terms are added inside the Cholesky kernel's loads (no read-modify-write pass)
+            defer_c = bool(defer_req and lower_only and not self._normalized and not self._tkind
+                           and nm.data_kind != 2 and nm.base_kind != 2)
+            fc = lib.spb_flux_conditional_lower if defer_c else lib.spb_flux_conditional
+            _lib.check(fc(h, Bc, nt, _ptr(A), 0 if Ic == 1 else nt * 256, _ptr(mean_ylm), _ptr(cov_ylm),
+                          _ptr(gp_mean), _ptr(K), ldk, _ptr(ws), nb, _stream()))
+            if defer_c:
+                defer = True
+            elif self._tkind:   # sp.py:697-698
                 _lib.check(lib.spb_temporal_scale(h, Bc, nt, nt, _ptr(t), _ptr(t), self._tkind,
                                                   _ptr(self._tau[b0:b1].contiguous()), 1, None, 0,
                                                   _ptr(K), ldk, nt * ldk, _stream()))
-            _lib.check(lib.spb_assemble_conditional(h, Bc, nt, _ptr(gp_mean), ctypes.byref(nm),
-                                                    _ptr(K), ldk, _ptr(z), _ptr(info), _ptr(ws_as),
-                                                    nb_as, _stream()))
+            if not defer_c:
+                _lib.check(lib.spb_assemble_conditional(h, Bc, nt, _ptr(gp_mean), ctypes.byref(nm),
+                                                        _ptr(K), ldk, _ptr(z), _ptr(info), _ptr(ws_as),
+                                                        nb_as, _stream()))
         if defer:
             af = _lib.Affine()
             if self._normalized:
