@@ -27,6 +27,7 @@ struct spb_context {
   // run-time switches (spb_set_option): A/B measurements and the bit-for-bit stress tests
   int opt_no_tma;         // Cholesky operand ring: cp.async instead of TMA
   int opt_no_cluster;     // Cholesky: never use the one-matrix-per-cluster kernel
+  int opt_syrk_i8;        // second-moment SYRK of the Ylm moments on the INT8 tensor cores (syrk_i8.cu)
   int opt_chol_tile;      // Cholesky batch kernel: rows per tile, 64 (4 warps, 3 CTAs/SM) or 128
   int max_active_clusters[3];   // cudaOccupancyMaxActiveClusters for cluster sizes 8, 4, 2 (-1: unknown)
   // ring of work counters for kernels that claim their work items dynamically (one per launch,
@@ -59,6 +60,12 @@ int spb_encode_tmap_3d_f64(CUtensorMap *out, void *base, unsigned long long d0,
                            unsigned long long s2, unsigned b0, unsigned b1, unsigned b2);
 int spb_encode_tmap_u8_4d(CUtensorMap *out, void *base, const unsigned long long dims[4],
                           const unsigned long long strides[3], const unsigned box[4]);
+
+// syrk_i8.cu: cov[b] = scale[b] (ldeg[b] o (X[b] X[b]^T) - vec[b] vec[b]^T) + diag on the INT8 tensor cores
+size_t spb_syrk_i8_workspace_bytes(int Bc);
+int spb_syrk_i8(spb_context *ctx, int Bc, const double *X, const int *rkeep, const double *scale,
+                const double *vec, const double *diag, const double *ldeg, double *C, void *workspace,
+                cudaStream_t stream);
 
 #define SPB_CHECK_CUDA(expr)                                                          \
   do {                                                                                \

@@ -60,6 +60,7 @@ extern "C" int spb_create(int device, const double *tables_host, size_t tables_c
   ctx->d_scratch = nullptr;
   ctx->opt_no_tma = getenv("SPB_NO_TMA") != nullptr;          // defaults of the A/B switches
   ctx->opt_no_cluster = getenv("SPB_NO_CLUSTER") != nullptr;
+  ctx->opt_syrk_i8 = getenv("SPB_SYRK_I8") ? atoi(getenv("SPB_SYRK_I8")) : 0;
   ctx->opt_chol_tile = getenv("SPB_CHOL_TILE") ? atoi(getenv("SPB_CHOL_TILE")) : 0;   // 0: automatic
   for (int k = 0; k < 3; ++k) ctx->max_active_clusters[k] = -1;
   SPB_CHECK_CUDA(cudaMalloc(&ctx->d_counters, SPB_NUM_COUNTERS * sizeof(unsigned int)));
@@ -85,6 +86,10 @@ extern "C" void spb_destroy(spb_context *ctx) { spb_release(ctx); }
 extern "C" int spb_set_option(spb_context *ctx, const char *name, int value) {
   SPB_REQUIRE(ctx != nullptr && name != nullptr, "spb_set_option: null argument");
   const std::string key(name);
+  if (key == "moments_syrk_i8") {
+    ctx->opt_syrk_i8 = value ? 1 : 0;
+    return 0;
+  }
   if (key == "cholesky_tma") ctx->opt_no_tma = value ? 0 : 1;
   else if (key == "cholesky_cluster") ctx->opt_no_cluster = value ? 0 : 1;
   else if (key == "cholesky_tile") {

@@ -1094,6 +1094,7 @@ constexpr int MOM_CHUNK = 1024;  // samples per pass (bounds the sqrtC_lon works
 struct MomWs {
   double *mom1, *S_lat, *scale, *X, *Sred, *qs, *E2;
   int *rkeep;
+  void *i8ws;   // digit planes + row scales of the INT8 SYRK (one chunk)
 };
 
 size_t mom_ws_layout(int B, unsigned char *base, MomWs *ws) {
@@ -1112,8 +1113,10 @@ size_t mom_ws_layout(int B, unsigned char *base, MomWs *ws) {
   size_t o_Sred = take((size_t)B * 1024 * 8);
   size_t o_qs = take((size_t)B * 16 * 8);
   size_t o_E2 = take((size_t)B * 256 * 8);
+  size_t o_i8 = take(spb_syrk_i8_workspace_bytes(Bc));
   if (ws) {
     ws->E2 = reinterpret_cast<double *>(base + o_E2);
+    ws->i8ws = base + o_i8;
     ws->Sred = reinterpret_cast<double *>(base + o_Sred);
     ws->qs = reinterpret_cast<double *>(base + o_qs);
     ws->mom1 = reinterpret_cast<double *>(base + o_mom1);
@@ -1264,7 +1267,11 @@ static int moments_tail(spb_context *ctx, int B, K1Params &p1, MomWs &ws, double
     d.rkeep = ws.rkeep + b0;
     d.ldeg = has_dr ? ws.E2 + (size_t)b0 * 256 : nullptr;
     d.alpha = 1.0;
-    int st = gnt::launch<gnt::EPI_SYRK_COV>(ctx, d, stream);
+    int st;
+    if (ctx->opt_syrk_i8)
+      st = spb_syrk_i8(ctx, Bc, ws.X, d.rkeep, d.scale, d.vec, d.diag, d.ldeg, d.C, ws.i8ws, stream);
+    else
+      st = gnt::launch<gnt::EPI_SYRK_COV>(ctx, d, stream);
     if (st) return st;
   }
   return 0;
