@@ -60,7 +60,7 @@ extern "C" int spb_create(int device, const double *tables_host, size_t tables_c
   ctx->d_scratch = nullptr;
   ctx->opt_no_tma = getenv("SPB_NO_TMA") != nullptr;          // defaults of the A/B switches
   ctx->opt_no_cluster = getenv("SPB_NO_CLUSTER") != nullptr;
-  ctx->opt_syrk_i8 = getenv("SPB_SYRK_I8") ? atoi(getenv("SPB_SYRK_I8")) : 0;
+  ctx->opt_syrk_i8 = getenv("SPB_SYRK_I8") ? atoi(getenv("SPB_SYRK_I8")) : 1;   // default: INT8 tensor cores
   ctx->opt_chol_tile = getenv("SPB_CHOL_TILE") ? atoi(getenv("SPB_CHOL_TILE")) : 0;   // 0: automatic
   for (int k = 0; k < 3; ++k) ctx->max_active_clusters[k] = -1;
   SPB_CHECK_CUDA(cudaMalloc(&ctx->d_counters, SPB_NUM_COUNTERS * sizeof(unsigned int)));

@@ -191,3 +191,37 @@ def test_i8_kernel_is_deterministic_under_load(spb):
             first = ll.clone()
         else:
             assert torch.equal(first, ll), "launch %d differs" % rep
+
+
+def test_moments_syrk_on_int8_tensor_cores_matches_fp64_syrk(spb, golden):
+    """contrast.py:21-33 (+ size.py:116-125 for the dr prior): cov_ylm from the INT8-tensor-core SYRK
+    (csrc/syrk_i8.cu, the default) against the FP64 (DMMA) SYRK -- elementwise to 1e-13 of the largest entry,
+    exactly symmetric -- and the log-likelihood of the bench draws against the reference golden at 1e-8."""
+    import bench
+
+    hp, t, flux, _ = bench.synthetic_inputs(4096, 1234)
+    sw = golden("bench_sweep_seed1234.npz")
+    ns = len(sw["r"])
+    ctx = spb.get_context()
+    cov, ll, covd = {}, {}, {}
+    try:
+        for on in (0, 1):
+            ctx.set_option("moments_syrk_i8", on)
+            gp = spb.StarryProcess(marginalize_over_inclination=True, normalized=True,
+                                   **{k: hp[k][:ns] for k in hp})
+            cov[on] = gp.cov_ylm.cpu().numpy()
+            ll[on] = gp.log_likelihood(t, flux, 1e-6, i=60.0, p=1.0, u=U_LD).cpu().numpy()
+            gd = spb.StarryProcess(r=hp["r"][:32], dr=np.full(32, 4.0), mu=hp["mu"][:32], sigma=hp["sigma"][:32],
+                                   c=hp["c"][:32], n=hp["n"][:32])
+            covd[on] = gd.cov_ylm.cpu().numpy()
+    finally:
+        ctx.set_option("moments_syrk_i8", 1)
+    for a in (cov, covd):
+        scale = np.abs(a[0]).max(axis=(1, 2), keepdims=True)
+        assert float((np.abs(a[1] - a[0]) / scale).max()) < 1e-13
+        assert np.array_equal(a[1], np.swapaxes(a[1], 1, 2))
+    ref = sw["lnlike_m1_n1"]
+    fin = np.isfinite(ref)
+    assert np.array_equal(np.isneginf(ll[1]), np.isneginf(ref))
+    assert np.max(np.abs(ll[1][fin] - ref[fin]) / np.abs(ref[fin])) <= 1e-8
+    assert np.max(np.abs(ll[1][fin] - ll[0][fin]) / np.abs(ll[0][fin])) <= 1e-10
