@@ -62,7 +62,8 @@ __global__ void __launch_bounds__(256) slice_rows_kernel(SyrkParams p) {
   const int KQ = 31 * rk4 / 4;                       // quads of packed entries (rk4 % 4 == 0)
   const int KPQ = sy_chunks(p.rkeep[b]) * (SY_KCH / 4);   // quads incl. the zero padding
   const double *xr = p.X + ((size_t)b * 256 + row) * 992;
-  double v[8][4];
+  // pass 1: the largest entry of the row (the row is read again in pass 2, from L1 / L2: 5 KB per warp --
+  // keeping it in registers instead costs 64 registers and half the occupancy of a bandwidth-bound kernel)
   double mx = 0.0;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
@@ -70,10 +71,7 @@ __global__ void __launch_bounds__(256) slice_rows_kernel(SyrkParams p) {
     if (q < KQ) {
       const int kk = 4 * q, e2 = kk / rk4, e = kk - e2 * rk4;
       const double4 t = *reinterpret_cast<const double4 *>(xr + e2 * 32 + e);
-      v[j][0] = t.x; v[j][1] = t.y; v[j][2] = t.z; v[j][3] = t.w;
       mx = fmax(mx, fmax(fmax(fabs(t.x), fabs(t.y)), fmax(fabs(t.z), fabs(t.w))));
-    } else {
-      v[j][0] = v[j][1] = v[j][2] = v[j][3] = 0.0;
     }
   }
 #pragma unroll
@@ -94,12 +92,18 @@ __global__ void __launch_bounds__(256) slice_rows_kernel(SyrkParams p) {
   for (int j = 0; j < 8; ++j) {
     const int q = lane + 32 * j;
     if (q >= KPQ) continue;
+    double v4[4] = {0.0, 0.0, 0.0, 0.0};
+    if (q < KQ) {
+      const int kk = 4 * q, e2 = kk / rk4, e = kk - e2 * rk4;
+      const double4 t = *reinterpret_cast<const double4 *>(xr + e2 * 32 + e);
+      v4[0] = t.x; v4[1] = t.y; v4[2] = t.z; v4[3] = t.w;
+    }
     uint32_t W[SY_S];
 #pragma unroll
     for (int s = 0; s < SY_S; ++s) W[s] = 0u;
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
-      const long long Xb = __double2ll_rn(v[j][c] * sinv) + BIAS;
+      const long long Xb = __double2ll_rn(v4[c] * sinv) + BIAS;
 #pragma unroll
       for (int jd = 0; jd < SY_S - 1; ++jd) W[SY_S - 1 - jd] |= ((uint32_t)(Xb >> (SY_RB * jd)) & 255u) << (8 * c);
       const int top = (int)(Xb >> (SY_RB * (SY_S - 1))) - 128;
