@@ -21,7 +21,7 @@
 namespace {
 
 constexpr int SY_S = 7, SY_D = 6, SY_RB = 8;   // 7 planes of 8-bit digits, plane pairs s + t <= 6
-constexpr int SY_KCH = 32, SY_TM = 128, SY_TN = 64, SY_STAGES = 3;
+constexpr int SY_KCH = 32, SY_TM = 128, SY_TN = 64, SY_STAGES = 5;
 constexpr int SY_LDQ = 1024;                   // bytes per plane row (31 x 32 = 992 entries at most)
 constexpr int SY_NCT = 256, SY_NTHREADS = 320;
 
