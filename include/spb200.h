@@ -226,6 +226,13 @@ typedef struct {
   int temporal_kind;         /* 0 none, 1 Matern-3/2, 2 squared exponential */
   const double *tau;         /* one value, or one per batch element (tau_stride 0 | 1) */
   long long tau_stride;
+  /* Hint for the marginal assembly: the time stamps are equally spaced, t_k = t_0 + k uniform_dt (to
+   * rounding).  The covariance then only depends on (i - j, number of period wraps between t_j and
+   * t_i), so the cubic interpolant is tabulated once per sample for the 2 nt possible arguments and the
+   * per-entry coefficient gathers disappear.  0 = general time stamps (the interpolant is evaluated per
+   * entry).  The caller vouches for the spacing (sp.py checks it); values agree with the general path to
+   * the rounding of |theta_i - theta_j| (1e-15 relative).                                          */
+  double uniform_dt;
 } spb_noise_model;
 
 size_t spb_assemble_workspace_bytes(const spb_context *ctx, int B, int nt);

@@ -24,6 +24,7 @@ class NoiseModel(_c.Structure):
         ("base_kind", _I), ("baseline_var", _P), ("base_stride", _LL),
         ("lower_only", _I), ("defer", _I),
         ("temporal_kind", _I), ("tau", _P), ("tau_stride", _LL),
+        ("uniform_dt", _D),
     ]
 
 

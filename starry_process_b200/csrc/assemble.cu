@@ -170,6 +170,82 @@ __global__ void __launch_bounds__(256) rowsum_sym_kernel(AsmParams p) {
   }
 }
 
+// ---- pass A'' : the same symmetric pass for EQUALLY SPACED time stamps (spb_noise_model.uniform_dt).
+// theta_i - theta_j = 2 pi ((t_i - t_j) / p - (floor(t_i / p) - floor(t_j / p))) = 2 pi (d dt / p - m) with
+// d = i - j and m one of floor(d dt / p), floor(d dt / p) + 1: the interpolant is tabulated once per CTA
+// for the 2 nt possible arguments (G[0][d], G[1][d]) and an entry costs two conflict-free shared-memory
+// loads (the wrap count of column j and the table value) instead of the phase load and four coefficient
+// gathers of the general kernel, which is bound by exactly those (shared-memory LSU 77 %).  Entries whose
+// wrap count is neither of the two candidates (cannot happen in exact arithmetic) take the general formula.
+__global__ void __launch_bounds__(256) rowsum_sym_uniform_kernel(AsmParams p) {
+  extern __shared__ double sh[];  // coef (4*nc) | theta (nt) | part (8 x RS_CB) | G (2 nt) | wraps (nt ints)
+  const int b = blockIdx.y, c = blockIdx.x;
+  const int nc = p.covpts + 1;
+  double *cf = sh, *th = sh + 4 * nc, *part = th + p.nt, *G = part + 8 * RS_CB;
+  int *fl = reinterpret_cast<int *>(G + 2 * p.nt);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int k = tid; k < 4 * nc; k += 256) cf[k] = p.coef[(size_t)b * 4 * nc + k];
+  for (int k = tid; k < p.nt; k += 256) {
+    th[k] = phase_of(p.t[k], p.period);
+    fl[k] = (int)floor(p.t[k] / p.period);
+  }
+  __syncthreads();
+  const double dx = (double)p.covpts / (2.0 * 3.14159265358979323846);  // 1 / dx
+  const double dtp = p.nm.uniform_dt / p.period;
+  for (int d = tid; d < p.nt; d += 256) {
+    const double x = (double)d * dtp, m0 = floor(x);
+    G[d] = interp_cov(cf, nc, dx, 2.0 * 3.14159265358979323846 * (x - m0), 0.0);
+    G[p.nt + d] = interp_cov(cf, nc, dx, 2.0 * 3.14159265358979323846 * (m0 + 1.0 - x), 0.0);
+  }
+  __syncthreads();
+  double *rowq = p.rowq + (size_t)b * p.nt;
+  double *colp = p.colpart + ((size_t)b * RS_G + c) * p.nt;
+  for (int cb0 = 0; cb0 < p.nt; cb0 += RS_CB) {
+    double cs[32];
+#pragma unroll
+    for (int k = 0; k < 32; ++k) cs[k] = 0.0;
+    for (int i = c * 8 + warp; i < p.nt; i += RS_G * 8) {
+      if (i < cb0) continue;
+      const double thi = th[i];
+      const int fli = fl[i];
+      double *Krow = p.K + ((size_t)b * p.nt + i) * p.ldk;
+      double rs = 0.0;
+#pragma unroll
+      for (int k = 0; k < 32; ++k) {
+        const int j = cb0 + 32 * k + lane;
+        if (cb0 + 32 * k <= i) {        // warp-uniform
+          if (j < i) {
+            const int d = i - j;
+            const int w = (fli - fl[j]) - (int)((double)d * dtp);   // 0 or 1
+            double v;
+            if ((unsigned)w <= 1u) v = G[w * p.nt + d];
+            else v = interp_cov(cf, nc, dx, thi, th[j]);
+            rs += v;
+            cs[k] += v;
+            if (p.nm.defer) Krow[j] = v;
+          } else if (j == i) {
+            const double v = (p.nt == 1) ? p.var[b] : G[0];
+            rs += v;
+            if (p.nm.defer) Krow[j] = v;
+          }
+        }
+      }
+      rs = warp_sum(rs);
+      if (lane == 0) rowq[i] = (cb0 == 0) ? rs : rowq[i] + rs;
+    }
+#pragma unroll
+    for (int k = 0; k < 32; ++k) part[warp * RS_CB + 32 * k + lane] = cs[k];
+    __syncthreads();
+    for (int j = tid; j < RS_CB && cb0 + j < p.nt; j += 256) {
+      double t = 0.0;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) t += part[w * RS_CB + j];
+      colp[cb0 + j] = t;
+    }
+    __syncthreads();
+  }
+}
+
 // ---- pass S: per-sample scalars of the normalisation series ---------------------------------
 __global__ void __launch_bounds__(256) norm_scalars_kernel(AsmParams p) {
   __shared__ double red[8];
@@ -316,6 +392,8 @@ int run_assemble(spb_context *ctx, AsmParams &p, void *workspace, size_t workspa
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
       SPB_CHECK_CUDA(cudaFuncSetAttribute(rowsum_sym_kernel<true>,
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      SPB_CHECK_CUDA(cudaFuncSetAttribute(rowsum_sym_uniform_kernel,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
       return 0;
     });
     if (st) return st;
@@ -325,7 +403,10 @@ int run_assemble(spb_context *ctx, AsmParams &p, void *workspace, size_t workspa
       const size_t smS = smA + (size_t)8 * RS_CB * sizeof(double);
       SPB_REQUIRE(smS <= 200 * 1024, "assemble: nt too large for the shared-memory staging");
       dim3 gridS(RS_G, p.B);
+      const size_t smU = smS + (size_t)p.nt * (2 * sizeof(double) + sizeof(int)) + 16;
       if (p.nm.temporal_kind) rowsum_sym_kernel<true><<<gridS, 256, smS, stream>>>(p);
+      else if (p.nm.uniform_dt > 0.0 && p.nt > 1 && smU <= 200 * 1024)
+        rowsum_sym_uniform_kernel<<<gridS, 256, smU, stream>>>(p);
       else rowsum_sym_kernel<false><<<gridS, 256, smS, stream>>>(p);
     } else {
       dim3 gridA(min((p.nt + 7) / 8, 16), p.B);

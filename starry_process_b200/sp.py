@@ -522,6 +522,36 @@ class StarryProcess(object):
     def _t(self, t):
         return torch.as_tensor(t, dtype=torch.float64).to(self.device).reshape(-1).contiguous()
 
+    _udt_cache = None
+
+    def _uniform_dt(self, t):
+        """Spacing of equally spaced time stamps (``t_k = t_0 + k dt`` to 4e-12 of a step, e.g. any
+        ``linspace`` / fixed-cadence grid), else 0: the marginal assembly then tabulates the covariance
+        interpolant instead of evaluating it per entry (``spb_noise_model.uniform_dt``).  Host arrays are
+        checked with NumPy; device tensors once per (storage, length, version) with one reduction."""
+        if isinstance(t, torch.Tensor) and t.is_cuda:
+            key = (t.data_ptr(), t.numel(), t._version)
+            if self._udt_cache is not None and self._udt_cache[0] == key:
+                return self._udt_cache[1]
+            tt = t.detach().reshape(-1).to(torch.float64)
+            n = tt.numel()
+            if n < 3:
+                return 0.0
+            dt = (tt[-1] - tt[0]) / (n - 1)
+            dev_ = (tt - (tt[0] + dt * torch.arange(n, dtype=torch.float64, device=tt.device))).abs().max()
+            dt, dev_ = float(dt), float(dev_)
+            out = dt if (dt > 0.0 and dev_ <= 4e-12 * dt) else 0.0
+            self._udt_cache = (key, out)
+            return out
+        ta = np.asarray(t, dtype=np.float64).reshape(-1)
+        n = ta.size
+        if n < 3:
+            return 0.0
+        dt = (ta[-1] - ta[0]) / (n - 1)
+        if not dt > 0.0:
+            return 0.0
+        return float(dt) if np.max(np.abs(ta - (ta[0] + dt * np.arange(n)))) <= 4e-12 * dt else 0.0
+
     def _inc(self, i):
         if not (isinstance(i, torch.Tensor) and i.is_cuda):
             _check_bounds("i", np.asarray(i, dtype=np.float64) * np.pi / 180, 0, 0.5 * np.pi)
@@ -563,6 +593,7 @@ class StarryProcess(object):
         nm.data_stride = 0
         nm.base_stride = 0
         nm.temporal_kind = self._tkind
+        nm.uniform_dt = float(getattr(self, "_udt", 0.0) or 0.0)
         nm.tau = self._tau[b0:].data_ptr() if self._tkind else None
         nm.tau_stride = 1 if self._tkind else 0
         if data_cov is not None:
@@ -699,6 +730,7 @@ class StarryProcess(object):
         marg = self._marginalize_over_inclination if marginalize_over_inclination is None \
             else bool(marginalize_over_inclination)
         self._compute_moments()
+        self._udt = self._uniform_dt(t) if os.environ.get("SPB200_NO_UNIFORM_T") is None else 0.0
         t = self._t(t)
         inc = self._inc(i)
         if inc.numel() not in (1, self._B):

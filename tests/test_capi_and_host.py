@@ -268,3 +268,21 @@ def test_sass_int8_cholesky_uses_tcgen05_tmem_and_tma(built_lib):
     body = sass[beg:end if end > 0 else None]
     for mnemonic in ("UTCIMMA", "LDTM", "UTMALDG.4D", "UTCBAR"):
         assert mnemonic in body, mnemonic
+
+
+def test_uniform_time_stamp_detection():
+    """Host logic of spb_noise_model.uniform_dt: linspace / arange grids are recognised, anything else is not."""
+    from starry_process_b200.sp import StarryProcess
+
+    f = StarryProcess._uniform_dt
+    assert f(None, np.linspace(0, 4, 1000)) == pytest.approx(4 / 999, rel=1e-14)
+    assert f(None, 0.02 * np.arange(5000)) == pytest.approx(0.02, rel=1e-12)
+    # a large offset rounds the stamps themselves off the grid (ulp(1e5) = 7e-10 of a step): the reference
+    # sees those roundings, so this is NOT treated as uniform
+    assert f(None, 1e5 + 0.02 * np.arange(5000)) == 0.0
+    assert f(None, [0.0, 1.0]) == 0.0                                  # too short
+    assert f(None, np.sort(np.random.default_rng(0).uniform(0, 4, 100))) == 0.0
+    t = np.linspace(0, 4, 1000)
+    t[500] += 1e-9
+    assert f(None, t) == 0.0                                            # one displaced stamp
+    assert f(None, t[::-1]) == 0.0                                      # decreasing

@@ -225,3 +225,31 @@ def test_moments_syrk_on_int8_tensor_cores_matches_fp64_syrk(spb, golden):
     assert np.array_equal(np.isneginf(ll[1]), np.isneginf(ref))
     assert np.max(np.abs(ll[1][fin] - ref[fin]) / np.abs(ref[fin])) <= 1e-8
     assert np.max(np.abs(ll[1][fin] - ll[0][fin]) / np.abs(ll[0][fin])) <= 1e-10
+
+
+def test_uniform_time_stamps_fast_path_matches_general_assembly(spb, monkeypatch):
+    """flux.py:256-276 for equally spaced time stamps: the tabulated interpolant (spb_noise_model.uniform_dt,
+    rowsum_sym_uniform_kernel) against the per-entry evaluation -- several periods (0, few and many wraps per
+    light curve), a shifted grid, and an irregular grid, which must not take the fast path."""
+    import bench
+
+    hp, t, flux, _ = bench.synthetic_inputs(48, 1234)
+    rng = np.random.default_rng(1)
+    grids = [(1.0, t), (0.37, t), (3.3, t), (11.0, t), (1.0, np.linspace(-2.0, 7.5, 777)),
+             (1.0, np.sort(rng.uniform(0, 4, 500)))]
+    for period, tt in grids:
+        fl = np.interp(tt, t, flux)
+        out = {}
+        for on in (False, True):
+            if on:
+                monkeypatch.delenv("SPB200_NO_UNIFORM_T", raising=False)
+            else:
+                monkeypatch.setenv("SPB200_NO_UNIFORM_T", "1")
+            gp = spb.StarryProcess(**hp)
+            out[on] = (gp.log_likelihood(tt, fl, 1e-6, p=period, u=U_LD).cpu().numpy(), gp._udt)
+        uniform = bool(np.allclose(np.diff(tt), np.diff(tt)[0], rtol=1e-9, atol=0))
+        assert (out[True][1] > 0) == uniform and out[False][1] == 0.0
+        fin = np.isfinite(out[False][0])
+        assert np.array_equal(np.isfinite(out[True][0]), fin)
+        d = np.max(np.abs(out[True][0][fin] - out[False][0][fin]) / np.abs(out[False][0][fin]))
+        assert d <= (2e-10 if uniform else 0.0), (period, len(tt), d)
