@@ -178,11 +178,12 @@ __global__ void __launch_bounds__(256) rowsum_sym_kernel(AsmParams p) {
 // gathers of the general kernel, which is bound by exactly those (shared-memory LSU 77 %).  Entries whose
 // wrap count is neither of the two candidates (cannot happen in exact arithmetic) take the general formula.
 __global__ void __launch_bounds__(256) rowsum_sym_uniform_kernel(AsmParams p) {
-  extern __shared__ double sh[];  // coef (4*nc) | theta (nt) | part (8 x RS_CB) | G (2 nt) | wraps (nt ints)
+  extern __shared__ double sh[];  // coef (4*nc) | theta (nt) | part (8 x RS_CB) | G (2 nt) | wraps (nt ints) | m0 (nt ints)
   const int b = blockIdx.y, c = blockIdx.x;
   const int nc = p.covpts + 1;
   double *cf = sh, *th = sh + 4 * nc, *part = th + p.nt, *G = part + 8 * RS_CB;
   int *fl = reinterpret_cast<int *>(G + 2 * p.nt);
+  int *m0t = fl + p.nt;          // floor(d dt / p) per lag d
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   for (int k = tid; k < 4 * nc; k += 256) cf[k] = p.coef[(size_t)b * 4 * nc + k];
   for (int k = tid; k < p.nt; k += 256) {
@@ -196,6 +197,7 @@ __global__ void __launch_bounds__(256) rowsum_sym_uniform_kernel(AsmParams p) {
     const double x = (double)d * dtp, m0 = floor(x);
     G[d] = interp_cov(cf, nc, dx, 2.0 * 3.14159265358979323846 * (x - m0), 0.0);
     G[p.nt + d] = interp_cov(cf, nc, dx, 2.0 * 3.14159265358979323846 * (m0 + 1.0 - x), 0.0);
+    m0t[d] = (int)m0;
   }
   __syncthreads();
   double *rowq = p.rowq + (size_t)b * p.nt;
@@ -216,7 +218,7 @@ __global__ void __launch_bounds__(256) rowsum_sym_uniform_kernel(AsmParams p) {
         if (cb0 + 32 * k <= i) {        // warp-uniform
           if (j < i) {
             const int d = i - j;
-            const int w = (fli - fl[j]) - (int)((double)d * dtp);   // 0 or 1
+            const int w = (fli - fl[j]) - m0t[d];   // 0 or 1
             double v;
             if ((unsigned)w <= 1u) v = G[w * p.nt + d];
             else v = interp_cov(cf, nc, dx, thi, th[j]);
@@ -403,7 +405,7 @@ int run_assemble(spb_context *ctx, AsmParams &p, void *workspace, size_t workspa
       const size_t smS = smA + (size_t)8 * RS_CB * sizeof(double);
       SPB_REQUIRE(smS <= 200 * 1024, "assemble: nt too large for the shared-memory staging");
       dim3 gridS(RS_G, p.B);
-      const size_t smU = smS + (size_t)p.nt * (2 * sizeof(double) + sizeof(int)) + 16;
+      const size_t smU = smS + (size_t)p.nt * (2 * sizeof(double) + 2 * sizeof(int)) + 16;
       if (p.nm.temporal_kind) rowsum_sym_kernel<true><<<gridS, 256, smS, stream>>>(p);
       else if (p.nm.uniform_dt > 0.0 && p.nt > 1 && smU <= 200 * 1024)
         rowsum_sym_uniform_kernel<<<gridS, 256, smU, stream>>>(p);
