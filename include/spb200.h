@@ -357,9 +357,11 @@ int spb_dmma_peak(spb_context *ctx, int iters, double *tflops_host, double *ms_h
  *   "cholesky_cluster" 1 | 0   few matrices: one matrix per thread-block cluster | per CTA
  *   "cholesky_tile"    64 | 128  rows per CTA tile of the batched Cholesky (4 warps, 3 CTAs per SM |
  *                              8 warps, 2 CTAs per SM)
- *   "moments_syrk_i8"  1 | 0   second-moment SYRK of spb_ylm_moments* (contrast.py:21-33) on the INT8 tensor
- *                              cores (exact 7 x 8-bit digit planes, tcgen05 + TMEM; cov_ylm within 1e-15
- *                              of its maximum of the FP64 result) | on the FP64 (DMMA) tensor cores;
+ *   "moments_syrk_i8"  1 | 0   the FP64 GEMMs with an INT8-tensor-core form -- the second-moment SYRK of
+ *                              spb_ylm_moments* (contrast.py:21-33) and, for nt >= 1024, the product
+ *                              (A Sigma) A^T of spb_flux_conditional_lower (flux.py:335-343) -- on the INT8
+ *                              tensor cores (exact 7 x 8-bit digit planes, tcgen05 + TMEM; cov_ylm within
+ *                              1e-15 of its maximum of the FP64 result) | on the FP64 (DMMA) tensor cores;
  *                              environment default SPB_SYRK_I8                                     */
 int spb_set_option(spb_context *ctx, const char *name, int value);
 int spb_launch_count(const spb_context *ctx, long long *count_host);

@@ -63,6 +63,9 @@ int spb_encode_tmap_u8_4d(CUtensorMap *out, void *base, const unsigned long long
 
 // syrk_i8.cu: cov[b] = scale[b] (ldeg[b] o (X[b] X[b]^T) - vec[b] vec[b]^T) + diag on the INT8 tensor cores
 size_t spb_syrk_i8_workspace_bytes(int Bc);
+size_t spb_gemm_i8_lower_workspace_bytes(int Bc, int nt);
+int spb_gemm_i8_lower(spb_context *ctx, int Bc, int nt, const double *T, const double *A, long long A_stride,
+                      double *C, int ldc, void *workspace, cudaStream_t stream);
 int spb_syrk_i8(spb_context *ctx, int Bc, const double *X, const int *rkeep, const double *scale,
                 const double *vec, const double *diag, const double *ldeg, double *C, void *workspace,
                 cudaStream_t stream);

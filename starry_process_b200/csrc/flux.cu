@@ -233,6 +233,7 @@ __global__ void cond_mean_kernel(int B, const double *A, long long A_stride, con
 // (8 slices left 64 CTAs on 148 SMs: 0.72 ms against 0.22 ms for its share of a 4096 batch).
 constexpr int MARG_KSPLIT = 32;
 constexpr int COND_CHUNK = 512;
+constexpr int COND_I8_MIN_NT = 1024;   // lower-only K = T A^T on the INT8 tensor cores from this size
 
 }  // namespace
 
@@ -323,7 +324,8 @@ extern "C" int spb_flux_marginal(spb_context *ctx, int B, const double *mean_ylm
 extern "C" size_t spb_flux_conditional_workspace_bytes(const spb_context *ctx, int B, int nt) {
   (void)ctx;
   const int Bc = B < COND_CHUNK ? B : COND_CHUNK;
-  return (size_t)Bc * nt * 256 * 8 + 1024;
+  // T = A Sigma of one chunk, plus (long light curves) the digit planes of the INT8 product T A^T
+  return (size_t)Bc * nt * 256 * 8 + 1024 + (nt >= COND_I8_MIN_NT ? spb_gemm_i8_lower_workspace_bytes(Bc, nt) : 0);
 }
 
 static int flux_conditional_impl(spb_context *ctx, int B, int nt, const double *A, long long A_stride,
@@ -381,8 +383,15 @@ static int flux_conditional_impl(spb_context *ctx, int B, int nt, const double *
     d2.ksplit = 1;
     d2.lower_only = 1;
     d2.alpha = 1.0;
-    st = lower_only ? gnt::launch<gnt::EPI_STORE>(ctx, d2, stream)
-                    : gnt::launch<gnt::EPI_MIRROR>(ctx, d2, stream);
+    if (lower_only && nt >= COND_I8_MIN_NT && ctx->opt_syrk_i8) {
+      // long light curves: the 4.3 GFLOP (nt = 4096) product on the INT8 tensor cores (syrk_i8.cu)
+      void *wi8 = reinterpret_cast<unsigned char *>(workspace) +
+                  (((size_t)(B < COND_CHUNK ? B : COND_CHUNK) * nt * 256 * 8 + 1023) & ~(size_t)1023);
+      st = spb_gemm_i8_lower(ctx, Bc, nt, T, A + (size_t)b0 * A_stride, A_stride, d2.C, ldk, wi8, stream);
+    } else {
+      st = lower_only ? gnt::launch<gnt::EPI_STORE>(ctx, d2, stream)
+                      : gnt::launch<gnt::EPI_MIRROR>(ctx, d2, stream);
+    }
     if (st) return st;
   }
   return 0;

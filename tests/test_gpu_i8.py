@@ -253,3 +253,27 @@ def test_uniform_time_stamps_fast_path_matches_general_assembly(spb, monkeypatch
         assert np.array_equal(np.isfinite(out[True][0]), fin)
         d = np.max(np.abs(out[True][0][fin] - out[False][0][fin]) / np.abs(out[False][0][fin]))
         assert d <= (2e-10 if uniform else 0.0), (period, len(tt), d)
+
+
+def test_conditional_covariance_product_on_int8_tensor_cores(spb):
+    """flux.py:335-343 for a long light curve: K = (A Sigma) A^T of the conditional log-likelihood (lower
+    triangle, unnormalised process) evaluated on the INT8 tensor cores (gemm_i8_lower_kernel) against the
+    FP64 (DMMA) GEMM: same lnlike to rounding noise, shared and per-sample inclinations, a size that is not
+    a multiple of the tile."""
+    import bench
+
+    hp, t0, f0, _ = bench.synthetic_inputs(12, 1234)
+    ctx = spb.get_context()
+    for nt, inc in ((1500, 60.0), (1111, np.linspace(20.0, 80.0, 12))):
+        tt = np.linspace(0.0, 9.0, nt)
+        fl = np.interp(tt, t0 * 2.25, f0)
+        out = {}
+        try:
+            for on in (0, 1):
+                ctx.set_option("moments_syrk_i8", on)
+                gp = spb.StarryProcess(marginalize_over_inclination=False, normalized=False, **hp)
+                out[on] = gp.log_likelihood(tt, fl, 1e-6, i=inc, p=1.3, u=U_LD).cpu().numpy()
+        finally:
+            ctx.set_option("moments_syrk_i8", 1)
+        assert np.all(np.isfinite(out[0]))
+        assert np.max(np.abs(out[1] - out[0]) / np.abs(out[0])) < 1e-10, nt
