@@ -50,3 +50,15 @@ for code in (78, 87, 77):
 ctx.set_option("cholesky_i8", -1)
 torch.cuda.synchronize()
 print("done int8")
+# round 2: conditional flux covariance (A Sigma) A^T on the INT8 tensor cores (nt >= 1024, lower triangle) and
+# the tabulated marginal assembly of equally spaced time stamps (already taken by the linspace grids above)
+tl = np.linspace(0, 5, 1100)
+fl = 1e-3 * rng.standard_normal(1100)
+gc = spb.StarryProcess(r=[12.0, 20.0, 15.0], mu=[30.0, 50.0, 10.0], sigma=[5.0, 10.0, 20.0], c=[0.1, 0.05, 0.2],
+                       n=[10.0, 3.0, 5.0], marginalize_over_inclination=False, normalized=False)
+print("conditional nt=1100", gc.log_likelihood(tl, fl, 1e-6, i=[40.0, 60.0, 80.0], p=1.7, u=[0.4, 0.26]).cpu().numpy())
+print("conditional nt=1100, one inclination", gc.log_likelihood(tl, fl, 1e-6, i=60.0, p=1.7, u=[0.4, 0.26]).cpu().numpy())
+ti = np.sort(rng.uniform(0, 2, 301))
+print("irregular stamps", gp2.log_likelihood(ti, f, 1e-6, i=60.0).cpu().numpy())
+torch.cuda.synchronize()
+print("done conditional int8")
