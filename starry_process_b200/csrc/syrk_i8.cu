@@ -63,8 +63,10 @@ __global__ void __launch_bounds__(256) slice_rows_kernel(SyrkParams p) {
   const int KQ = 31 * rk4 / 4;                       // quads of packed entries (rk4 % 4 == 0)
   const int KPQ = sy_chunks(p.rkeep[b]) * (SY_KCH / 4);   // quads incl. the zero padding
   const double *xr = p.X + ((size_t)b * 256 + row) * 992;
-  // pass 1: the largest entry of the row (the row is read again in pass 2, from L1 / L2: 5 KB per warp --
-  // keeping it in registers instead costs 64 registers and half the occupancy of a bandwidth-bound kernel)
+  // pass 1: the largest entry of the row; the kept entries are parked in shared memory (8 KB per warp) so
+  // that pass 2 neither re-reads them from DRAM (ncu: the second read missed L2) nor holds them in 64 registers
+  extern __shared__ __align__(16) double sy_stage[];
+  double *stg = sy_stage + (size_t)(threadIdx.x >> 5) * 992;
   double mx = 0.0;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
@@ -72,6 +74,7 @@ __global__ void __launch_bounds__(256) slice_rows_kernel(SyrkParams p) {
     if (q < KQ) {
       const int kk = 4 * q, e2 = kk / rk4, e = kk - e2 * rk4;
       const double4 t = *reinterpret_cast<const double4 *>(xr + e2 * 32 + e);
+      *reinterpret_cast<double4 *>(stg + 4 * q) = t;
       mx = fmax(mx, fmax(fmax(fabs(t.x), fabs(t.y)), fmax(fabs(t.z), fabs(t.w))));
     }
   }
@@ -95,8 +98,7 @@ __global__ void __launch_bounds__(256) slice_rows_kernel(SyrkParams p) {
     if (q >= KPQ) continue;
     double v4[4] = {0.0, 0.0, 0.0, 0.0};
     if (q < KQ) {
-      const int kk = 4 * q, e2 = kk / rk4, e = kk - e2 * rk4;
-      const double4 t = *reinterpret_cast<const double4 *>(xr + e2 * 32 + e);
+      const double4 t = *reinterpret_cast<const double4 *>(stg + 4 * q);   // this lane's own copy
       v4[0] = t.x; v4[1] = t.y; v4[2] = t.z; v4[3] = t.w;
     }
     uint32_t W[SY_S];
@@ -561,12 +563,14 @@ int spb_syrk_i8(spb_context *ctx, int Bc, const double *X, const int *rkeep, con
     const int st = spb_once_per_device(attr_once, ctx->device, [&]() -> int {
       SPB_CHECK_CUDA(cudaFuncSetAttribute(syrk_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           (int)sizeof(SmemSy)));
+      SPB_CHECK_CUDA(cudaFuncSetAttribute(slice_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)(8 * 992 * sizeof(double))));
       return 0;
     });
     if (st) return st;
   }
   dim3 gs(32, Bc);
-  slice_rows_kernel<<<gs, 256, 0, stream>>>(p);
+  slice_rows_kernel<<<gs, 256, 8 * 992 * sizeof(double), stream>>>(p);
   SPB_LAUNCH_CHECK(ctx);
   const int grid = 6 * Bc < ctx->num_sms ? 6 * Bc : ctx->num_sms;
   syrk_i8_kernel<<<grid, SY_NTHREADS, sizeof(SmemSy), stream>>>(p, tmA, tmB);
