@@ -177,11 +177,12 @@ __global__ void __launch_bounds__(256) rowsum_sym_kernel(AsmParams p) {
 // loads (the wrap count of column j and the table value) instead of the phase load and four coefficient
 // gathers of the general kernel, which is bound by exactly those (shared-memory LSU 77 %).  Entries whose
 // wrap count is neither of the two candidates (cannot happen in exact arithmetic) take the general formula.
-__global__ void __launch_bounds__(256) rowsum_sym_uniform_kernel(AsmParams p) {
-  extern __shared__ double sh[];  // coef (4*nc) | theta (nt) | part (8 x RS_CB) | G (2 nt) | wraps (nt ints) | m0 (nt ints)
+constexpr int RSU_CB = 512;   // columns per register block of the uniform kernel (16 per lane: 3 CTAs per SM)
+__global__ void __launch_bounds__(256, 3) rowsum_sym_uniform_kernel(AsmParams p) {
+  extern __shared__ double sh[];  // coef (4*nc) | theta (nt) | part (8 x RSU_CB) | G (2 nt) | wraps (nt ints) | m0 (nt ints)
   const int b = blockIdx.y, c = blockIdx.x;
   const int nc = p.covpts + 1;
-  double *cf = sh, *th = sh + 4 * nc, *part = th + p.nt, *G = part + 8 * RS_CB;
+  double *cf = sh, *th = sh + 4 * nc, *part = th + p.nt, *G = part + 8 * RSU_CB;
   int *fl = reinterpret_cast<int *>(G + 2 * p.nt);
   int *m0t = fl + p.nt;          // floor(d dt / p) per lag d
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -202,10 +203,10 @@ __global__ void __launch_bounds__(256) rowsum_sym_uniform_kernel(AsmParams p) {
   __syncthreads();
   double *rowq = p.rowq + (size_t)b * p.nt;
   double *colp = p.colpart + ((size_t)b * RS_G + c) * p.nt;
-  for (int cb0 = 0; cb0 < p.nt; cb0 += RS_CB) {
-    double cs[32];
+  for (int cb0 = 0; cb0 < p.nt; cb0 += RSU_CB) {
+    double cs[RSU_CB / 32];
 #pragma unroll
-    for (int k = 0; k < 32; ++k) cs[k] = 0.0;
+    for (int k = 0; k < RSU_CB / 32; ++k) cs[k] = 0.0;
     for (int i = c * 8 + warp; i < p.nt; i += RS_G * 8) {
       if (i < cb0) continue;
       const double thi = th[i];
@@ -213,7 +214,7 @@ __global__ void __launch_bounds__(256) rowsum_sym_uniform_kernel(AsmParams p) {
       double *Krow = p.K + ((size_t)b * p.nt + i) * p.ldk;
       double rs = 0.0;
 #pragma unroll
-      for (int k = 0; k < 32; ++k) {
+      for (int k = 0; k < RSU_CB / 32; ++k) {
         const int j = cb0 + 32 * k + lane;
         if (cb0 + 32 * k <= i) {        // warp-uniform
           if (j < i) {
@@ -236,12 +237,12 @@ __global__ void __launch_bounds__(256) rowsum_sym_uniform_kernel(AsmParams p) {
       if (lane == 0) rowq[i] = (cb0 == 0) ? rs : rowq[i] + rs;
     }
 #pragma unroll
-    for (int k = 0; k < 32; ++k) part[warp * RS_CB + 32 * k + lane] = cs[k];
+    for (int k = 0; k < RSU_CB / 32; ++k) part[warp * RSU_CB + 32 * k + lane] = cs[k];
     __syncthreads();
-    for (int j = tid; j < RS_CB && cb0 + j < p.nt; j += 256) {
+    for (int j = tid; j < RSU_CB && cb0 + j < p.nt; j += 256) {
       double t = 0.0;
 #pragma unroll
-      for (int w = 0; w < 8; ++w) t += part[w * RS_CB + j];
+      for (int w = 0; w < 8; ++w) t += part[w * RSU_CB + j];
       colp[cb0 + j] = t;
     }
     __syncthreads();
@@ -405,7 +406,8 @@ int run_assemble(spb_context *ctx, AsmParams &p, void *workspace, size_t workspa
       const size_t smS = smA + (size_t)8 * RS_CB * sizeof(double);
       SPB_REQUIRE(smS <= 200 * 1024, "assemble: nt too large for the shared-memory staging");
       dim3 gridS(RS_G, p.B);
-      const size_t smU = smS + (size_t)p.nt * (2 * sizeof(double) + 2 * sizeof(int)) + 16;
+      const size_t smU = smA + (size_t)8 * RSU_CB * sizeof(double) +
+                         (size_t)p.nt * (2 * sizeof(double) + 2 * sizeof(int)) + 16;
       if (p.nm.temporal_kind) rowsum_sym_kernel<true><<<gridS, 256, smS, stream>>>(p);
       else if (p.nm.uniform_dt > 0.0 && p.nt > 1 && smU <= 200 * 1024)
         rowsum_sym_uniform_kernel<<<gridS, 256, smU, stream>>>(p);
