@@ -914,6 +914,13 @@ def run_b200(args):
         "warmup": warm, "ms_per_step": total_ms / args.steps,
         "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
+        "arithmetic": ("all inputs, outputs and intermediate results are fp64; the two largest GEMM-shaped pieces "
+                       "(panel updates of the Cholesky factorisation: code %d; second-moment SYRK of the Ylm moments: "
+                       "%s) are evaluated on the INT8 tensor cores as EXACT integer products of 7 planes of 8-bit "
+                       "digits (55 bits per row, error-free accumulation in TMEM) -- agreement with the FP64 "
+                       "tensor-core kernels at rounding-noise level (phases.int8_cholesky_nt1000), parity with the "
+                       "reference unchanged; SPB200_CHOLESKY_I8=0 SPB_SYRK_I8=0 select the FP64 (DMMA) kernels"
+                       % (i8_code, "on" if os.environ.get("SPB_SYRK_I8", "1") != "0" else "off")),
         "config": config_dict(args),
         "e2e": {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps},
