@@ -106,12 +106,12 @@ __global__ void __launch_bounds__(256) rowsum_kernel(AsmParams p) {
 // column sums in registers; the 8 warps are combined through shared memory in a fixed order and
 // each of the RS_G CTAs of a sample leaves one partial vector that pass S adds up.
 constexpr int RS_G = 8;      // CTAs per sample
-constexpr int RS_CB = 1024;  // columns per register block (32 per lane)
+constexpr int RS_CB = 512;   // columns per register block (16 per lane: 3 CTAs per SM)
 
 // TEMPORAL is a compile-time switch: the time-variable branch must not cost the static path (the
 // bench workload) registers or predicated instructions in its inner loop.
 template <bool TEMPORAL>
-__global__ void __launch_bounds__(256) rowsum_sym_kernel(AsmParams p) {
+__global__ void __launch_bounds__(256, 3) rowsum_sym_kernel(AsmParams p) {
   extern __shared__ double sh[];  // coef (4*nc) | theta (nt) | part (8 x RS_CB) | t (nt, optional)
   const int b = blockIdx.y, c = blockIdx.x;
   const int nc = p.covpts + 1;
@@ -128,9 +128,9 @@ __global__ void __launch_bounds__(256) rowsum_sym_kernel(AsmParams p) {
   double *rowq = p.rowq + (size_t)b * p.nt;
   double *colp = p.colpart + ((size_t)b * RS_G + c) * p.nt;
   for (int cb0 = 0; cb0 < p.nt; cb0 += RS_CB) {
-    double cs[32];
+    double cs[RS_CB / 32];
 #pragma unroll
-    for (int k = 0; k < 32; ++k) cs[k] = 0.0;
+    for (int k = 0; k < RS_CB / 32; ++k) cs[k] = 0.0;
     for (int i = c * 8 + warp; i < p.nt; i += RS_G * 8) {
       if (i < cb0) continue;
       const double thi = th[i];
@@ -138,7 +138,7 @@ __global__ void __launch_bounds__(256) rowsum_sym_kernel(AsmParams p) {
       double *Krow = p.K + ((size_t)b * p.nt + i) * p.ldk;
       double rs = 0.0;
 #pragma unroll
-      for (int k = 0; k < 32; ++k) {
+      for (int k = 0; k < RS_CB / 32; ++k) {
         const int j = cb0 + 32 * k + lane;
         if (cb0 + 32 * k <= i) {        // warp-uniform
           if (j < i) {
@@ -158,7 +158,7 @@ __global__ void __launch_bounds__(256) rowsum_sym_kernel(AsmParams p) {
       if (lane == 0) rowq[i] = (cb0 == 0) ? rs : rowq[i] + rs;
     }
 #pragma unroll
-    for (int k = 0; k < 32; ++k) part[warp * RS_CB + 32 * k + lane] = cs[k];
+    for (int k = 0; k < RS_CB / 32; ++k) part[warp * RS_CB + 32 * k + lane] = cs[k];
     __syncthreads();
     for (int j = tid; j < RS_CB && cb0 + j < p.nt; j += 256) {
       double t = 0.0;
